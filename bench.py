@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""bench.py -- time-to-tolerance and space-time DOF/s of the MGRIT hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg5|cfg2]
+
+Workload (BASELINE.json configs[4], the one the metric's target is quoted on; fits one GPU):
+    heat_1d backward Euler, nx = 1025 (1023 dofs), nt = 2^20 + 1 on t in [0, 2], FCF-relaxation V-cycles,
+    coarsening 4, nested iteration, tol 1e-10; strong scaling over the time ranks (one process per GPU).
+One "step" = one complete solve: setup (incl. nested iteration) + MGRIT iterations until conv < 1e-10.
+Prints ONE JSON line (rank 0).  `value` times the solve with every table already in HBM; `e2e` times the public API
+from host NumPy inputs (application objects, Mgrit(), solve(), result copied back to the host).
+`--impl reference` times the reference's CPU algorithm (the oracle port: per-point Python loop + SciPy SuperLU, exactly
+what pymgrit does) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import logging
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = 'MGRIT space-time DOF/s (heat_1d nx=1025, solve to 1e-10)'
+UNIT = 'DOF/s'
+
+
+def rhs(x, t):
+    return -np.sin(np.pi * x) * (np.sin(t) - np.pi ** 2 * np.cos(t))
+
+
+def init_cond(x):
+    return np.sin(np.pi * x)
+
+
+WORKLOADS = {
+    # name: (nt, levels, coarsening)
+    'cfg5': (2 ** 20 + 1, 8, 4),
+    'cfg2': (16385, 3, 4),
+}
+HEAT_KW = dict(x_start=0, x_end=1, nx=1025, a=1, init_cond=init_cond, rhs=rhs, t_start=0, t_stop=2)
+SOLVER_KW = dict(cf_iter=1, cycle_type='V', nested_iteration=True, tol=1e-10)
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get('hbm_gbs', 6650.0), 'measured'
+    return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(nt_sample, levels, coarsening, solver='spsolve'):
+    """Full MGRIT solve of the same problem at reduced nt on one host core; returns (DOF/s, seconds, iterations)."""
+    from oracle import mgrit_oracle as O
+    t0 = time.time()
+    prob = O.simple_hierarchy(O.Heat1DOracle(solver=solver, nt=nt_sample, **HEAT_KW), levels, coarsening)
+    mg = O.MgritOracle(prob, **SOLVER_KW)
+    info = mg.solve()
+    sec = time.time() - t0
+    return 1023 * nt_sample / sec, sec, len(info['conv'])
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    nt, levels, m = WORKLOADS[args.workload]
+    nt_s, lv_s = 1025, 3                      # ~10 s of reference-style CPU work per step
+    times, its = [], 0
+    for k in range(args.warmup + args.steps):
+        dofs, sec, its = cpu_sample(nt_s, lv_s, m)
+        if k >= args.warmup:
+            times.append(sec)
+    sec = float(np.mean(times))
+    val = 1023 * nt_s / sec
+    sample = (f'heat_1d nx=1025 nt={nt_s} {lv_s}-level m={m} FCF V-cycle to 1e-10 ({its} iterations), SciPy SuperLU per step '
+              f'as in the reference; DOF/s is linear in nt')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'{args.workload}: heat_1d nx=1025 nt={nt} {levels}-level m={m} FCF V-cycle tol 1e-10',
+                       'sample': sample},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import pymgrit_b200 as P
+    from pymgrit_b200 import _lib
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    nt, levels, m = WORKLOADS[args.workload]
+    if args.levels:
+        levels = args.levels
+    ndof = 1023
+
+    def make_problem():
+        return P.simple_setup_problem(P.Heat1D(nt=nt, **HEAT_KW), level=levels, coarsening=m)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident timing: tables in HBM, time setup sweeps (nested iteration) + iterations ----
+    solver = P.Mgrit(problem=make_problem(), logging_lvl=logging.WARNING, **SOLVER_KW)
+    info = None
+    for _ in range(args.warmup):
+        solver.restart()
+        info = solver.solve()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = solver.launches
+    ev0.record()
+    for _ in range(args.steps):
+        solver.restart()
+        info = solver.solve()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    launches = (solver.launches - launches0)
+    iters = len(info['conv'])
+    value = ndof * nt / (ms_step * 1e-3)
+
+    # ---- end to end through the public API from host inputs, result back on the host ----
+    e2e_ms = []
+    h2d = d2h = 0
+    for k in range(max(1, min(args.steps, 3)) + 1):
+        barrier()
+        t0 = time.perf_counter()
+        s2 = P.Mgrit(problem=make_problem(), logging_lvl=logging.WARNING, **SOLVER_KW)
+        inf2 = s2.solve()
+        last = s2.u[0][-1].get_values()             # solution at the final time (device -> host)
+        conv_host = np.array(inf2['conv'])
+        torch.cuda.synchronize()
+        dt_ms = (time.perf_counter() - t0) * 1e3
+        if k > 0:
+            e2e_ms.append(max_over_ranks(dt_ms))
+        h2d = s2.h2d_bytes
+        d2h = last.nbytes + 8 * len(conv_host)
+        del s2
+    e2e_ms = float(np.mean(e2e_ms))
+
+    # ---- per-kernel roofline on level 0 (CUDA events around single launches on the solved state) ----
+    kernels = solver.time_level0_sweeps(repeats=5)
+    hbm, which = peaks()
+    dom = max(kernels, key=lambda k: k['share_ms'])
+    roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
+                'frac': dom['gbs'] / hbm, 'traffic': None, 'peak_source': which}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            dofs, sec, its = cpu_sample(1025, 3, m)
+            cpu = {'value': dofs, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                   'sample': f'heat_1d nx=1025 nt=1025 3-level m={m} FCF V-cycle to 1e-10 ({its} iterations, {sec:.1f} s), '
+                             f'SciPy SuperLU per step as in the reference; DOF/s is linear in nt'}
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic',
+                'config': {'workload': f'{args.workload}: heat_1d nx=1025 nt={nt} {levels}-level m={m} FCF V-cycle nested '
+                                       f'iteration tol 1e-10', 'iterations': iters, 'conv': [float(c) for c in info['conv']],
+                           'l2': 'working set (level 0: %.1f GB) is far larger than L2' % (ndof * nt * 8 / 1e9),
+                           'parallelism': f'time-slab x{world}'},
+                'time_to_tolerance_s': ms_step * 1e-3, 'clocks': clocks, 'gpu_launches': launches // args.steps,
+                'e2e': {'value': ndof * nt / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
+                        'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+                'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--workload', default='cfg5', choices=sorted(WORKLOADS))
+    ap.add_argument('--levels', type=int, default=0)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

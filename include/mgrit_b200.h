@@ -1,0 +1,166 @@
+/*
+ * mgrit_b200.h -- C ABI of libmgrit_b200.so: the batched MGRIT sweeps of the pymgrit hot path as
+ * hand-written sm_100a CUDA kernels.
+ *
+ * The reference (pymgrit v1.0.6, /root/reference) is pure Python: the interface this library sits
+ * behind is not an FFI but the Python plugin API  Application.step / Vector / Mgrit  (SURVEY.md 8b).
+ * Every entry point below replaces one Python loop of src/pymgrit/core/mgrit.py that calls
+ * Application.step once per time point; the citation on each declaration names that loop.  The
+ * Python host package pymgrit_b200 binds these symbols with ctypes (pymgrit_b200/_lib.py); the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; all pointers named *_dev are CUDA device pointers owned by the caller
+ *     (the Python host allocates them as torch tensors), everything else is host memory;
+ *   - every level of the time-grid hierarchy is one row-major array u[npts][pitch] of doubles, one
+ *     row per time point (row = the reference's Vector.get_values()), pitch >= n, pitch even, so
+ *     that rows are 16-byte aligned for bulk (TMA) copies;  g has the same shape (FAS right-hand
+ *     side, levels > 0 only).  The FAS copy v of the reference (mgrit.py:520) is never stored: with
+ *     injection it is bit-identical to the fine level's C-point rows while it is live;
+ *   - point 0 of a level is never written by a sweep: it is the initial condition on time rank 0
+ *     and the ghost row received from the previous rank otherwise (mgrit.py:781-790);
+ *   - cpts_dev lists the C-points of the level in ascending order and always starts with 0;
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*); no allocation,
+ *     no synchronisation, no host<->device copy happens inside a sweep;
+ *   - return value 0 = ok, otherwise an MGB_E* code; mgb_last_error() gives the message.  Nothing
+ *     throws across the ABI.  There is no CPU fallback: without a CUDA device every launch fails.
+ */
+#ifndef MGRIT_B200_H
+#define MGRIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_ABI_VERSION 1
+
+/* application kinds (which Phi) */
+#define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
+#define MGB_APP_ADVECTION1D 2 /* advection/advection_1d.py:129-143   implicit upwind, cyclic bidiagonal     */
+#define MGB_APP_DAHLQUIST 3   /* dahlquist/dahlquist.py:88-111       scalar BE / FE / TR / MR                */
+#define MGB_APP_BRUSSELATOR 4 /* brusselator/brusselator.py:105-132  classical RK4 on 2 components           */
+#define MGB_APP_HEAT2D 5      /* heat/heat_2d.py:322-366 (BE branch) 5-point Laplacian, Dirichlet data      */
+
+/* error codes */
+#define MGB_OK 0
+#define MGB_EINVAL 1     /* bad argument                                     */
+#define MGB_ENOSHAPE 2   /* no kernel instantiation for this problem size    */
+#define MGB_ECUDA 3      /* CUDA runtime error (launch failed, no device...) */
+
+/* temporal norm of the convergence criterion (mgrit.py:182) */
+#define MGB_TNORM_ONE 1
+#define MGB_TNORM_TWO 2
+#define MGB_TNORM_INF 3
+
+/* Dahlquist methods (dahlquist.py:98-110) */
+#define MGB_DAHLQUIST_BE 0
+#define MGB_DAHLQUIST_FE 1
+#define MGB_DAHLQUIST_TR 2
+#define MGB_DAHLQUIST_MR 3
+
+/*
+ * One level of the hierarchy as seen by one time rank.  Mirrors the per-level state the reference
+ * keeps in Mgrit.u/g/t/index_local_c (mgrit.py:150-172, 840-858) plus what its Application object
+ * holds for Phi (heat_1d.py:149-175 etc.).
+ */
+typedef struct mgb_level {
+    int32_t app;            /* MGB_APP_*                                                          */
+    int32_t n;              /* spatial dofs per time point                                        */
+    int32_t pitch;          /* row pitch in doubles                                               */
+    int32_t npts;           /* time points held (incl. point 0 = initial condition / ghost)       */
+    double *u_dev;          /* [npts][pitch] solution                                             */
+    double *g_dev;          /* [npts][pitch] FAS right-hand side, NULL on level 0                 */
+    const int32_t *cpts_dev;/* [ncpts] C-point indices, ascending, cpts[0] == 0; NULL on coarsest */
+    int32_t ncpts;
+    int32_t team_threads;   /* kernel shape for this n: threads per system ...                    */
+    int32_t chunk;          /* ... and contiguous elements per thread (mgb_team_shape)            */
+
+    /* Phi data.  The step that produces point i uses dt_i = t[i] - t[i-1]. */
+    int32_t ndt;            /* distinct dt values on this level (1 for a uniform grid)            */
+    int32_t cw;             /* doubles per row of the step-constant table (mgb_step_consts_width) */
+    const int32_t *dtidx_dev; /* [npts] row of sconst for the step into point i; NULL if ndt == 1 */
+    const double *sconst_dev; /* [ndt][cw] per-dt constants of Phi (mgb_*_step_consts)            */
+
+    /* right-hand side of the PDE, b(x, t_i) * dt_i = sum_k rhs_t[i][k] * rhs_x[k][x]  (heat only) */
+    int32_t nrhs;           /* number of separable terms; 0 = homogeneous                         */
+    int32_t reserved0;
+    const double *rhs_x_dev;/* [nrhs][chunk][team_threads]: spatial factors, thread-transposed    */
+    const double *rhs_t_dev;/* [npts][nrhs]: time factors already multiplied by dt_i              */
+    const double *rhs_dense_dev; /* [npts][pitch] b(x,t_i)*dt_i for non-separable data, or NULL   */
+
+    const double *t_dev;    /* [npts] time values of the level's points (needed by the ODE apps)  */
+    double p[8];            /* application scalars (dahlquist: p[0] = lambda)                     */
+    int32_t ip[4];          /* application integers (dahlquist: ip[0] = method)                   */
+} mgb_level;
+
+int mgb_abi_version(void);
+const char *mgb_last_error(void);
+
+/* Shape of the kernel instantiation used for n dofs: threads per system and elements per thread.
+ * Returns MGB_ENOSHAPE if n is larger than the largest compiled shape. */
+int mgb_team_shape(int32_t app, int32_t n, int32_t *team_threads, int32_t *chunk);
+
+/* Width (doubles) of one row of the step-constant table for a shape. */
+int mgb_step_consts_width(int32_t app, int32_t team_threads, int32_t chunk);
+
+/* Host helpers: fill one row of the step-constant table.
+ *   heat1d:      r  = dt * a / dx^2   (heat_1d.py:185, 213)
+ *   advection1d: nu = dt * c / dx     (advection_1d.py:108, 140) */
+int mgb_heat1d_step_consts(double r, int32_t n, int32_t team_threads, int32_t chunk, double *out);
+int mgb_advection1d_step_consts(double nu, int32_t n, int32_t team_threads, int32_t chunk, double *out);
+
+/* ---- sweeps (one launch covers every coarse interval of the level) -------------------------- */
+
+/* F-relaxation, mgrit.py:292-333: for every C-point c and every F-point i that follows it,
+ * u[i] = (g[i] +) Phi(u[i-1]). */
+int mgb_f_relax(const mgb_level *lvl, void *stream);
+
+/* C-relaxation, mgrit.py:335-370: for every C-point c != 0,
+ * u[c] = w * ((g[c] +) Phi(u[c-1])) + (1 - w) * u[c]. */
+int mgb_c_relax(const mgb_level *lvl, double weight, void *stream);
+
+/* FAS restriction, mgrit.py:488-549 with GridTransferCopy (grid_transfer_copy.py:25-47): for every
+ * C-point j, coarse.u[j] = fine.u[c_j]; for j >= 1
+ *   coarse.g[j] = (Phi_f(fine.u[c_j - 1]) - fine.u[c_j] (+ fine.g[c_j])) + fine.u[c_j]
+ *                 - Phi_c(fine.u[c_{j-1}]). */
+int mgb_fas_residual(const mgb_level *fine, const mgb_level *coarse, void *stream);
+
+/* Coarse-grid correction, mgrit.py:715-726: fine.u[c_j] += coarse.u[j] - v[j], j >= 1, followed, if
+ * f_relax != 0, by the F-relaxation of mgrit.py:287 out of the same registers. */
+int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t f_relax, void *stream);
+
+/* Sequential solve on the coarsest level, mgrit.py:459-486: u[i] = (g[i] +) Phi(u[i-1]), i = 1..npts-1. */
+int mgb_forward_solve(const mgb_level *lvl, void *stream);
+
+/* Space-time residual at the C-points of level 0, mgrit.py:387-413: out_sq_dev[j] = ||Phi(u[c_j-1]) -
+ * u[c_j]||_2^2 for j >= 1 (out_sq_dev[0] = 0). */
+int mgb_residual_norms(const mgb_level *lvl, double *out_sq_dev, void *stream);
+
+/* Jump criterion, mgrit.py:372-385: out_sq_dev[j] = ||u[c_j] - last[c_j]||_2^2 for j >= 1, then
+ * last <- u for every point. */
+int mgb_jump_norms(const mgb_level *lvl, double *last_dev, double *out_sq_dev, void *stream);
+
+/* Temporal norm of mgrit.py:430-431 over sq_dev[0..count): writes the rank-local partial
+ * (TWO: sum of squares, ONE: sum of roots, INF: max of roots) to out_dev[0]. */
+int mgb_temporal_norm(const double *sq_dev, int32_t count, int32_t t_norm, double *out_dev, void *stream);
+
+/* Nested iteration, mgrit.py:559-563: fine.u[c_j] = coarse.u[j] for j >= 1. */
+int mgb_inject_up(const mgb_level *fine, const mgb_level *coarse, void *stream);
+
+/* One application of Phi for Application.step (heat_1d.py:198 etc.): out = Phi(in) for the step that
+ * produces point `point` of the level (its dt and right-hand side). */
+int mgb_step(const mgb_level *lvl, int32_t point, const double *in_dev, double *out_dev, void *stream);
+
+/* ---- Vector arithmetic (core/vector.py:38-110) ---------------------------------------------- */
+/* out = a*x + b*y on n doubles */
+int mgb_vec_axpby(int32_t n, double a, const double *x_dev, double b, const double *y_dev, double *out_dev,
+                  void *stream);
+/* out_dev[0] = sum of squares of x (Vector.norm = sqrt of it, heat_1d.py:62-68) */
+int mgb_vec_sumsq(int32_t n, const double *x_dev, double *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGRIT_B200_H */

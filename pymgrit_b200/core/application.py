@@ -1,0 +1,90 @@
+"""Application API of the reference (core/application.py:17-107), plus the device-side contract.
+
+`Application` is the abstract plugin class, unchanged: time grid from (t_start, t_stop, nt) or
+t_interval, required attributes vector_template / vector_t_start, abstract step().
+`DeviceApplication` adds what the batched engine needs: which Phi kernel family the application
+maps to and the per-level tables of that kernel (built on the host, uploaded once per level).
+"""
+from abc import ABCMeta, abstractmethod
+
+import numpy as np
+
+from pymgrit_b200.core.vector import Vector
+
+
+class MetaApplication(ABCMeta):
+    """Checks that the required attributes exist after construction (core/application.py:17-29)."""
+    required_attributes = []
+
+    def __call__(cls, *args, **kwargs):
+        obj = super().__call__(*args, **kwargs)
+        for name in obj.required_attributes:
+            if not hasattr(obj, name):
+                raise ValueError('required attribute (%s) not set' % name)
+        return obj
+
+
+class Application(object, metaclass=MetaApplication):
+    required_attributes = ['vector_template', 'vector_t_start']
+
+    def __init__(self, t_start: float = None, t_stop: float = None, nt: int = None,
+                 t_interval: np.ndarray = None) -> None:
+        if t_interval is None:
+            if t_start is None or t_stop is None or nt is None:
+                raise Exception('Specify an interval by t_start, t_stop and nt or by t_interval')
+            self.t_start = t_start
+            self.t_end = t_stop
+            self.nt = nt
+            self.t = np.linspace(self.t_start, self.t_end, nt)
+        else:
+            if not isinstance(t_interval, np.ndarray):
+                raise Exception('t_interval has the wrong type. Should be a numpy array')
+            self.t_start = t_interval[0]
+            self.t_end = t_interval[-1]
+            self.nt = len(t_interval)
+            self.t = t_interval
+
+    @property
+    def vector_template(self) -> Vector:
+        return self._vector_template
+
+    @vector_template.setter
+    def vector_template(self, value: Vector) -> None:
+        self._vector_template = value
+
+    @property
+    def vector_t_start(self) -> Vector:
+        return self._vector_t_start
+
+    @vector_t_start.setter
+    def vector_t_start(self, value: Vector) -> None:
+        self._vector_t_start = value
+
+    @abstractmethod
+    def step(self, u_start: Vector, t_start: float, t_stop: float) -> Vector:
+        """Time integration from t_start to t_stop."""
+
+
+class DeviceApplication(Application):
+    """An application whose Phi exists as a kernel family of libmgrit_b200.
+
+    Subclasses set
+      kind          MGB_APP_* constant
+      ndof          spatial unknowns per time point
+    and implement level_tables(t), the host arrays of struct mgb_level for a time grid t.
+    step() is provided here: one launch of mgb_step on a two-point level.
+    """
+    kind = 0
+    ndof = 0
+
+    def level_tables(self, t: np.ndarray, team_threads: int, chunk: int) -> dict:
+        raise NotImplementedError
+
+    def step(self, u_start, t_start: float, t_stop: float):
+        from pymgrit_b200.core.device_level import single_step
+        return single_step(self, u_start, t_start, t_stop)
+
+    def __getstate__(self):          # simple_setup_problem deep-copies applications
+        state = dict(self.__dict__)
+        state.pop('_step_cache', None)
+        return state

@@ -1,0 +1,116 @@
+"""Time communicator: the few collective operations the batched engine needs, over torch.distributed.
+
+The reference exchanges pickled vectors with mpi4py isend/recv and eight message kinds (core/mgrit.py:693-713).  With the
+aligned slab partition (core/partition.py) three exchanges remain:
+  exchange_ghost  my last row of a level -> ghost row (point 0) of the next rank     (reference kinds 0 and 4)
+  chain           coarsest-level forward solve: receive ghost, solve, send last row   (reference kind 5)
+  reduce_norm     one double per rank, SUM (1-/2-norm) or MAX (inf-norm)              (gather + bcast, mgrit.py:428-432)
+One process drives one GPU; rows move GPU to GPU through NCCL P2P (NVLink) without touching the host.  `SerialComm` is the
+single-rank case (no torch.distributed needed).  The same class runs over gloo with CPU tensors (tests).
+"""
+
+
+class SerialComm:
+    def Get_rank(self):
+        return 0
+
+    def Get_size(self):
+        return 1
+
+    def barrier(self):
+        return None
+
+    def allgather(self, value):
+        return [value]
+
+    # engine hooks -----------------------------------------------------------------------------
+    def exchange_ghost(self, solver, lvl):
+        return None
+
+    def recv_chain(self, solver, lvl):
+        return None
+
+    def send_chain(self, solver, lvl):
+        return None
+
+    def reduce_norm(self, partial, t_norm):
+        return partial
+
+
+class TorchDistComm:
+    """torch.distributed process group as the time communicator (NCCL on GPUs, gloo in CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+
+    def Get_rank(self):
+        return self.rank
+
+    def Get_size(self):
+        return self.size
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+    def allgather(self, value):
+        out = [None] * self.size
+        self.dist.all_gather_object(out, value, group=self.group)
+        return out
+
+    def _global(self, r):
+        return self.dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def shift_rows(self, send_row, recv_row):
+        """send_row -> next rank, previous rank -> recv_row (either may be None at the ends)."""
+        ops = []
+        if send_row is not None and self.rank + 1 < self.size:
+            ops.append(self.dist.P2POp(self.dist.isend, send_row, self._global(self.rank + 1), group=self.group))
+        if recv_row is not None and self.rank > 0:
+            ops.append(self.dist.P2POp(self.dist.irecv, recv_row, self._global(self.rank - 1), group=self.group))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def exchange_ghost(self, solver, lvl):
+        lv = solver._lv[lvl]
+        if lv.npts == 0:
+            return
+        self.shift_rows(lv.u[lv.npts - 1], lv.u[0])
+
+    def recv_chain(self, solver, lvl):
+        lv = solver._lv[lvl]
+        if self.rank > 0 and lv.npts > 0:
+            self.dist.recv(lv.u[0], self._global(self.rank - 1), group=self.group)
+
+    def send_chain(self, solver, lvl):
+        lv = solver._lv[lvl]
+        if self.rank + 1 < self.size and lv.npts > 0:
+            self.dist.send(lv.u[lv.npts - 1], self._global(self.rank + 1), group=self.group)
+
+    def reduce_norm(self, partial, t_norm):
+        op = self.dist.ReduceOp.MAX if t_norm == 3 else self.dist.ReduceOp.SUM
+        self.dist.all_reduce(partial, op=op, group=self.group)
+        return partial
+
+
+def as_time_comm(comm):
+    """None -> the torch.distributed world if one is initialised (the reference defaults to MPI.COMM_WORLD), else serial."""
+    if comm is None:
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                return TorchDistComm(None)
+        except ImportError:
+            pass
+        return SerialComm()
+    if isinstance(comm, (SerialComm, TorchDistComm)):
+        return comm
+    if hasattr(comm, 'Get_rank') and hasattr(comm, 'Get_size'):
+        if comm.Get_size() == 1:
+            return SerialComm()
+        raise Exception('pass a torch.distributed process group (or TorchDistComm) as comm_time for more than one rank')
+    return TorchDistComm(comm)

@@ -1,0 +1,143 @@
+"""One level of the time-grid hierarchy in HBM: the arrays and the struct mgb_level handed to the
+C ABI (include/mgrit_b200.h).  PyTorch owns the buffers; nothing here computes."""
+import ctypes as C
+
+import numpy as np
+
+from pymgrit_b200 import _lib
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise Exception('pymgrit_b200 needs a CUDA device: there is no CPU fallback')
+    return torch
+
+
+def team_shape(kind, n):
+    t, e = C.c_int32(0), C.c_int32(0)
+    _lib.check(_lib.lib().mgb_team_shape(kind, n, C.byref(t), C.byref(e)), 'team_shape')
+    return t.value, e.value
+
+
+def step_const_table(kind, values, n, team_threads, chunk):
+    """[len(values)][cw] table of Phi constants, one row per distinct dt-dependent parameter."""
+    lib = _lib.lib()
+    cw = lib.mgb_step_consts_width(kind, team_threads, chunk)
+    fn = {_lib.APP_HEAT1D: lib.mgb_heat1d_step_consts, _lib.APP_ADVECTION1D: lib.mgb_advection1d_step_consts}[kind]
+    out = np.zeros((len(values), cw))
+    for k, v in enumerate(values):
+        _lib.check(fn(float(v), n, team_threads, chunk, out[k].ctypes.data_as(_lib.c_double_p)), 'step_consts')
+    return out
+
+
+class DeviceLevel:
+    """Arrays of one level on the current CUDA device + the matching struct mgb_level."""
+
+    def __init__(self, app, t, cpts=None, with_g=False, u_init=None):
+        torch = _torch()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.app = app
+        self.t = np.asarray(t, dtype=float)
+        self.npts = len(self.t)
+        self.n = int(app.ndof)
+        tiny = app.kind in (_lib.APP_DAHLQUIST, _lib.APP_BRUSSELATOR)
+        self.pitch = self.n if tiny else self.n + (self.n & 1)
+        self.team_threads, self.chunk = team_shape(app.kind, self.n)
+        tab = app.level_tables(self.t, self.team_threads, self.chunk)
+        self._keep = []                                   # tensors referenced by the struct
+        self.h2d_bytes = 0
+
+        def up(a, dtype):
+            if a is None:
+                return None
+            host = np.ascontiguousarray(a, dtype=dtype)
+            ten = torch.as_tensor(host).to(dev)
+            self.h2d_bytes += host.nbytes
+            self._keep.append(ten)
+            return ten
+
+        self.u = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if u_init is None else u_init
+        self.g = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if with_g else None
+        self.cpts = None if cpts is None else np.asarray(cpts, dtype=np.int32)
+        self.cpts_dev = up(self.cpts, np.int32)
+        self.t_dev = up(self.t, np.float64)
+        sconst = up(tab.get('sconst'), np.float64)
+        dtidx = up(tab.get('dtidx'), np.int32)
+        rhs_x = up(tab.get('rhs_x'), np.float64)
+        rhs_t = up(tab.get('rhs_t'), np.float64)
+        rhs_dense = None
+        if tab.get('rhs_dense') is not None:
+            dense = np.zeros((self.npts, self.pitch))
+            dense[:, :self.n] = tab['rhs_dense']
+            rhs_dense = up(dense, np.float64)
+
+        def ptr(ten):
+            return None if ten is None else ten.data_ptr()
+
+        c = _lib.MgbLevel()
+        c.app, c.n, c.pitch, c.npts = app.kind, self.n, self.pitch, self.npts
+        c.u_dev, c.g_dev = ptr(self.u), ptr(self.g)
+        c.cpts_dev, c.ncpts = ptr(self.cpts_dev), 0 if self.cpts is None else len(self.cpts)
+        c.team_threads, c.chunk = self.team_threads, self.chunk
+        c.ndt, c.cw = int(tab.get('ndt', 1)), int(tab.get('cw', 0))
+        c.dtidx_dev, c.sconst_dev = ptr(dtidx), ptr(sconst)
+        c.nrhs = int(tab.get('nrhs', 0))
+        c.rhs_x_dev, c.rhs_t_dev, c.rhs_dense_dev = ptr(rhs_x), ptr(rhs_t), ptr(rhs_dense)
+        c.t_dev = ptr(self.t_dev)
+        for k, v in enumerate(tab.get('p', [])):
+            c.p[k] = float(v)
+        for k, v in enumerate(tab.get('ip', [])):
+            c.ip[k] = int(v)
+        self.c = c
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+    def row(self, arr, i):
+        """View of time point i as a tensor of the application's vector shape."""
+        shape = self.app.vector_template.shape
+        return arr[i, :self.n].view(shape if shape else ())
+
+
+def dt_classes(t):
+    """dt_i = t[i] - t[i-1] grouped by exact value: (distinct values, index per point or None)."""
+    t = np.asarray(t, dtype=float)
+    if len(t) < 2:
+        return np.array([1.0]), None
+    dt = t[1:] - t[:-1]
+    uniq, inv = np.unique(dt, return_inverse=True)
+    if len(uniq) == 1:
+        return uniq, None
+    idx = np.zeros(len(t), dtype=np.int32)
+    idx[1:] = inv
+    return uniq, idx
+
+
+def rhs_x_layout(basis, n, team_threads, chunk):
+    """[q][n] spatial factors -> [q][chunk][team_threads] (thread-transposed, zero padded)."""
+    q = basis.shape[0]
+    full = np.zeros((q, team_threads * chunk))
+    full[:, :n] = basis
+    return np.ascontiguousarray(full.reshape(q, team_threads, chunk).transpose(0, 2, 1))
+
+
+def single_step(app, u_start, t_start, t_stop):
+    """Application.step on the device: out = Phi(u_start) from t_start to t_stop (one launch)."""
+    torch = _torch()
+    cache = app.__dict__.setdefault('_step_cache', {})
+    key = (float(t_start), float(t_stop))
+    lvl = cache.get(key)
+    if lvl is None:
+        if len(cache) > 64:
+            cache.clear()
+        lvl = DeviceLevel(app, np.array(key))
+        cache[key] = lvl
+    x = u_start.device_values.reshape(-1)
+    buf_in = torch.zeros(lvl.pitch, dtype=torch.float64, device=x.device)
+    buf_in[:lvl.n] = x
+    buf_out = torch.zeros_like(buf_in)
+    _lib.check(_lib.lib().mgb_step(lvl.ref, 1, buf_in.data_ptr(), buf_out.data_ptr(), _lib.current_stream_ptr()), 'step')
+    shape = app.vector_template.shape
+    return app.vector_template._new(buf_out[:lvl.n].view(shape if shape else ()))

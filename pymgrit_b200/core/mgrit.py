@@ -1,0 +1,441 @@
+"""MGRIT (FAS) solver with the reference's interface (core/mgrit.py:20-858), executed as batched GPU sweeps.
+
+The constructor arguments, the attributes user code reads (u, t, index_local*, conv, solve_iter, comm_time_rank...),
+the log lines and the return value of solve() are the reference's.  What differs is how a sweep runs: where the
+reference loops over time points and calls Application.step once per point (mgrit.py:314-327, 356-368, 407-412,
+472-481, 524-547), each method below makes ONE call into libmgrit_b200 (include/mgrit_b200.h) that covers every
+coarse interval of the level; the state of a level is one [points x dofs] array in HBM.
+
+Supported on the device path: applications derived from DeviceApplication, the identity GridTransferCopy, the global
+convergence criteria (conv_crit 0 and 1).  Anything else raises: there is no per-point Python fallback.
+"""
+import logging
+import sys
+import time
+from typing import List
+
+import numpy as np
+
+from pymgrit_b200 import _lib
+from pymgrit_b200.core.application import Application, DeviceApplication
+from pymgrit_b200.core.comm import SerialComm, as_time_comm
+from pymgrit_b200.core.device_level import DeviceLevel
+from pymgrit_b200.core.grid_transfer import GridTransfer
+from pymgrit_b200.core.grid_transfer_copy import GridTransferCopy
+from pymgrit_b200.core import partition
+
+
+class _LevelVectors:
+    """`mgrit.u[lvl]`: sequence of Vector views onto the rows of a level array (row i = local point i)."""
+
+    def __init__(self, level: DeviceLevel, which: str):
+        self._level, self._which = level, which
+
+    def _array(self):
+        return getattr(self._level, self._which)
+
+    def __len__(self):
+        return self._level.npts
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return self._level.app.vector_template._new(self._level.row(self._array(), i))
+
+    def __setitem__(self, i, vec):
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        self._level.row(self._array(), i).copy_(vec.device_values.reshape(self._level.app.vector_template.shape))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class Mgrit:
+    """
+    MGRIT solver class (FAS formulation) for time-stepping problems u_i = Phi(u_{i-1}).
+    """
+
+    def __init__(self, problem: List[Application], transfer: List[GridTransfer] = None, weight_c: float = 1.0,
+                 max_iter: int = 100, tol: float = 1e-7, nested_iteration: bool = True, cf_iter: int = 1,
+                 cycle_type: str = 'V', comm_time=None, comm_space=None,
+                 logging_lvl: int = logging.INFO, output_fcn=None, output_lvl=1, t_norm=2,
+                 random_init_guess: bool = False, conv_crit: int = 0) -> None:
+        logging.basicConfig(format='%(levelname)s - %(asctime)s - %(message)s', datefmt='%d-%m-%y %H:%M:%S',
+                            level=logging_lvl, stream=sys.stdout)
+        self._log_lvl = logging_lvl
+
+        if transfer is None:
+            transfer = [GridTransferCopy() for _ in range(len(problem) - 1)]
+
+        # argument checks, mgrit.py:79-128
+        if len(problem) != (len(transfer) + 1):
+            raise Exception('There should be exactly one transfer operator for each level except the coarsest grid')
+        for i in range(len(problem) - 1):
+            if len(problem[i].t) < len(problem[i + 1].t):
+                raise Exception(
+                    'The time grid on level ' + str(i + 1) + ' contains more time points than level ' + str(i))
+        if cycle_type != 'V' and cycle_type != 'F':
+            raise Exception("Cycle-type " + str(cycle_type) + " is not implemented. Choose 'V' or 'F'")
+        if output_lvl not in [0, 1, 2]:
+            raise Exception("Unknown output level. Choose 0, 1 or 2.")
+        for lvl in range(1, len(problem)):
+            if len(np.intersect1d(problem[lvl - 1].t, problem[lvl].t)) != len(problem[lvl].t):
+                raise Exception('Some points from level ' + str(lvl - 1) + ' are not points of level ' + str(lvl))
+        if t_norm not in [1, 2, 3]:
+            raise Exception('Unknown norm. Please choose 1 (one norm), 2 (two-norm) or 3 (inf-norm)')
+        if conv_crit not in [0, 1, 2, 3]:
+            raise Exception('Unknown convergence criterion. Please choose: '
+                            '0 (global space-time residual), 1 (global jump)'
+                            '2 (local space-time residual)3 (local jump)')
+        if isinstance(cf_iter, int):
+            cf_iter = [cf_iter for _ in range(len(problem))]
+        elif isinstance(cf_iter, list):
+            if len(cf_iter) < len(problem) - 1:
+                raise Exception('Too few cf_iter. '
+                                'Specify a list of values for all but the coarsest level or an integer '
+                                '(used for all levels).')
+        else:
+            raise Exception('Incorrect datatype cf_iter. '
+                            'Specify a list of values for all but the coarsest level or an integer '
+                            '( used for all levels).')
+
+        # what the device path does not cover fails loudly (no per-point fallback)
+        for p in problem:
+            if not isinstance(p, DeviceApplication):
+                raise Exception('pymgrit_b200.Mgrit runs applications derived from DeviceApplication only; '
+                                + type(p).__name__ + ' has no device kernels')
+        for tr in transfer:
+            if type(tr) is not GridTransferCopy:
+                raise Exception('only the identity GridTransferCopy is fused into the device sweeps')
+        if conv_crit in (2, 3):
+            raise Exception('local convergence criteria (conv_crit 2, 3) are not available on the device path')
+        if len({(p.kind, p.ndof) for p in problem}) != 1:
+            raise Exception('all levels must use the same application kind and spatial size')
+
+        self.comm_time = as_time_comm(comm_time)
+        self.comm_space = comm_space
+        self.comm_time_rank = self.comm_time.Get_rank()
+        self.comm_time_size = self.comm_time.Get_size()
+        if self.comm_time_size > len(problem[0].t):
+            raise Exception('More processors than time points. Not useful and not implemented yet')
+        self.spatial_parallel = False
+        self.comm_space_rank = -99
+        self.comm_space_size = 1
+
+        self.comm_time.barrier()
+        runtime_setup_start = time.time()
+        self.log_info(f"Start setup")
+
+        self.launches = 0
+        self.problem = problem
+        self.weight_c = weight_c
+        self.lvl_max = len(problem)
+        self.step = [p.step for p in problem]
+        self.t = []
+        self.m = []
+        self.restriction = [tr.restriction for tr in transfer]
+        self.interpolation = [tr.interpolation for tr in transfer]
+        self.tol = tol
+        self.conv = np.zeros(max_iter + 1)
+        self.cf_iter = cf_iter
+        self.cycle_type = cycle_type
+        self.random_init_guess = random_init_guess
+        self.iter_max = max_iter
+        self.solve_iter = 0
+        self.nes_it = nested_iteration
+        self.runtime_solve = 0
+        self.runtime_setup = 0
+        self.t_norm = 1 if t_norm == 1 else None if t_norm == 2 else np.inf
+        self._t_norm_id = t_norm
+        self.conv_crit = conv_crit
+        self.global_conv_crit = True
+        self.save_values_last_iter = None
+        self.output_lvl = output_lvl
+        self.output_fcn = output_fcn if output_fcn is not None and callable(output_fcn) else None
+
+        # index tables (mgrit.py:206-222, 742-827) and level storage in HBM (mgrit.py:840-858)
+        self.global_t = [np.copy(p.t) for p in problem]
+        part = partition.Partition(self.global_t, self.comm_time_size, self.comm_time_rank)
+        self._part = part
+        self.m = part.m
+        self.cpts = part.cpts
+        self.index_local = part.index_local
+        self.index_local_c = part.index_local_c
+        self.index_local_f = part.index_local_f
+        self.t = part.t_local
+        self.int_start, self.int_stop = part.int_start, part.int_stop
+        self.send_to, self.get_from = part.send_to, part.get_from
+        self._lv = []
+        for lvl in range(self.lvl_max):
+            cp = part.sweep_cpts[lvl] if lvl < self.lvl_max - 1 else None
+            self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0))
+        self.u = [_LevelVectors(lv, 'u') for lv in self._lv]
+        self.g = [None] + [_LevelVectors(lv, 'g') for lv in self._lv[1:]]
+        self.v = [None] * self.lvl_max       # never materialised: identical to the fine level's C-point rows
+        self._init_levels()
+        torch = _lib_torch()
+        dev = self._lv[0].u.device
+        ncp0 = len(self._lv[0].cpts) if self._lv[0].cpts is not None else 1
+        self._sq = torch.zeros(max(ncp0, 1), dtype=torch.float64, device=dev)
+        self._norm_out = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._norm_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+        if nested_iteration:
+            self.nested_iteration()
+
+        if self.conv_crit == 1:
+            self.save_values_last_iter = self._lv[0].u.clone()
+
+        if self.iter_max == 0:
+            self.comm_time.barrier()
+        torch.cuda.synchronize()
+        self.runtime_setup = time.time() - runtime_setup_start
+
+        if self.output_fcn is not None and self.output_lvl == 2:
+            self.output_fcn(self)
+
+        self.log_info(f"Setup took {self.runtime_setup} s")
+
+    # ------------------------------------------------------------------------------------------
+    def _init_levels(self):
+        """mgrit.py:846-858: zero (or random) initial guess, initial condition at the first point of rank 0."""
+        if self.random_init_guess:
+            lv = self._lv[0]
+            shape = lv.app.vector_template.shape
+            vals = np.stack([np.random.rand(*shape).reshape(-1) if shape else np.random.rand(1)
+                             for _ in range(lv.npts)])
+            lv.u[:, :lv.n] = _lib_torch().as_tensor(vals).to(lv.u.device)
+        if self.comm_time_rank == 0:
+            for lv in self._lv:
+                if lv.npts > 0:
+                    lv.row(lv.u, 0).copy_(lv.app.vector_t_start.device_values.reshape(lv.app.vector_template.shape))
+
+    def log_info(self, message: str) -> None:
+        """Only the last time rank logs (mgrit.py:247-259)."""
+        if self.comm_time_rank == self.comm_time_size - 1:
+            logging.info(message)
+
+    def _stream(self):
+        self.launches += 1                      # every C-ABI sweep below is one kernel launch of this library
+        return _lib.current_stream_ptr()
+
+    def restart(self) -> None:
+        """Forget the current iterate and redo the setup sweeps (initial guess, nested iteration) with the level tables
+        that are already in HBM.  Not in the reference (which rebuilds everything); used by bench.py."""
+        for lv in self._lv:
+            lv.u.zero_()
+            if lv.g is not None:
+                lv.g.zero_()
+        self.conv = np.zeros(self.iter_max + 1)
+        self.solve_iter = 0
+        self._init_levels()
+        if self.nes_it:
+            self.nested_iteration()
+        if self.conv_crit == 1:
+            self.save_values_last_iter = self._lv[0].u.clone()
+
+    @property
+    def h2d_bytes(self):
+        """Bytes copied host -> device while building the levels (tables, time grids, initial condition)."""
+        return sum(lv.h2d_bytes for lv in self._lv) + 8 * self._lv[0].n * self.lvl_max
+
+    def time_level0_sweeps(self, repeats: int = 5):
+        """CUDA-event timing of each level-0 sweep alone (bench.py roofline): list of dicts with the algorithmic
+        bytes (rows each interval must read or write exactly once), ms and GB/s."""
+        torch = _lib_torch()
+        lv = self._lv[0]
+        if self.lvl_max < 2 or lv.cpts is None:
+            return []
+        k0 = len(lv.cpts) - 1
+        m = self.m[0]
+        row = 8.0 * lv.n
+        sweeps = [
+            ('f_relax', lambda: self.f_relax(0), m, 1),
+            ('c_relax', lambda: self.c_relax(0), 2 + (1 if self.weight_c != 1.0 else 0), 1),
+            ('fas_residual', lambda: self.fas_residual(0), 5, 1),
+            ('error_correction+f_relax', lambda: self.error_correction(0, f_relax=True), m + 2, 1),
+            ('residual_norms', lambda: self.compute_residual(), 2, 1),
+        ]
+        out = []
+        for name, fn, rows, per_iter in sweeps:
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(repeats):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / repeats
+            nbytes = rows * k0 * row
+            out.append({'name': name, 'rows_per_interval': rows, 'intervals': k0, 'algorithmic_bytes': nbytes, 'ms': ms,
+                        'gbs': nbytes / (ms * 1e-3) / 1e9, 'share_ms': ms * per_iter})
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def iteration(self, lvl: int, cycle_type: str, iteration: int, first_f: bool) -> None:
+        """One MGRIT cycle from level lvl downwards (mgrit.py:261-290)."""
+        if lvl == self.lvl_max - 1:
+            self.forward_solve(lvl=lvl)
+            return
+        if (lvl > 0 or (iteration == 0 and lvl == 0)) and first_f:
+            self.f_relax(lvl=lvl)
+        for _ in range(self.cf_iter[lvl]):
+            self.c_relax(lvl=lvl)
+            self.f_relax(lvl=lvl)
+        self.fas_residual(lvl=lvl)
+        self.iteration(lvl=lvl + 1, cycle_type=cycle_type, iteration=iteration, first_f=True)
+        self.error_correction(lvl=lvl, f_relax=True)        # correction + the F-relaxation of mgrit.py:287, one launch
+        if lvl != 0 and cycle_type == 'F':
+            self.iteration(lvl=lvl, cycle_type='V', iteration=iteration, first_f=False)
+
+    def f_relax(self, lvl: int) -> None:
+        """F-relaxation (mgrit.py:292-333): one launch over all coarse intervals."""
+        _lib.check(_lib.lib().mgb_f_relax(self._lv[lvl].ref, self._stream()), 'f_relax')
+
+    def c_relax(self, lvl: int) -> None:
+        """C-relaxation (mgrit.py:335-370)."""
+        _lib.check(_lib.lib().mgb_c_relax(self._lv[lvl].ref, float(self.weight_c), self._stream()), 'c_relax')
+        self._exchange_ghost(lvl)
+
+    def fas_residual(self, lvl: int) -> None:
+        """Injection + FAS right-hand side of the next coarser level (mgrit.py:488-549)."""
+        fine, coarse = self._lv[lvl], self._lv[lvl + 1]
+        if coarse.npts > 0 and fine.npts > 0:
+            coarse.u[0].copy_(fine.u[0])             # the ghost / initial C-point is injected like any other
+        _lib.check(_lib.lib().mgb_fas_residual(fine.ref, coarse.ref, self._stream()), 'fas_residual')
+
+    def error_correction(self, lvl: int, f_relax: bool = False) -> None:
+        """Coarse-grid correction of the C-points (mgrit.py:715-726), optionally fused with the next F-relaxation."""
+        _lib.check(_lib.lib().mgb_error_correction(self._lv[lvl].ref, self._lv[lvl + 1].ref, 1 if f_relax else 0,
+                                                   self._stream()), 'error_correction')
+        self._exchange_ghost(lvl)
+
+    def forward_solve(self, lvl: int) -> None:
+        """Sequential time stepping on level lvl (mgrit.py:459-486)."""
+        self.comm_time.recv_chain(self, lvl)
+        _lib.check(_lib.lib().mgb_forward_solve(self._lv[lvl].ref, self._stream()), 'forward_solve')
+        self.comm_time.send_chain(self, lvl)
+
+    def nested_iteration(self) -> None:
+        """Coarsest solve, then interpolate upwards with a V-cycle per level (mgrit.py:551-566)."""
+        self.forward_solve(self.lvl_max - 1)
+        for lvl in range(self.lvl_max - 2, -1, -1):
+            _lib.check(_lib.lib().mgb_inject_up(self._lv[lvl].ref, self._lv[lvl + 1].ref, self._stream()), 'inject_up')
+            self._exchange_ghost(lvl)
+            if lvl > 0:
+                self.iteration(lvl=lvl, cycle_type='V', iteration=0, first_f=True)
+
+    def _exchange_ghost(self, lvl: int) -> None:
+        """After the C-points of a level changed: my last point becomes the next rank's ghost (mgrit.py:305-310)."""
+        self.comm_time.exchange_ghost(self, lvl)
+
+    # ------------------------------------------------------------------------------------------
+    def compute_residual(self):
+        """Squared residual norms at the local C-points of level 0 (mgrit.py:387-413), left on the device."""
+        _lib.check(_lib.lib().mgb_residual_norms(self._lv[0].ref, self._sq.data_ptr(), self._stream()), 'residual_norms')
+        return self._sq
+
+    def compute_jump(self):
+        """Squared jump norms at the local C-points (mgrit.py:372-385)."""
+        _lib.check(_lib.lib().mgb_jump_norms(self._lv[0].ref, self.save_values_last_iter.data_ptr(), self._sq.data_ptr(),
+                                             self._stream()), 'jump_norms')
+        return self._sq
+
+    def convergence_criterion(self, iteration: int) -> None:
+        """Global criterion (mgrit.py:415-432): temporal norm of the per-point norms, reduced over the time ranks."""
+        lv0 = self._lv[0]
+        ncp = 0 if lv0.cpts is None else len(lv0.cpts)
+        if ncp > 0:
+            sq = self.compute_residual() if self.conv_crit == 0 else self.compute_jump()
+            _lib.check(_lib.lib().mgb_temporal_norm(sq.data_ptr(), ncp, self._t_norm_id, self._norm_out.data_ptr(),
+                                                    self._stream()), 'temporal_norm')
+        else:
+            self._norm_out.zero_()
+        part = self.comm_time.reduce_norm(self._norm_out, self._t_norm_id)
+        self._norm_host.copy_(part, non_blocking=False)
+        val = float(self._norm_host[0])
+        self.conv[iteration] = np.sqrt(val) if self._t_norm_id == 2 else val
+
+    # ------------------------------------------------------------------------------------------
+    def ouput_run_information(self) -> None:
+        msg = ['Run parameter overview',
+               '  ' + '{0: <25}'.format(f'time interval') + ' : ' + '[' + str(self.problem[0].t[0]) + ', ' + str(
+                   self.problem[0].t[-1]) + ']',
+               '  ' + '{0: <25}'.format(f'number of time points ') + ' : ' + str(len(self.problem[0].t)),
+               '  ' + '{0: <25}'.format(f'max dt ') + ' : ' + str(
+                   np.max(self.problem[0].t[1:] - self.problem[0].t[:-1])),
+               '  ' + '{0: <25}'.format(f'number of levels') + ' : ' + str(self.lvl_max),
+               '  ' + '{0: <25}'.format(f'coarsening factors') + ' : ' + str(self.m[:-1]),
+               '  ' + '{0: <25}'.format(f'relaxation weight') + ' : ' + str(self.weight_c),
+               '  ' + '{0: <25}'.format(f'cf_iter') + ' : ' + str(self.cf_iter[:self.lvl_max - 1]),
+               '  ' + '{0: <25}'.format(f'nested iteration') + ' : ' + str(self.nes_it),
+               '  ' + '{0: <25}'.format(f'cycle type') + ' : ' + str(self.cycle_type),
+               '  ' + '{0: <25}'.format(f'stopping tolerance') + ' : ' + str(self.tol),
+               '  ' + '{0: <25}'.format(f'time communicator size') + ' : ' + str(self.comm_time_size),
+               '  ' + '{0: <25}'.format(f'space communicator size') + ' : ' + str(self.comm_space_size),
+               '  ' + '{0: <25}'.format(f'convergence criterion') + ' : ' + str(self.conv_crit)]
+        self.log_info(message='\n'.join(msg))
+
+    def solve(self) -> dict:
+        """Iterate until the stopping criterion is met (mgrit.py:590-646)."""
+        torch = _lib_torch()
+        self.log_info("Start solve")
+        runtime_solve_start = time.time()
+        for iteration in range(self.iter_max):
+            self.solve_iter = iteration + 1
+            time_it_start = time.time()
+            self.iteration(lvl=0, cycle_type=self.cycle_type, iteration=iteration, first_f=True)
+            if self._log_lvl <= logging.INFO:
+                torch.cuda.synchronize()        # so that the per-iteration runtime in the log is the device time
+            time_it_stop = time.time()
+            self.convergence_criterion(iteration=iteration + 1)
+
+            if iteration == 0:
+                self.log_info('{0: <7}'.format(f"iter {iteration + 1}") +
+                              '{0: <32}'.format(f" | conv: {self.conv[iteration + 1]}") +
+                              '{0: <37}'.format(f" | conv factor: -") +
+                              '{0: <35}'.format(f" | runtime: {time_it_stop - time_it_start} s"))
+            else:
+                self.log_info('{0: <7}'.format(f"iter {iteration + 1}") +
+                              '{0: <32}'.format(f" | conv: {self.conv[iteration + 1]}") +
+                              '{0: <37}'.format(f" | conv factor: {self.conv[iteration + 1] / self.conv[iteration]}") +
+                              '{0: <35}'.format(f" | runtime: {time_it_stop - time_it_start} s"))
+
+            if self.output_fcn is not None and self.output_lvl == 2:
+                self.output_fcn(self)
+
+            if self.conv[iteration + 1] < self.tol or iteration == self.iter_max - 1:
+                break
+        torch.cuda.synchronize()
+        self.comm_time.barrier()
+        self.runtime_solve = time.time() - runtime_solve_start
+        self.log_info(f"Solve took {self.runtime_solve} s")
+
+        if self.output_fcn is not None and self.output_lvl == 1:
+            self.output_fcn(self)
+
+        self.ouput_run_information()
+        return {'conv': self.conv[np.where(self.conv != 0)], 'time_setup': self.runtime_setup,
+                'time_solve': self.runtime_solve}
+
+    # helpers kept for API compatibility (mgrit.py:728-740, 829-838)
+    def split_into(self, number_points: int, number_processes: int) -> np.ndarray:
+        return partition.split_into(number_points, number_processes)
+
+    def split_points(self, length: int, size: int, rank: int):
+        return partition.split_points(length, size, rank)
+
+
+def _lib_torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise Exception('pymgrit_b200 needs a CUDA device: there is no CPU fallback')
+    return torch

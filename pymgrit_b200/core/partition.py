@@ -1,0 +1,174 @@
+"""Time-parallel decomposition: which time points of every level a time rank owns.
+
+Two things live here.
+
+`reference_decomposition` restates, as index arithmetic on boolean masks, the tables the reference builds in
+Mgrit.setup_points_and_comm_info (core/mgrit.py:742-827, pinned by tests/core/test_mgrit.py:86-218): block split of the
+level-0 points (split_into, mgrit.py:829-838), one ghost point on ranks > 0, local C/F index lists (F-points grouped by
+interval, last interval first), the eight communication flags and send_to / get_from.
+
+`Partition` is what the batched engine uses.  It differs from the reference's split in one respect: slab boundaries are
+moved onto points of the coarsest grid, so that on every level the slab of a rank starts right after a C-point (its ghost)
+and ends on a C-point.  Then every rank sees an ordinary serial problem whose "initial condition" is the ghost row, no
+coarse interval is ever split across ranks (reference message kinds 1, 2, 3 and 7 disappear, mgrit.py:316-331, 347-352,
+398-403, 503-508) and only the ghost exchange (kind 0/4) and the coarsest chain (kind 5) remain.  For nt = 2^k + 1 and a
+power-of-two number of ranks the two partitions coincide.  Results do not depend on the partition.
+"""
+import numpy as np
+
+
+def split_into(number_points: int, number_processes: int) -> np.ndarray:
+    """Block sizes: the first (points % processes) ranks get one extra point (mgrit.py:829-838)."""
+    base, extra = divmod(int(number_points), int(number_processes))
+    return np.array([base + 1] * extra + [base] * (number_processes - extra))
+
+
+def split_points(length: int, size: int, rank: int):
+    """(block size, index of first point) of a rank (mgrit.py:728-740)."""
+    split = split_into(length, size)
+    return split[rank], (np.sum(split[:rank]) if split[rank] > 0 else 0)
+
+
+def c_point_masks(global_t):
+    """is_c[l][i]: point i of level l is also a point of level l+1 (mgrit.py:212, 768-770); all True on the coarsest."""
+    masks = []
+    for l, t in enumerate(global_t):
+        masks.append(np.isin(t, global_t[l + 1]) if l + 1 < len(global_t) else np.ones(len(t), dtype=bool))
+    return masks
+
+
+def coarsening_factors(global_t, masks):
+    """m[l] = distance between the first two C-points (mgrit.py:213-214); 1 on the coarsest level."""
+    out = []
+    for l in range(len(global_t)):
+        if l + 1 < len(global_t):
+            idx = np.flatnonzero(masks[l])
+            out.append(int(idx[1] - idx[0]) if len(idx) > 1 else 1)
+        else:
+            out.append(1)
+    return out
+
+
+_SET_ORDER_LIMIT = 1 << 16
+
+
+def _f_groups_reversed(fpts):
+    """F-points grouped into runs of consecutive indices, runs in reverse order (mgrit.py:774-776)."""
+    if len(fpts) == 0:
+        return np.array([], dtype=float)
+    breaks = np.flatnonzero(np.diff(fpts) != 1) + 1
+    runs = np.split(fpts, breaks)
+    return np.concatenate(runs[::-1])
+
+
+def _level_tables(global_t, masks, lvl, size, rank, window):
+    """Tables of one level for the owner of the level-0 index window [first, last] (inclusive)."""
+    t = global_t[lvl]
+    n = len(t)
+    is_c = masks[lvl]
+    t0 = global_t[0]
+    first0, last0 = window
+    if first0 > last0:
+        own = np.array([], dtype=int)
+    elif lvl == 0:
+        own = np.arange(first0, last0 + 1)
+    else:
+        own = np.flatnonzero((t >= t0[first0]) & (t <= t0[last0]))
+    cpts = own[is_c[own]] if len(own) else own
+    fpts = own[~is_c[own]] if len(own) else own
+    if 0 < len(own) <= _SET_ORDER_LIMIT:
+        # The reference builds the F-point list from a Python set difference (mgrit.py:773), so the order in which
+        # it visits the F-intervals is CPython's set iteration order.  Results do not depend on it, but
+        # index_local_f is part of the de-facto API (tests/core/test_mgrit.py:171-177): reproduce it when cheap.
+        fpts = np.array(list(set(own) - set(cpts)), dtype=own.dtype)
+    ghost = rank != 0 and len(own) > 0
+    with_ghost = np.concatenate([[own[0] - 1], own]) if ghost else own
+    off = 1 if ghost else 0
+    pos = {'index_local': np.arange(len(own)) + off,
+           'index_local_c': (cpts - own[0] + off) if len(own) else cpts,
+           'index_local_f': (_f_groups_reversed(fpts) - own[0] + off) if len(fpts) else np.array([], dtype=float)}
+
+    def is_f(i):
+        return 0 <= i < n and not is_c[i]
+
+    def is_cc(i):
+        return 0 <= i < n and bool(is_c[i])
+
+    has = len(own) > 0
+    flags = dict(
+        comm_front=bool(len(fpts) > 0 and is_f(fpts.min() - 1)),
+        comm_back=bool(len(fpts) > 0 and is_f(fpts.max() + 1)),
+        first_is_c_point=bool(has and is_c[own[0]] and own[0] != 0 and is_f(own[0] - 1)),
+        first_is_f_point=bool(has and not is_c[own[0]] and is_cc(own[0] - 1)),
+        last_is_c_point=bool(has and is_c[own[-1]] and own[-1] != n - 1 and is_f(own[-1] + 1)),
+        last_is_f_point=bool(has and not is_c[own[-1]] and own[-1] != n - 1 and is_cc(own[-1] + 1)),
+    )
+    return own, with_ghost, cpts, pos, flags
+
+
+def reference_decomposition(global_t, size, rank):
+    """Per-level dicts with the reference's tables for (size, rank)."""
+    masks = c_point_masks(global_t)
+    split = split_into(len(global_t[0]), size)
+    block, first = split[rank], int(np.sum(split[:rank])) if split[rank] > 0 else 0
+    window = (first, first + block - 1)
+    split_t = global_t[0][np.cumsum(split) - 1]
+    out = []
+    for lvl, t in enumerate(global_t):
+        own, with_ghost, cpts, pos, flags = _level_tables(global_t, masks, lvl, size, rank, window)
+        t_local = t[with_ghost] if len(with_ghost) else np.array([])
+        send_to = get_from = -99
+        if len(with_ghost) > 0:
+            if t_local[-1] != t[-1]:
+                send_to = int(np.searchsorted(split_t, t[with_ghost[-1] + 1]))
+            if len(with_ghost) > len(own) or t_local[0] != global_t[0][0]:
+                get_from = int(np.searchsorted(split_t, t_local[0]))
+        d = dict(t=t_local, cpts=cpts, send_to=send_to, get_from=get_from, **pos, **flags)
+        out.append(d)
+    return out
+
+
+class Partition:
+    """Aligned slab partition used by the engine (see module docstring)."""
+
+    def __init__(self, global_t, size, rank):
+        self.size, self.rank = size, rank
+        L = len(global_t)
+        masks = c_point_masks(global_t)
+        self.m = coarsening_factors(global_t, masks)
+        t0 = global_t[0]
+        n0 = len(t0)
+        if size == 1:
+            bounds = np.array([n0 - 1])
+        else:
+            # slab ends must be points of the coarsest grid: spread its intervals over the ranks
+            coarse_idx = np.flatnonzero(np.isin(t0, global_t[-1]))
+            nc = len(coarse_idx)
+            if nc - 1 < size:
+                raise Exception(f'{size} time ranks need at least {size} intervals on the coarsest grid '
+                                f'(it has {nc - 1}); use fewer ranks or a finer coarsest level')
+            cuts = np.cumsum(split_into(nc - 1, size))            # coarsest-interval index at which each slab ends
+            bounds = coarse_idx[cuts]
+            bounds[-1] = n0 - 1                                    # trailing points after the last coarse point
+        self.bounds = bounds
+        first = 0 if rank == 0 else int(bounds[rank - 1]) + 1
+        last = int(bounds[rank])
+        self.window = (first, last)
+        self.int_start, self.int_stop = t0[first], t0[last]
+        self.t_local, self.cpts, self.index_local, self.index_local_c, self.index_local_f = [], [], [], [], []
+        self.sweep_cpts, self.send_to, self.get_from, self.owned = [], [], [], []
+        for lvl in range(L):
+            own, with_ghost, cpts, pos, _ = _level_tables(global_t, masks, lvl, size, rank, (first, last))
+            self.owned.append(own)
+            self.t_local.append(global_t[lvl][with_ghost])
+            self.cpts.append(cpts)
+            self.index_local.append(pos['index_local'])
+            self.index_local_c.append(pos['index_local_c'])
+            self.index_local_f.append(pos['index_local_f'])
+            # C-points as the sweeps want them: local indices, starting with point 0 (initial condition or ghost)
+            lc = np.asarray(pos['index_local_c'], dtype=np.int64)
+            if rank != 0:
+                lc = np.concatenate([[0], lc])
+            self.sweep_cpts.append(lc.astype(np.int32))
+            self.send_to.append(rank + 1 if rank + 1 < size else -99)
+            self.get_from.append(rank - 1 if rank > 0 else -99)

@@ -1,0 +1,419 @@
+// api.cu -- the C ABI of include/mgrit_b200.h: argument checks, shape dispatch, host-side constant
+// tables, and the small row-wise kernels (injection, jump, temporal norm, Vector arithmetic).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/mgrit_b200.h"
+#include "phi.cuh"
+#include "table.h"
+
+namespace mgb {
+
+// ---- error state ---------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *a = "", long b = 0, long c = 0) {
+    snprintf(g_err, sizeof g_err, fmt, a, b, c);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return MGB_OK;
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return MGB_ECUDA;
+}
+
+const DeviceInfo *device_info() {
+    static DeviceInfo info;
+    static int state = 0;  // 0 unknown, 1 ok, 2 failed
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (state == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&info.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&info.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) {
+            cuda_fail(e, "no usable CUDA device (this library has no CPU fallback)");
+            state = 2;
+        } else {
+            state = 1;
+        }
+    }
+    return state == 1 ? &info : nullptr;
+}
+
+// ---- compiled shapes --------------------------------------------------------------------------------
+#define MGB_APP_Heat1D MGB_APP_HEAT1D
+#define MGB_APP_Advection1D MGB_APP_ADVECTION1D
+#define MGB_SHAPE(APP, T, E) const SweepTable *mgb_table_##APP##_##T##_##E();
+#include "shapes.inc"
+#undef MGB_SHAPE
+const SweepTable *mgb_table_tiny(int app);  // tiny.cu
+
+struct ShapeEntry {
+    int app, T, E;
+    const SweepTable *(*get)();
+};
+static const ShapeEntry g_shapes[] = {
+#define MGB_SHAPE(APP, T, E) {MGB_APP_##APP, T, E, &mgb_table_##APP##_##T##_##E},
+#include "shapes.inc"
+#undef MGB_SHAPE
+};
+
+static const SweepTable *find_table(int app, int T, int E) {
+    if (app == MGB_APP_DAHLQUIST || app == MGB_APP_BRUSSELATOR) return mgb_table_tiny(app);
+    for (const ShapeEntry &s : g_shapes)
+        if (s.app == app && s.T == T && s.E == E) return s.get();
+    return nullptr;
+}
+
+static int check_level(const mgb_level *l, const SweepTable **tab, LevelDev *out) {
+    if (l == nullptr) return fail(MGB_EINVAL, "null level%s");
+    if (l->n < 1 || l->pitch < l->n || l->npts < 1 || l->u_dev == nullptr)
+        return fail(MGB_EINVAL, "bad level geometry%s (n=%ld, npts=%ld)", "", l->n, l->npts);
+    const bool tiny = (l->app == MGB_APP_DAHLQUIST || l->app == MGB_APP_BRUSSELATOR);
+    if (!tiny) {
+        if (l->pitch % 2) return fail(MGB_EINVAL, "pitch must be even%s (got %ld)", "", l->pitch);
+        if ((long)l->team_threads * l->chunk < l->pitch)
+            return fail(MGB_EINVAL, "team shape%s %ld x %ld does not cover a row", "", l->team_threads, l->chunk);
+        if (l->sconst_dev == nullptr || l->ndt < 1 || (l->ndt > 1 && l->dtidx_dev == nullptr))
+            return fail(MGB_EINVAL, "missing step-constant table%s");
+        if (l->nrhs > 0 && (l->rhs_x_dev == nullptr || l->rhs_t_dev == nullptr))
+            return fail(MGB_EINVAL, "missing right-hand-side tables%s");
+    }
+    *tab = find_table(l->app, l->team_threads, l->chunk);
+    if (*tab == nullptr)
+        return fail(MGB_ENOSHAPE, "no kernels compiled for app%s %ld with team %ld", "", l->app, l->team_threads);
+    out->u = l->u_dev;
+    out->g = l->g_dev;
+    out->cpts = l->cpts_dev;
+    out->ncpts = l->cpts_dev ? l->ncpts : 0;
+    out->npts = l->npts;
+    out->n = l->n;
+    out->pitch = l->pitch;
+    out->ndt = l->ndt;
+    out->cw = l->cw;
+    out->dtidx = l->dtidx_dev;
+    out->sconst = l->sconst_dev;
+    out->nrhs = l->nrhs;
+    out->rhs_x = l->rhs_x_dev;
+    out->rhs_t = l->rhs_t_dev;
+    out->rhs_dense = l->rhs_dense_dev;
+    out->t = l->t_dev;
+    for (int k = 0; k < 8; ++k) out->p[k] = l->p[k];
+    for (int k = 0; k < 4; ++k) out->ip[k] = l->ip[k];
+    if (tiny && l->t_dev == nullptr) return fail(MGB_EINVAL, "ODE applications need the time grid t_dev%s");
+    return MGB_OK;
+}
+
+static int check_pair(const mgb_level *f, const mgb_level *c) {
+    if (f->app != c->app || f->n != c->n || f->pitch != c->pitch || f->team_threads != c->team_threads ||
+        f->chunk != c->chunk)
+        return fail(MGB_EINVAL, "fine and coarse level differ in application or spatial size%s");
+    if (f->cpts_dev == nullptr || c->npts < f->ncpts)
+        return fail(MGB_EINVAL, "coarse level has fewer points than the fine level has C-points%s");
+    if (c->g_dev == nullptr) return fail(MGB_EINVAL, "coarse level needs a g array%s");
+    return MGB_OK;
+}
+
+// ---- row-wise helper kernels ------------------------------------------------------------------------
+__global__ void k_inject_up(double *__restrict__ fu, const double *__restrict__ cu, const int *__restrict__ cpts,
+                            int ncpts, int n, int pitch) {
+    for (int j = 1 + blockIdx.x; j < ncpts; j += gridDim.x) {
+        double *dst = fu + (size_t)cpts[j] * pitch;
+        const double *src = cu + (size_t)j * pitch;
+        for (int q = threadIdx.x; q < n; q += blockDim.x) dst[q] = src[q];
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double s[32];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s[warp] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s[w];
+    return tot;
+}
+
+// out_sq[j] = ||u[c_j] - last[c_j]||^2 (j >= 1); then last <- u everywhere (mgrit.py:379-384)
+__global__ void k_jump(const double *__restrict__ u, double *__restrict__ last, const int *__restrict__ cpts, int ncpts,
+                       int npts, int n, int pitch, double *__restrict__ out_sq) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) out_sq[0] = 0.0;
+    for (int j = 1 + blockIdx.x; j < ncpts; j += gridDim.x) {
+        const size_t off = (size_t)cpts[j] * pitch;
+        double acc = 0.0;
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {
+            const double d = u[off + q] - last[off + q];
+            acc = fma(d, d, acc);
+        }
+        acc = block_sum(acc);
+        if (threadIdx.x == 0) out_sq[j] = acc;
+    }
+}
+
+__global__ void k_copy_rows(const double *__restrict__ src, double *__restrict__ dst, size_t count) {
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < count; q += (size_t)gridDim.x * blockDim.x)
+        dst[q] = src[q];
+}
+
+// single CTA, fixed-order reduction -> deterministic
+__global__ void k_temporal_norm(const double *__restrict__ sq, int count, int mode, double *__restrict__ out) {
+    double acc = 0.0;
+    for (int q = threadIdx.x; q < count; q += blockDim.x) {
+        const double v = sq[q];
+        if (mode == MGB_TNORM_TWO)
+            acc += v;
+        else if (mode == MGB_TNORM_ONE)
+            acc += sqrt(v);
+        else
+            acc = fmax(acc, sqrt(v));
+    }
+    __shared__ double s[1024];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = blockDim.x >> 1; d >= 1; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            if (mode == MGB_TNORM_INF)
+                s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + d]);
+            else
+                s[threadIdx.x] += s[threadIdx.x + d];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+
+__global__ void k_axpby(int n, double a, const double *__restrict__ x, double b, const double *__restrict__ y,
+                        double *__restrict__ out) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        // products and sum rounded separately, like numpy's x*a + y*b
+        const double xa = (a == 1.0) ? x[q] : __dmul_rn(x[q], a);
+        const double yb = (b == 0.0 || y == nullptr) ? 0.0 : ((b == 1.0) ? y[q] : (b == -1.0 ? -y[q] : __dmul_rn(y[q], b)));
+        out[q] = (b == 0.0 || y == nullptr) ? xa : __dadd_rn(xa, yb);
+    }
+}
+
+__global__ void k_sumsq(int n, const double *__restrict__ x, double *__restrict__ out) {
+    double acc = 0.0;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) acc = fma(x[q], x[q], acc);
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) out[0] = acc;
+}
+
+// ---- host-side step constants -------------------------------------------------------------------------
+static long double lpow(long double b, long e) { return e <= 0 ? 1.0L : powl(b, (long double)e); }
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" {
+
+int mgb_abi_version(void) { return MGB_ABI_VERSION; }
+
+const char *mgb_last_error(void) { return g_err; }
+
+int mgb_team_shape(int32_t app, int32_t n, int32_t *team_threads, int32_t *chunk) {
+    if (n < 1 || team_threads == nullptr || chunk == nullptr) return fail(MGB_EINVAL, "bad argument%s");
+    if (app == MGB_APP_DAHLQUIST || app == MGB_APP_BRUSSELATOR) {
+        *team_threads = 1;
+        *chunk = n;
+        return MGB_OK;
+    }
+    const int pitch = n + (n & 1);
+    long best = -1;
+    for (const ShapeEntry &s : g_shapes) {
+        if (s.app != app || (long)s.T * s.E < pitch) continue;
+        // fewest threads first, then the smallest chunk
+        const long key = (long)s.T * 1000 + s.E;
+        if (best < 0 || key < best) {
+            best = key;
+            *team_threads = s.T;
+            *chunk = s.E;
+        }
+    }
+    if (best < 0) return fail(MGB_ENOSHAPE, "no kernel shape for app%s %ld with n = %ld", "", app, n);
+    return MGB_OK;
+}
+
+int mgb_step_consts_width(int32_t app, int32_t team_threads, int32_t chunk) {
+    (void)app;
+    const int sub = (chunk % 3 == 0) ? 3 : 1;
+    return kScalarConsts + team_threads * (2 + 2 * sub);
+}
+
+int mgb_heat1d_step_consts(double r_, int32_t n, int32_t T, int32_t E, double *out) {
+    if (!(r_ > 0.0) || n < 1 || T < 32 || E < 1 || out == nullptr) return fail(MGB_EINVAL, "bad argument%s");
+    const int SUB = (E % 3 == 0) ? 3 : 1, SL = E / SUB, PT = 2 + 2 * SUB;
+    if (SL > 14) return fail(MGB_EINVAL, "chunk too long%s");
+    const long double r = r_;
+    // delta = 2 + 1/r; beta = smaller root of b^2 - delta b + 1;  delta^2 - 4 = (4 + 1/r)/r
+    const long double delta = 2.0L + 1.0L / r;
+    const long double beta = 2.0L / (delta + sqrtl((4.0L + 1.0L / r) / r));
+    const long double om = 1.0L - beta * beta;
+    const long double h0 = (beta - lpow(beta, 2L * n + 1)) / om;
+    const long double B = lpow(beta, E);
+    memset(out, 0, sizeof(double) * (size_t)(kScalarConsts + T * PT));
+    out[0] = (double)beta;
+    out[1] = (double)(beta / r);
+    out[2] = (double)(beta / (1.0L + beta * h0));
+    out[3] = (double)lpow(beta, SL);
+    for (int k = 0; k < 5; ++k) out[4 + k] = (double)lpow(B, 1L << k);
+    out[9] = (double)lpow(B, 32);
+    for (int j = 0; j < SL; ++j) out[10 + j] = (double)lpow(beta, j + 1);
+    for (int t = 0; t < T; ++t) {
+        double *pt = out + kScalarConsts + t * PT;
+        const int lane = t & 31;
+        pt[0] = (double)lpow(B, lane);
+        pt[1] = (double)lpow(B, 31 - lane);
+        for (int s = 0; s < SUB; ++s) {
+            const long base = (long)t * E + (long)s * SL;  // first element of the sub-chunk
+            if (base >= n) continue;                      // no valid element: leave zeros
+            pt[2 + s] = (double)(lpow(beta, base) / om);
+            const long ex = 2L * n + 1 - base - SL;       // >= 0 whenever the sub-chunk holds a valid element
+            pt[2 + SUB + s] = (double)((ex >= 0 ? lpow(beta, ex) : 1.0L / lpow(beta, -ex)) / om);
+        }
+    }
+    return MGB_OK;
+}
+
+int mgb_advection1d_step_consts(double nu_, int32_t n, int32_t T, int32_t E, double *out) {
+    if (!(nu_ > 0.0) || n < 1 || T < 32 || E < 1 || out == nullptr) return fail(MGB_EINVAL, "bad argument%s");
+    const int SUB = (E % 3 == 0) ? 3 : 1, SL = E / SUB, PT = 2 + 2 * SUB;
+    if (SL > 14) return fail(MGB_EINVAL, "chunk too long%s");
+    const long double nu = nu_;
+    const long double rho = nu / (1.0L + nu), sig = 1.0L / (1.0L + nu);
+    const long double B = lpow(rho, E);
+    memset(out, 0, sizeof(double) * (size_t)(kScalarConsts + T * PT));
+    out[0] = (double)rho;
+    out[1] = (double)sig;
+    out[2] = (double)(1.0L / (1.0L - lpow(rho, n)));
+    out[3] = (double)lpow(rho, SL);
+    for (int k = 0; k < 5; ++k) out[4 + k] = (double)lpow(B, 1L << k);
+    out[9] = (double)lpow(B, 32);
+    for (int j = 0; j < SL; ++j) out[10 + j] = (double)lpow(rho, j + 1);
+    for (int t = 0; t < T; ++t) {
+        double *pt = out + kScalarConsts + t * PT;
+        pt[0] = (double)lpow(B, t & 31);
+        for (int s = 0; s < SUB; ++s) pt[2 + s] = (double)lpow(rho, (long)t * E + (long)s * SL);
+    }
+    return MGB_OK;
+}
+
+#define MGB_PROLOGUE(lvl)                \
+    const SweepTable *tab = nullptr;     \
+    LevelDev L;                          \
+    if (int rc = check_level(lvl, &tab, &L)) return rc; \
+    cudaStream_t st = (cudaStream_t)stream;
+
+int mgb_f_relax(const mgb_level *lvl, void *stream) {
+    MGB_PROLOGUE(lvl)
+    if (L.cpts == nullptr) return fail(MGB_EINVAL, "f_relax needs the C-point table%s");
+    return tab->f_relax(L, st);
+}
+
+int mgb_c_relax(const mgb_level *lvl, double weight, void *stream) {
+    MGB_PROLOGUE(lvl)
+    if (L.cpts == nullptr) return fail(MGB_EINVAL, "c_relax needs the C-point table%s");
+    return tab->c_relax(L, weight, st);
+}
+
+int mgb_fas_residual(const mgb_level *fine, const mgb_level *coarse, void *stream) {
+    MGB_PROLOGUE(fine)
+    const SweepTable *tab2 = nullptr;
+    LevelDev G;
+    if (int rc = check_level(coarse, &tab2, &G)) return rc;
+    if (int rc = check_pair(fine, coarse)) return rc;
+    return tab->fas_residual(L, G, st);
+}
+
+int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t f_relax, void *stream) {
+    MGB_PROLOGUE(fine)
+    const SweepTable *tab2 = nullptr;
+    LevelDev G;
+    if (int rc = check_level(coarse, &tab2, &G)) return rc;
+    if (int rc = check_pair(fine, coarse)) return rc;
+    return tab->correct(L, G, f_relax, st);
+}
+
+int mgb_forward_solve(const mgb_level *lvl, void *stream) {
+    MGB_PROLOGUE(lvl)
+    return tab->forward_solve(L, st);
+}
+
+int mgb_residual_norms(const mgb_level *lvl, double *out_sq_dev, void *stream) {
+    MGB_PROLOGUE(lvl)
+    if (L.cpts == nullptr || out_sq_dev == nullptr) return fail(MGB_EINVAL, "residual_norms needs C-points and an output%s");
+    return tab->residual(L, out_sq_dev, st);
+}
+
+int mgb_jump_norms(const mgb_level *lvl, double *last_dev, double *out_sq_dev, void *stream) {
+    MGB_PROLOGUE(lvl)
+    (void)tab;
+    if (L.cpts == nullptr || last_dev == nullptr || out_sq_dev == nullptr) return fail(MGB_EINVAL, "bad argument%s");
+    const DeviceInfo *di = device_info();
+    if (di == nullptr) return MGB_ECUDA;
+    const int threads = L.n >= 256 ? 256 : 32 * ((L.n + 31) / 32);
+    int grid = L.ncpts - 1 < 8 * di->sms ? L.ncpts - 1 : 8 * di->sms;
+    if (grid < 1) grid = 1;
+    k_jump<<<grid, threads, 0, st>>>(L.u, last_dev, L.cpts, L.ncpts, L.npts, L.n, L.pitch, out_sq_dev);
+    const size_t count = (size_t)L.npts * L.pitch;
+    k_copy_rows<<<4 * di->sms, 256, 0, st>>>(L.u, last_dev, count);
+    return cuda_fail(cudaGetLastError(), "jump_norms");
+}
+
+int mgb_temporal_norm(const double *sq_dev, int32_t count, int32_t t_norm, double *out_dev, void *stream) {
+    if (sq_dev == nullptr || out_dev == nullptr || count < 0 || t_norm < 1 || t_norm > 3)
+        return fail(MGB_EINVAL, "bad argument%s");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    k_temporal_norm<<<1, 1024, 0, (cudaStream_t)stream>>>(sq_dev, count, t_norm, out_dev);
+    return cuda_fail(cudaGetLastError(), "temporal_norm");
+}
+
+int mgb_inject_up(const mgb_level *fine, const mgb_level *coarse, void *stream) {
+    MGB_PROLOGUE(fine)
+    (void)tab;
+    if (coarse == nullptr || coarse->u_dev == nullptr || L.cpts == nullptr || coarse->npts < L.ncpts ||
+        coarse->pitch != L.pitch)
+        return fail(MGB_EINVAL, "bad level pair%s");
+    const DeviceInfo *di = device_info();
+    if (di == nullptr) return MGB_ECUDA;
+    if (L.ncpts < 2) return MGB_OK;
+    const int threads = L.n >= 256 ? 256 : 32 * ((L.n + 31) / 32);
+    const int grid = L.ncpts - 1 < 8 * di->sms ? L.ncpts - 1 : 8 * di->sms;
+    k_inject_up<<<grid, threads, 0, st>>>(L.u, coarse->u_dev, L.cpts, L.ncpts, L.n, L.pitch);
+    return cuda_fail(cudaGetLastError(), "inject_up");
+}
+
+int mgb_step(const mgb_level *lvl, int32_t point, const double *in_dev, double *out_dev, void *stream) {
+    MGB_PROLOGUE(lvl)
+    if (point < 1 || point >= L.npts || in_dev == nullptr || out_dev == nullptr)
+        return fail(MGB_EINVAL, "bad step%s (point %ld of %ld)", "", point, L.npts);
+    return tab->step(L, point, in_dev, out_dev, st);
+}
+
+int mgb_vec_axpby(int32_t n, double a, const double *x_dev, double b, const double *y_dev, double *out_dev, void *stream) {
+    if (n < 1 || x_dev == nullptr || out_dev == nullptr) return fail(MGB_EINVAL, "bad argument%s");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    const int threads = 256;
+    int grid = (n + threads - 1) / threads;
+    if (grid > 1184) grid = 1184;
+    k_axpby<<<grid, threads, 0, (cudaStream_t)stream>>>(n, a, x_dev, b, y_dev, out_dev);
+    return cuda_fail(cudaGetLastError(), "vec_axpby");
+}
+
+int mgb_vec_sumsq(int32_t n, const double *x_dev, double *out_dev, void *stream) {
+    if (n < 1 || x_dev == nullptr || out_dev == nullptr) return fail(MGB_EINVAL, "bad argument%s");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    k_sumsq<<<1, 1024, 0, (cudaStream_t)stream>>>(n, x_dev, out_dev);
+    return cuda_fail(cudaGetLastError(), "vec_sumsq");
+}
+
+}  // extern "C"

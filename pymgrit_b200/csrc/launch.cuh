@@ -1,0 +1,107 @@
+// launch.cuh -- host-side launchers for the team kernels of sweeps.cuh, one table per (Phi, T, E).
+#pragma once
+#include "sweeps.cuh"
+#include "table.h"
+
+namespace mgb {
+
+template <class Phi>
+struct Launch {
+    using SH = typename Phi::SH;
+
+    static size_t smem_bytes(int nin) { return kHeaderBytes + (size_t)(nin + 1) * SH::SLOT_BYTES; }
+
+    // persistent grid: as many CTAs as fit on the device at once, but no more than there are items
+    template <class K>
+    static int grid_for(K kernel, int nitems, int nin, int *grid) {
+        const size_t smem = smem_bytes(nin);
+        const DeviceInfo *di = device_info();
+        if (di == nullptr) return 3;
+        if ((int)smem > di->max_smem_optin) return 2;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Phi::T, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        if (per_sm < 1) return 2;
+        const long cap = (long)per_sm * di->sms;
+        *grid = (int)(nitems < cap ? nitems : cap);
+        if (*grid < 1) *grid = 1;
+        return 0;
+    }
+
+    static int rows_extra(const LevelDev &L) { return (L.g ? 1 : 0) + (L.rhs_dense ? 1 : 0); }
+
+    static int f_relax(const LevelDev &L, cudaStream_t st) {
+        if (L.ncpts < 1) return 0;
+        const int nin = 2 + rows_extra(L);
+        int grid;
+        if (int rc = grid_for(k_chain<Phi>, L.ncpts, nin, &grid)) return rc;
+        k_chain<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, L.ncpts, nin);
+        return cuda_fail(cudaGetLastError(), "f_relax");
+    }
+
+    static int forward_solve(const LevelDev &L0, cudaStream_t st) {
+        LevelDev L = L0;
+        L.cpts = nullptr;  // one interval [0, npts)
+        L.ncpts = 0;
+        if (L.npts < 2) return 0;
+        const int nin = 4;
+        int grid;
+        if (int rc = grid_for(k_chain<Phi>, 1, nin, &grid)) return rc;
+        k_chain<Phi><<<1, Phi::T, smem_bytes(nin), st>>>(L, 1, nin);
+        return cuda_fail(cudaGetLastError(), "forward_solve");
+    }
+
+    static int c_relax(const LevelDev &L, double w, cudaStream_t st) {
+        if (L.ncpts < 2) return 0;
+        const int nin = 3;
+        int grid;
+        if (int rc = grid_for(k_c_relax<Phi>, L.ncpts - 1, nin, &grid)) return rc;
+        k_c_relax<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, w, nin);
+        return cuda_fail(cudaGetLastError(), "c_relax");
+    }
+
+    static int fas_residual(const LevelDev &L, const LevelDev &G, cudaStream_t st) {
+        if (L.ncpts < 2) return 0;
+        const int nin = 4;
+        int grid;
+        if (int rc = grid_for(k_fas_residual<Phi>, L.ncpts - 1, nin, &grid)) return rc;
+        k_fas_residual<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, nin);
+        return cuda_fail(cudaGetLastError(), "fas_residual");
+    }
+
+    static int correct(const LevelDev &L, const LevelDev &G, int frelax, cudaStream_t st) {
+        if (L.ncpts < 1) return 0;
+        const int nin = 3 + rows_extra(L);
+        int grid;
+        if (int rc = grid_for(k_correct<Phi>, L.ncpts, nin, &grid)) return rc;
+        k_correct<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, frelax, nin);
+        return cuda_fail(cudaGetLastError(), "error_correction");
+    }
+
+    static int residual(const LevelDev &L, double *out_sq, cudaStream_t st) {
+        if (L.ncpts < 1) return 0;
+        const int nin = 3;
+        int grid;
+        if (int rc = grid_for(k_residual<Phi>, L.ncpts > 1 ? L.ncpts - 1 : 1, nin, &grid)) return rc;
+        k_residual<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, out_sq, nin);
+        return cuda_fail(cudaGetLastError(), "residual_norms");
+    }
+
+    static int step(const LevelDev &L, int point, const double *in, double *out, cudaStream_t st) {
+        const int nin = 2;
+        int grid;
+        if (int rc = grid_for(k_step<Phi>, 1, nin, &grid)) return rc;
+        k_step<Phi><<<1, Phi::T, smem_bytes(nin), st>>>(L, point, in, out, nin);
+        return cuda_fail(cudaGetLastError(), "step");
+    }
+
+    static const SweepTable *table() {
+        static const SweepTable t = {Phi::T,       Phi::E,   &f_relax, &forward_solve, &c_relax,
+                                     &fas_residual, &correct, &residual, &step};
+        return &t;
+    }
+};
+
+}  // namespace mgb

@@ -1,0 +1,250 @@
+// phi.cuh -- the time integrators Phi as register-resident device functors.
+//
+//  Heat1D      heat/heat_1d.py:198-217       y = (I + dt L)^-1 (u + dt b(x, t_stop)),  L = (a/dx^2) tridiag(-1,2,-1)
+//  Advection1D advection/advection_1d.py:129-143   y = (I + dt L)^-1 u,  L = (c/dx)(I - S_periodic)
+//
+// Both matrices are Toeplitz, so the solve is done without any per-row table:
+//   heat:  (1/r)(I + dt L) = tridiag(-1, delta, -1), delta = 2 + 1/r, = L U + beta e0 e0^T with
+//          L = bidiag(alpha; -1), U = bidiag(1; -beta), alpha + beta = delta, alpha beta = 1, beta < 1.
+//          L and U are inverted by the two constant-coefficient recurrences
+//              y_i = beta (f_i + y_{i-1}),      z_i = y_i + beta z_{i+1},
+//          and the rank-one term by Sherman-Morrison with the closed-form h = (LU)^-1 e0.
+//   advection: y_i = sigma u_i + rho y_{i-1} (cyclic), closed by y_{n-1} = p_{n-1} / (1 - rho^n).
+// Each thread runs the recurrence over its own chunk (split into SUB independent sub-chunks for
+// instruction-level parallelism); the chunk-to-chunk carries are one constant-ratio scan over the
+// team per direction (warp shuffles; shared memory only across warps).  This is the "Thomas inside
+// a lane / parallel scan across lanes" hybrid named in BASELINE.json's north_star.
+#pragma once
+#include "common.cuh"
+
+namespace mgb {
+
+// Kernel-side view of mgb_level (include/mgrit_b200.h).
+struct LevelDev {
+    double *u;
+    double *g;
+    const int *cpts;
+    int ncpts;
+    int npts;
+    int n;
+    int pitch;
+    int ndt;
+    int cw;
+    const int *dtidx;
+    const double *sconst;
+    int nrhs;
+    const double *rhs_x;
+    const double *rhs_t;
+    const double *rhs_dense;
+    const double *t;  // [npts] time values (ODE applications)
+    double p[8];
+    int ip[4];
+};
+
+constexpr int kScalarConsts = 24;  // doubles before the per-thread part of a step-constant row
+
+template <int E>
+struct SubSplit {
+    static constexpr int SUB = (E % 3 == 0) ? 3 : 1;
+    static constexpr int SL = E / SUB;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Heat1D.  Step-constant row layout (doubles), written by mgb_heat1d_step_consts:
+//   [0] beta  [1] beta/r  [2] kappa = beta/(1+beta h0)  [3] beta^SL  [4..8] B^1,2,4,8,16 (B = beta^E)
+//   [9] B^32  [10..10+SL) beta^(jj+1)
+//   [24 + tid*PT ...): B^lane, B^(31-lane), PH[SUB], QH[SUB]      (PT = 2 + 2 SUB)
+// with PH[s] = beta^(tid E + s SL)/(1-beta^2), QH[s] = beta^(2n+1-tid E-(s+1) SL)/(1-beta^2) (0 where
+// the sub-chunk holds no valid element).
+// ---------------------------------------------------------------------------------------------
+template <int T_, int E_>
+struct Heat1D {
+    using SH = Shape<T_, E_>;
+    static constexpr int T = T_, E = E_;
+    static constexpr int SUB = SubSplit<E_>::SUB, SL = SubSplit<E_>::SL;
+    static constexpr int PT = 2 + 2 * SUB;
+    static_assert(SL <= 14, "power table does not fit the scalar block");
+
+    struct C {
+        double beta, cs, kappa, bsl, Bd[5], B32, pw[SL], blf, blb, PH[SUB], QH[SUB];
+    };
+
+    __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int tid) {
+        c.beta = __ldg(row + 0);
+        c.cs = __ldg(row + 1);
+        c.kappa = __ldg(row + 2);
+        c.bsl = __ldg(row + 3);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) c.Bd[k] = __ldg(row + 4 + k);
+        c.B32 = __ldg(row + 9);
+#pragma unroll
+        for (int j = 0; j < SL; ++j) c.pw[j] = __ldg(row + 10 + j);
+        const double *pt = row + kScalarConsts + tid * PT;
+        c.blf = __ldg(pt + 0);
+        c.blb = __ldg(pt + 1);
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) {
+            c.PH[s] = __ldg(pt + 2 + s);
+            c.QH[s] = __ldg(pt + 2 + SUB + s);
+        }
+    }
+
+    // x <- Phi(x) for the step that produces point i.  (the separable right-hand side is added here;
+    // a dense right-hand-side row is added by the caller before.)
+    template <class TeamT>
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const LevelDev &L, int i, TeamT &team) {
+        const int tid = team.tid;
+        const int nv = L.n - tid * E;
+        // b = u + dt * rhs(x, t_i)                                           heat_1d.py:214
+        for (int k = 0; k < L.nrhs; ++k) {
+            const double ct = __ldg(L.rhs_t + (size_t)i * L.nrhs + k);
+            const double *__restrict__ rx = L.rhs_x + (size_t)k * E * T + tid;
+#pragma unroll
+            for (int j = 0; j < E; ++j) x[j] = fma(ct, __ldg(rx + j * T), x[j]);
+        }
+        // f = b * beta / r, forward recurrence y = beta (f + y_prev) inside each sub-chunk
+        double e[SUB];
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) e[s] = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < SL; ++jj) {
+#pragma unroll
+            for (int s = 0; s < SUB; ++s) {
+                const int j = s * SL + jj;
+                e[s] = fma(c.beta, e[s], x[j] * c.cs);
+                x[j] = e[s];
+            }
+        }
+        double a = e[0];
+#pragma unroll
+        for (int s = 1; s < SUB; ++s) a = fma(c.bsl, a, e[s]);
+        double in = team.scan_fwd(a, c.Bd, c.B32, c.blf);
+        // add the inflow, zero the padding
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) {
+#pragma unroll
+            for (int jj = 0; jj < SL; ++jj) {
+                const int j = s * SL + jj;
+                const double y = fma(c.pw[jj], in, x[j]);
+                x[j] = (j < nv) ? y : 0.0;
+            }
+            in = fma(c.bsl, in, e[s]);
+        }
+        // backward recurrence z = y + beta z_next
+        double f[SUB];
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) f[s] = 0.0;
+#pragma unroll
+        for (int jj = SL - 1; jj >= 0; --jj) {
+#pragma unroll
+            for (int s = 0; s < SUB; ++s) {
+                const int j = s * SL + jj;
+                f[s] = fma(c.beta, f[s], x[j]);
+                x[j] = f[s];
+            }
+        }
+        double a2 = f[SUB - 1];
+#pragma unroll
+        for (int s = SUB - 2; s >= 0; --s) a2 = fma(c.bsl, a2, f[s]);
+        double inb[SUB];
+        inb[SUB - 1] = team.scan_bwd(a2, c.Bd, c.B32, c.blb);
+#pragma unroll
+        for (int s = SUB - 2; s >= 0; --s) inb[s] = fma(c.bsl, inb[s + 1], f[s + 1]);
+        // Sherman-Morrison:  x = z - gamma h,  gamma = kappa * z_0
+        const double z0 = team.bcast(fma(c.pw[SL - 1], inb[0], x[0]), 0);
+        const double gamma = c.kappa * z0;
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) {
+            const double Bc = fma(gamma, c.QH[s], inb[s]);
+            const double Ac = -gamma * c.PH[s];
+#pragma unroll
+            for (int jj = 0; jj < SL; ++jj) {
+                const int j = s * SL + jj;
+                x[j] = fma(c.pw[SL - 1 - jj], Bc, fma(c.pw[jj], Ac, x[j]));
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Advection1D.  Step-constant row layout:
+//   [0] rho  [1] sigma  [2] 1/(1-rho^n)  [3] rho^SL  [4..8] B^1,2,4,8,16 (B = rho^E)  [9] B^32
+//   [10..10+SL) rho^(jj+1)
+//   [24 + tid*PT ...): B^lane, (unused), RH[SUB] = rho^(tid E + s SL), (unused)[SUB]
+// ---------------------------------------------------------------------------------------------
+template <int T_, int E_>
+struct Advection1D {
+    using SH = Shape<T_, E_>;
+    static constexpr int T = T_, E = E_;
+    static constexpr int SUB = SubSplit<E_>::SUB, SL = SubSplit<E_>::SL;
+    static constexpr int PT = 2 + 2 * SUB;
+
+    struct C {
+        double rho, sig, dinv, rsl, Bd[5], B32, pw[SL], blf, RH[SUB];
+    };
+
+    __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int tid) {
+        c.rho = __ldg(row + 0);
+        c.sig = __ldg(row + 1);
+        c.dinv = __ldg(row + 2);
+        c.rsl = __ldg(row + 3);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) c.Bd[k] = __ldg(row + 4 + k);
+        c.B32 = __ldg(row + 9);
+#pragma unroll
+        for (int j = 0; j < SL; ++j) c.pw[j] = __ldg(row + 10 + j);
+        const double *pt = row + kScalarConsts + tid * PT;
+        c.blf = __ldg(pt + 0);
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) c.RH[s] = __ldg(pt + 2 + s);
+    }
+
+    template <class TeamT>
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const LevelDev &L, int i, TeamT &team) {
+        const int tid = team.tid;
+        const int last = L.n - 1;
+        const int jstar = last - tid * E;  // position of element n-1 in this thread's chunk (if 0 <= jstar < E)
+        double e[SUB];
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) e[s] = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < SL; ++jj) {
+#pragma unroll
+            for (int s = 0; s < SUB; ++s) {
+                const int j = s * SL + jj;
+                e[s] = fma(c.rho, e[s], x[j] * c.sig);
+                x[j] = e[s];
+            }
+        }
+        double a = e[0];
+#pragma unroll
+        for (int s = 1; s < SUB; ++s) a = fma(c.rsl, a, e[s]);
+        double in = team.scan_fwd(a, c.Bd, c.B32, c.blf);
+        // solution with zero inflow at element 0; pick out its last element
+        double ylast = 0.0;
+        double ins[SUB];
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) {
+            ins[s] = in;
+#pragma unroll
+            for (int jj = 0; jj < SL; ++jj) {
+                const int j = s * SL + jj;
+                const double y = fma(c.pw[jj], in, x[j]);
+                ylast = (j == jstar) ? y : ylast;
+            }
+            in = fma(c.rsl, in, e[s]);
+        }
+        const double Y = team.bcast(ylast, last / E) * c.dinv;  // y_{n-1} of the cyclic system
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) {
+            const double cf = fma(c.RH[s], Y, ins[s]);
+#pragma unroll
+            for (int jj = 0; jj < SL; ++jj) {
+                const int j = s * SL + jj;
+                x[j] = fma(c.pw[jj], cf, x[j]);
+            }
+        }
+    }
+};
+
+}  // namespace mgb

@@ -1,0 +1,28 @@
+// table.h -- one dispatch table per compiled kernel shape (application, threads per system, chunk).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mgb {
+
+struct LevelDev;
+
+struct DeviceInfo {
+    int sms;
+    int max_smem_optin;
+};
+const DeviceInfo *device_info();                 // api.cu; nullptr (and an error message) without a CUDA device
+int cuda_fail(cudaError_t e, const char *what);  // api.cu: records the message, returns MGB_ECUDA or 0
+
+struct SweepTable {
+    int team_threads;
+    int chunk;
+    int (*f_relax)(const LevelDev &, cudaStream_t);
+    int (*forward_solve)(const LevelDev &, cudaStream_t);
+    int (*c_relax)(const LevelDev &, double, cudaStream_t);
+    int (*fas_residual)(const LevelDev &, const LevelDev &, cudaStream_t);
+    int (*correct)(const LevelDev &, const LevelDev &, int, cudaStream_t);
+    int (*residual)(const LevelDev &, double *, cudaStream_t);
+    int (*step)(const LevelDev &, int, const double *, double *, cudaStream_t);
+};
+
+}  // namespace mgb

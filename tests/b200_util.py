@@ -1,0 +1,40 @@
+"""Instantiate a tests/cases.py case against the product package (GPU)."""
+import logging
+
+import numpy as np
+
+import cases as C
+
+
+def b200_apps():
+    import pymgrit_b200 as P
+    apps = {'heat1d': P.Heat1D, 'advection1d': P.Advection1D, 'dahlquist': P.Dahlquist, 'brusselator': P.Brusselator}
+    if hasattr(P, 'Heat2D'):
+        apps['heat2d'] = P.Heat2D
+    return apps
+
+
+def b200_problem(case):
+    apps = b200_apps()
+    grids = C.case_time_grids(case)
+    return [apps[case['app']](t_interval=t, **C.level_app_kw(case, l)) for l, t in enumerate(grids)]
+
+
+def run_b200(name, **extra):
+    import pymgrit_b200 as P
+    case = C.CASES[name]
+    kw = dict(case['solver'])
+    kw.update(extra)
+    solver = P.Mgrit(problem=b200_problem(case), logging_lvl=logging.WARNING, **kw)
+    info = solver.solve()
+    return solver, info
+
+
+def solution_rows(solver, idx=None):
+    """Level-0 solution as host arrays: (rows at idx, per-point 2-norms of all points)."""
+    lv = solver._lv[0]
+    u = lv.u[:, :lv.n].detach().cpu().numpy()
+    shape = lv.app.vector_template.shape
+    norms = np.sqrt(np.sum(u * u, axis=1))
+    rows = u if idx is None else u[idx]
+    return rows.reshape((rows.shape[0],) + tuple(shape)), norms

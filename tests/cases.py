@@ -104,6 +104,15 @@ CASES = {
     'heat1d_nonuniform_t': dict(app='heat1d', app_kw=dict(nx=33, **HEAT),
                                 t_interval=np.linspace(0, 1, 65) ** 1.5 * 2, grids=_simple(3, 2),
                                 solver=dict(tol=1e-9)),
+    # non-uniform coarsening with adjacent C-points (tests/mpi/varying_coarsening.py, on the PDE kernels)
+    'heat1d_varying': dict(app='heat1d', app_kw=dict(nx=40, **HEAT), t=(0, 2, 65),
+                           grids=('index', [np.array([0, 3, 4, 8, 12, 13, 14, 20, 25, 26, 32, 36, 40, 41, 47, 50, 55, 56,
+                                                      60, 64]), slice(None, None, 2)]),
+                           solver=dict(tol=1e-7, nested_iteration=False)),
+    'heat1d_varying_w': dict(app='heat1d', app_kw=dict(nx=40, **HEAT), t=(0, 2, 65),
+                             grids=('index', [np.array([0, 1, 2, 8, 12, 13, 14, 20, 25, 26, 32, 36, 40, 41, 47, 50, 55,
+                                                        56, 60, 64]), slice(None, None, 3)]),
+                             solver=dict(tol=1e-7, weight_c=1.2, cycle_type='F')),
     # right-hand sides: rank-2 separable, and not separable (dense table path)
     'heat1d_rhs_rank2': dict(app='heat1d', app_kw=dict(x_start=0, x_end=1, nx=65, a=0.5, init_cond=heat_init,
                                                        rhs=heat_rhs_rank2),

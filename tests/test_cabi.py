@@ -1,0 +1,96 @@
+"""CPU-side checks of the C ABI: the library loads and exports every symbol include/mgrit_b200.h declares, the host
+helpers behave, and a sweep without a CUDA device fails loudly (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from pymgrit_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def test_exports_every_declared_symbol(lib):
+    from pymgrit_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'mgrit_b200.h')).read()
+    declared = set(re.findall(r'\b(mgb_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.mgb_abi_version() == 1
+
+
+def test_struct_layout_matches_header(lib):
+    from pymgrit_b200 import _lib
+    # offsets implied by include/mgrit_b200.h on LP64
+    assert C.sizeof(_lib.MgbLevel) % 8 == 0
+    assert _lib.MgbLevel.u_dev.offset == 16
+    assert _lib.MgbLevel.p.offset + 8 * 8 == _lib.MgbLevel.ip.offset
+
+
+def test_team_shape_and_consts(lib):
+    from pymgrit_b200 import _lib
+    t, e = C.c_int32(), C.c_int32()
+    assert lib.mgb_team_shape(_lib.APP_HEAT1D, 1023, C.byref(t), C.byref(e)) == 0
+    assert (t.value, e.value) == (32, 33)
+    assert lib.mgb_team_shape(_lib.APP_HEAT1D, 4095, C.byref(t), C.byref(e)) == 0
+    assert t.value * e.value >= 4096
+    assert lib.mgb_team_shape(_lib.APP_HEAT1D, 10 ** 6, C.byref(t), C.byref(e)) == 2
+    assert b'no kernel shape' in lib.mgb_last_error()
+    cw = lib.mgb_step_consts_width(_lib.APP_HEAT1D, 32, 33)
+    row = np.zeros(cw)
+    r = 128.0
+    assert lib.mgb_heat1d_step_consts(r, 1023, 32, 33, row.ctypes.data_as(_lib.c_double_p)) == 0
+    beta = row[0]
+    assert abs(beta + 1 / beta - (2 + 1 / r)) < 1e-14          # root of b^2 - (2 + 1/r) b + 1
+    assert abs(row[1] - beta / r) < 1e-18 and abs(row[3] - beta ** 11) < 1e-15
+    assert lib.mgb_heat1d_step_consts(-1.0, 1023, 32, 33, row.ctypes.data_as(_lib.c_double_p)) == 1
+
+
+def test_heat1d_constants_solve_the_system(lib):
+    """Host-side check of the Toeplitz factorisation the kernel uses: emulate Phi with the table in numpy."""
+    from pymgrit_b200 import _lib
+    n, T, E = 38, 32, 3
+    for r in (0.01, 2.0, 128.0, 2048.0):
+        cw = lib.mgb_step_consts_width(_lib.APP_HEAT1D, T, E)
+        row = np.zeros(cw)
+        assert lib.mgb_heat1d_step_consts(r, n, T, E, row.ctypes.data_as(_lib.c_double_p)) == 0
+        beta, cs, kappa = row[0], row[1], row[2]
+        rng = np.random.default_rng(0)
+        b = rng.standard_normal(n)
+        y = np.zeros(n)
+        acc = 0.0
+        for i in range(n):
+            acc = beta * acc + b[i] * cs
+            y[i] = acc
+        z = np.zeros(n)
+        acc = 0.0
+        for i in range(n - 1, -1, -1):
+            acc = beta * acc + y[i]
+            z[i] = acc
+        i = np.arange(n)
+        h = (beta ** (i + 1.0) - beta ** (2.0 * n + 1 - i)) / (1 - beta * beta)
+        x = z - kappa * z[0] * h
+        A = np.diag(np.full(n, 1 + 2 * r)) + np.diag(np.full(n - 1, -r), 1) + np.diag(np.full(n - 1, -r), -1)
+        assert np.max(np.abs(A @ x - b)) <= 1e-11 * np.max(np.abs(b)) * (1 + 4 * r)
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA device present')
+    from pymgrit_b200 import _lib
+    out = np.zeros(4)
+    rc = lib.mgb_vec_sumsq(4, out.ctypes.data, out.ctypes.data, None)
+    assert rc == 3 and b'CUDA' in lib.mgb_last_error()
+    import pymgrit_b200 as P
+    with pytest.raises(Exception):
+        P.Mgrit(problem=[P.Dahlquist(t_start=0, t_stop=5, nt=11)]).solve()
