@@ -40,10 +40,13 @@ def init_cond(x):
 
 
 WORKLOADS = {
-    # name: (nt, levels, coarsening)
-    'cfg5': (2 ** 20 + 1, 8, 4),
-    'cfg2': (16385, 3, 4),
+    # name: (nt, coarsening factor per level transition).  cfg2 is BASELINE.json configs[1] verbatim; for cfg5 BASELINE
+    # leaves the hierarchy to the builder: (16, 16, 8) -> 513 coarsest points converges in 3 FCF V-cycles and moves
+    # the fewest bytes per cycle of the hierarchies tried (scripts/hierarchy_sweep.py, profiles/r01_hierarchy_sweep.txt).
+    'cfg5': (2 ** 20 + 1, (16, 16, 8)),
+    'cfg2': (16385, (4, 4)),
 }
+CPU_SAMPLE = (2049, (16, 16))      # nt and coarsening of the bounded CPU sample (same problem, same cycle)
 HEAT_KW = dict(x_start=0, x_end=1, nx=1025, a=1, init_cond=init_cond, rhs=rhs, t_start=0, t_stop=2)
 SOLVER_KW = dict(cf_iter=1, cycle_type='V', nested_iteration=True, tol=1e-10)
 
@@ -98,11 +101,25 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(nt_sample, levels, coarsening, solver='spsolve'):
+def hierarchy(make, nt, coarsening):
+    """[fine, coarse, ...]: level l+1 lives on every coarsening[l]-th point of level l (t_interval = t[::m])."""
+    kw = {k: v for k, v in HEAT_KW.items() if k not in ('t_start', 't_stop')}
+    levels = [make(nt=nt, **HEAT_KW)]
+    for m in coarsening:
+        levels.append(make(t_interval=levels[-1].t[::m], **kw))
+    return levels
+
+
+def describe(name, nt, coarsening):
+    return (f'{name}: heat_1d backward Euler nx=1025 nt={nt} on [0,2], {len(coarsening) + 1}-level, coarsening '
+            f'{"x".join(str(m) for m in coarsening)}, FCF V-cycle, nested iteration, tol 1e-10')
+
+
+def cpu_sample(nt_sample, coarsening, solver='spsolve'):
     """Full MGRIT solve of the same problem at reduced nt on one host core; returns (DOF/s, seconds, iterations)."""
     from oracle import mgrit_oracle as O
     t0 = time.time()
-    prob = O.simple_hierarchy(O.Heat1DOracle(solver=solver, nt=nt_sample, **HEAT_KW), levels, coarsening)
+    prob = hierarchy(lambda **kw: O.Heat1DOracle(solver=solver, **kw), nt_sample, coarsening)
     mg = O.MgritOracle(prob, **SOLVER_KW)
     info = mg.solve()
     sec = time.time() - t0
@@ -113,22 +130,24 @@ def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    nt, levels, m = WORKLOADS[args.workload]
-    nt_s, lv_s = 1025, 3                      # ~10 s of reference-style CPU work per step
+    nt, coarsening = WORKLOADS[args.workload]
+    if args.coarsening:
+        coarsening = tuple(int(x) for x in args.coarsening.split(','))
+    nt_s, co_s = CPU_SAMPLE                   # ~10 s of reference-style CPU work per step
     times, its = [], 0
-    for k in range(args.warmup + args.steps):
-        dofs, sec, its = cpu_sample(nt_s, lv_s, m)
-        if k >= args.warmup:
+    warm = min(args.warmup, 1)                # a CPU loop has nothing to warm beyond imports; keeps the run in minutes
+    for k in range(warm + args.steps):
+        dofs, sec, its = cpu_sample(nt_s, co_s)
+        if k >= warm:
             times.append(sec)
     sec = float(np.mean(times))
     val = 1023 * nt_s / sec
-    sample = (f'heat_1d nx=1025 nt={nt_s} {lv_s}-level m={m} FCF V-cycle to 1e-10 ({its} iterations), SciPy SuperLU per step '
-              f'as in the reference; DOF/s is linear in nt')
+    sample = (f'{describe("sample", nt_s, co_s)} ({its} iterations): per-point Python loop + SciPy SuperLU per step as in '
+              f'the reference, 1 core; DOF/s is linear in nt')
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'{args.workload}: heat_1d nx=1025 nt={nt} {levels}-level m={m} FCF V-cycle tol 1e-10',
-                       'sample': sample},
+            'config': {'workload': describe(args.workload, nt, coarsening), 'sample': sample},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
@@ -148,14 +167,16 @@ def gpu_arm(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    nt, levels, m = WORKLOADS[args.workload]
-    if args.levels:
-        levels = args.levels
+    nt, coarsening = WORKLOADS[args.workload]
+    if args.coarsening:
+        coarsening = tuple(int(x) for x in args.coarsening.split(','))
     ndof = 1023
 
     def make_problem():
-        return P.simple_setup_problem(P.Heat1D(nt=nt, **HEAT_KW), level=levels, coarsening=m)
+        return hierarchy(P.Heat1D, nt, coarsening)
 
     def barrier():
         if world > 1:
@@ -222,15 +243,15 @@ def gpu_arm(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            dofs, sec, its = cpu_sample(1025, 3, m)
+            dofs, sec, its = cpu_sample(*CPU_SAMPLE)
             cpu = {'value': dofs, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-                   'sample': f'heat_1d nx=1025 nt=1025 3-level m={m} FCF V-cycle to 1e-10 ({its} iterations, {sec:.1f} s), '
+                   'sample': f'{describe("sample", *CPU_SAMPLE)} ({its} iterations, {sec:.1f} s): per-point Python loop + '
                              f'SciPy SuperLU per step as in the reference; DOF/s is linear in nt'}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic',
-                'config': {'workload': f'{args.workload}: heat_1d nx=1025 nt={nt} {levels}-level m={m} FCF V-cycle nested '
-                                       f'iteration tol 1e-10', 'iterations': iters, 'conv': [float(c) for c in info['conv']],
+                'config': {'workload': describe(args.workload, nt, coarsening), 'iterations': iters,
+                           'conv': [float(c) for c in info['conv']],
                            'l2': 'working set (level 0: %.1f GB) is far larger than L2' % (ndof * nt * 8 / 1e9),
                            'parallelism': f'time-slab x{world}'},
                 'time_to_tolerance_s': ms_step * 1e-3, 'clocks': clocks, 'gpu_launches': launches // args.steps,
@@ -249,7 +270,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--workload', default='cfg5', choices=sorted(WORKLOADS))
-    ap.add_argument('--levels', type=int, default=0)
+    ap.add_argument('--coarsening', default='', help='comma-separated coarsening factors per level (overrides the workload)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

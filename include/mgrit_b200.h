@@ -127,9 +127,15 @@ int mgb_c_relax(const mgb_level *lvl, double weight, void *stream);
  *                 - Phi_c(fine.u[c_{j-1}]). */
 int mgb_fas_residual(const mgb_level *fine, const mgb_level *coarse, void *stream);
 
-/* Coarse-grid correction, mgrit.py:715-726: fine.u[c_j] += coarse.u[j] - v[j], j >= 1, followed, if
- * f_relax != 0, by the F-relaxation of mgrit.py:287 out of the same registers. */
-int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t f_relax, void *stream);
+/* Coarse-grid correction, mgrit.py:715-726: fine.u[c_j] += coarse.u[j] - v[j], j >= 1.  flags:
+ *   MGB_CORRECT_F_RELAX  also run the F-relaxation of mgrit.py:287 out of the same registers (one launch);
+ *   MGB_CORRECT_GHOST    point 0 is the ghost copy of the previous time rank's last C-point (time rank > 0):
+ *                        correct it too, exactly as its owner does, so that no exchange is needed before the
+ *                        F-relaxation of the first interval.  On time rank 0 point 0 is the initial condition
+ *                        and is never corrected (mgrit.py:723). */
+#define MGB_CORRECT_F_RELAX 1
+#define MGB_CORRECT_GHOST 2
+int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t flags, void *stream);
 
 /* Sequential solve on the coarsest level, mgrit.py:459-486: u[i] = (g[i] +) Phi(u[i-1]), i = 1..npts-1. */
 int mgb_forward_solve(const mgb_level *lvl, void *stream);

@@ -107,9 +107,9 @@ def dt_classes(t):
     if len(t) < 2:
         return np.array([1.0]), None
     dt = t[1:] - t[:-1]
+    if np.all(dt == dt[0]):
+        return dt[:1].copy(), None
     uniq, inv = np.unique(dt, return_inverse=True)
-    if len(uniq) == 1:
-        return uniq, None
     idx = np.zeros(len(t), dtype=np.int32)
     idx[1:] = inv
     return uniq, idx

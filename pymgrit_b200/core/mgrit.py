@@ -85,8 +85,9 @@ class Mgrit:
             raise Exception("Cycle-type " + str(cycle_type) + " is not implemented. Choose 'V' or 'F'")
         if output_lvl not in [0, 1, 2]:
             raise Exception("Unknown output level. Choose 0, 1 or 2.")
+        masks = partition.c_point_masks([p.t for p in problem])
         for lvl in range(1, len(problem)):
-            if len(np.intersect1d(problem[lvl - 1].t, problem[lvl].t)) != len(problem[lvl].t):
+            if int(np.count_nonzero(masks[lvl - 1])) != len(np.unique(problem[lvl].t)):
                 raise Exception('Some points from level ' + str(lvl - 1) + ' are not points of level ' + str(lvl))
         if t_norm not in [1, 2, 3]:
             raise Exception('Unknown norm. Please choose 1 (one norm), 2 (two-norm) or 3 (inf-norm)')
@@ -168,7 +169,6 @@ class Mgrit:
         self.cpts = part.cpts
         self.index_local = part.index_local
         self.index_local_c = part.index_local_c
-        self.index_local_f = part.index_local_f
         self.t = part.t_local
         self.int_start, self.int_stop = part.int_start, part.int_stop
         self.send_to, self.get_from = part.send_to, part.get_from
@@ -230,7 +230,8 @@ class Mgrit:
         """Forget the current iterate and redo the setup sweeps (initial guess, nested iteration) with the level tables
         that are already in HBM.  Not in the reference (which rebuilds everything); used by bench.py."""
         for lv in self._lv:
-            lv.u.zero_()
+            if not self.nes_it:
+                lv.u.zero_()         # with nested iteration every point is written before it is read
             if lv.g is not None:
                 lv.g.zero_()
         self.conv = np.zeros(self.iter_max + 1)
@@ -314,9 +315,10 @@ class Mgrit:
 
     def error_correction(self, lvl: int, f_relax: bool = False) -> None:
         """Coarse-grid correction of the C-points (mgrit.py:715-726), optionally fused with the next F-relaxation."""
-        _lib.check(_lib.lib().mgb_error_correction(self._lv[lvl].ref, self._lv[lvl + 1].ref, 1 if f_relax else 0,
-                                                   self._stream()), 'error_correction')
-        self._exchange_ghost(lvl)
+        flags = (1 if f_relax else 0) | (2 if self.comm_time_rank > 0 else 0)      # MGB_CORRECT_F_RELAX | MGB_CORRECT_GHOST
+        _lib.check(_lib.lib().mgb_error_correction(self._lv[lvl].ref, self._lv[lvl + 1].ref, flags, self._stream()),
+                   'error_correction')
+        # no exchange: every rank corrects its ghost copy itself (MGB_CORRECT_GHOST)
 
     def forward_solve(self, lvl: int) -> None:
         """Sequential time stepping on level lvl (mgrit.py:459-486)."""
@@ -425,6 +427,11 @@ class Mgrit:
         self.ouput_run_information()
         return {'conv': self.conv[np.where(self.conv != 0)], 'time_setup': self.runtime_setup,
                 'time_solve': self.runtime_solve}
+
+    @property
+    def index_local_f(self):
+        """Local indices of the F-points per level, in the reference's visiting order (mgrit.py:171, 802)."""
+        return self._part.index_local_f
 
     # helpers kept for API compatibility (mgrit.py:728-740, 829-838)
     def split_into(self, number_points: int, number_processes: int) -> np.ndarray:

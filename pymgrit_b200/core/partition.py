@@ -33,7 +33,17 @@ def c_point_masks(global_t):
     """is_c[l][i]: point i of level l is also a point of level l+1 (mgrit.py:212, 768-770); all True on the coarsest."""
     masks = []
     for l, t in enumerate(global_t):
-        masks.append(np.isin(t, global_t[l + 1]) if l + 1 < len(global_t) else np.ones(len(t), dtype=bool))
+        if l + 1 == len(global_t):
+            masks.append(np.ones(len(t), dtype=bool))
+            continue
+        tc = global_t[l + 1]
+        mask = np.zeros(len(t), dtype=bool)
+        if np.all(t[1:] > t[:-1]):                       # sorted grid: binary search instead of np.isin's sort
+            idx = np.minimum(np.searchsorted(t, tc), len(t) - 1)
+            mask[idx[t[idx] == tc]] = True
+        else:
+            mask = np.isin(t, tc)
+        masks.append(mask)
     return masks
 
 
@@ -56,12 +66,12 @@ def _f_groups_reversed(fpts):
     """F-points grouped into runs of consecutive indices, runs in reverse order (mgrit.py:774-776)."""
     if len(fpts) == 0:
         return np.array([], dtype=float)
-    breaks = np.flatnonzero(np.diff(fpts) != 1) + 1
-    runs = np.split(fpts, breaks)
-    return np.concatenate(runs[::-1])
+    run_id = np.zeros(len(fpts), dtype=np.int64)
+    run_id[1:] = np.cumsum(np.diff(fpts) != 1)
+    return fpts[np.argsort(-run_id, kind='stable')]
 
 
-def _level_tables(global_t, masks, lvl, size, rank, window):
+def _level_tables(global_t, masks, lvl, size, rank, window, lazy_f=False):
     """Tables of one level for the owner of the level-0 index window [first, last] (inclusive)."""
     t = global_t[lvl]
     n = len(t)
@@ -84,9 +94,12 @@ def _level_tables(global_t, masks, lvl, size, rank, window):
     ghost = rank != 0 and len(own) > 0
     with_ghost = np.concatenate([[own[0] - 1], own]) if ghost else own
     off = 1 if ghost else 0
+    def f_list():
+        return (_f_groups_reversed(fpts) - own[0] + off) if len(fpts) else np.array([], dtype=float)
+
     pos = {'index_local': np.arange(len(own)) + off,
            'index_local_c': (cpts - own[0] + off) if len(own) else cpts,
-           'index_local_f': (_f_groups_reversed(fpts) - own[0] + off) if len(fpts) else np.array([], dtype=float)}
+           'index_local_f': f_list if lazy_f else f_list()}
 
     def is_f(i):
         return 0 <= i < n and not is_c[i]
@@ -155,16 +168,17 @@ class Partition:
         last = int(bounds[rank])
         self.window = (first, last)
         self.int_start, self.int_stop = t0[first], t0[last]
-        self.t_local, self.cpts, self.index_local, self.index_local_c, self.index_local_f = [], [], [], [], []
+        self.t_local, self.cpts, self.index_local, self.index_local_c, self._f_lists = [], [], [], [], []
+        self.masks = masks
         self.sweep_cpts, self.send_to, self.get_from, self.owned = [], [], [], []
         for lvl in range(L):
-            own, with_ghost, cpts, pos, _ = _level_tables(global_t, masks, lvl, size, rank, (first, last))
+            own, with_ghost, cpts, pos, _ = _level_tables(global_t, masks, lvl, size, rank, (first, last), lazy_f=True)
             self.owned.append(own)
             self.t_local.append(global_t[lvl][with_ghost])
             self.cpts.append(cpts)
             self.index_local.append(pos['index_local'])
             self.index_local_c.append(pos['index_local_c'])
-            self.index_local_f.append(pos['index_local_f'])
+            self._f_lists.append(pos['index_local_f'])
             # C-points as the sweeps want them: local indices, starting with point 0 (initial condition or ghost)
             lc = np.asarray(pos['index_local_c'], dtype=np.int64)
             if rank != 0:
@@ -172,3 +186,9 @@ class Partition:
             self.sweep_cpts.append(lc.astype(np.int32))
             self.send_to.append(rank + 1 if rank + 1 < size else -99)
             self.get_from.append(rank - 1 if rank > 0 else -99)
+
+    @property
+    def index_local_f(self):
+        """Local F-point lists in the reference's visiting order; built on first use (the sweeps do not need them)."""
+        self._f_lists = [f() if callable(f) else f for f in self._f_lists]
+        return self._f_lists

@@ -4,7 +4,7 @@ The reference evaluates `rhs(self.x, t_stop)` inside every step (heat/heat_1d.py
 cannot call Python, so the callable is turned into tables once per level:
 
   separable   b(x, t) = sum_k T_k(t) X_k(x), k < q <= MAX_TERMS.  Found numerically: sample b at a
-              few times, take the row space (SVD), pick q well-conditioned spatial points (pivoted
+              few times, take the row space (pivoted QR), pick q well-conditioned spatial points (pivoted
               QR) and get T_k(t_i) for every time point from b at those q points only.  The kernel
               then adds dt_i * sum_k T_k(t_i) X_k(x) out of an L1-resident table: no HBM traffic.
   dense       anything else: one row b(x, t_i) * dt_i per time point, streamed like the FAS rows.
@@ -45,12 +45,14 @@ class RhsSplit:
         if scale == 0.0 and not np.any(_rows(self.rhs, self.x, mid)):
             self.kind = 'zero'
             return self
-        _, s, vt = np.linalg.svd(R, full_matrices=False)
-        q = int(np.sum(s > 1e-13 * s[0]))
+        # row space of the samples by pivoted QR (rank-revealing enough here, and far cheaper than an SVD)
+        qmat, rmat, _ = qr(R.T, mode='economic', pivoting=True)
+        diag = np.abs(np.diag(rmat))
+        q = int(np.sum(diag > 1e-13 * diag[0]))
         if q > MAX_TERMS or q >= len(sample_t):
             self.kind = 'dense'
             return self
-        basis = vt[:q]                                            # orthonormal rows spanning b(., t)
+        basis = np.ascontiguousarray(qmat[:, :q].T)              # orthonormal rows spanning b(., t)
         _, _, piv = qr(basis, pivoting=True, mode='economic')
         sel = np.sort(piv[:q])
         self.basis, self.sel = basis, sel
@@ -76,7 +78,7 @@ class RhsSplit:
             vals = None
         if vals is None:
             vals = np.stack([_eval(self.rhs, self.x, float(tt))[self.sel] for tt in t])
-        return np.linalg.solve(self.basis[:, self.sel].T, vals.T).T
+        return vals @ np.linalg.inv(self.basis[:, self.sel])      # q x q system, q <= MAX_TERMS
 
     def dense(self, t):
         return _rows(self.rhs, self.x, np.asarray(t, dtype=float))

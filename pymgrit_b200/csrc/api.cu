@@ -163,28 +163,29 @@ __global__ void k_copy_rows(const double *__restrict__ src, double *__restrict__
         dst[q] = src[q];
 }
 
-// single CTA, fixed-order reduction -> deterministic
+// single CTA, fixed-order reduction -> deterministic.  Four independent accumulators per thread keep enough loads in
+// flight that the single CTA is not latency-bound on a 2 MB input.
+__device__ __forceinline__ double tn_map(double v, int mode) { return mode == MGB_TNORM_TWO ? v : sqrt(v); }
+__device__ __forceinline__ double tn_comb(double a, double b, int mode) { return mode == MGB_TNORM_INF ? fmax(a, b) : a + b; }
+
 __global__ void k_temporal_norm(const double *__restrict__ sq, int count, int mode, double *__restrict__ out) {
-    double acc = 0.0;
-    for (int q = threadIdx.x; q < count; q += blockDim.x) {
-        const double v = sq[q];
-        if (mode == MGB_TNORM_TWO)
-            acc += v;
-        else if (mode == MGB_TNORM_ONE)
-            acc += sqrt(v);
-        else
-            acc = fmax(acc, sqrt(v));
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int T = blockDim.x;
+    int q = threadIdx.x;
+    for (; q + 3 * T < count; q += 4 * T) {
+        const double v0 = sq[q], v1 = sq[q + T], v2 = sq[q + 2 * T], v3 = sq[q + 3 * T];
+        a0 = tn_comb(a0, tn_map(v0, mode), mode);
+        a1 = tn_comb(a1, tn_map(v1, mode), mode);
+        a2 = tn_comb(a2, tn_map(v2, mode), mode);
+        a3 = tn_comb(a3, tn_map(v3, mode), mode);
     }
+    for (; q < count; q += T) a0 = tn_comb(a0, tn_map(sq[q], mode), mode);
+    double acc = tn_comb(tn_comb(a0, a1, mode), tn_comb(a2, a3, mode), mode);
     __shared__ double s[1024];
     s[threadIdx.x] = acc;
     __syncthreads();
     for (int d = blockDim.x >> 1; d >= 1; d >>= 1) {
-        if ((int)threadIdx.x < d) {
-            if (mode == MGB_TNORM_INF)
-                s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + d]);
-            else
-                s[threadIdx.x] += s[threadIdx.x + d];
-        }
+        if ((int)threadIdx.x < d) s[threadIdx.x] = tn_comb(s[threadIdx.x], s[threadIdx.x + d], mode);
         __syncthreads();
     }
     if (threadIdx.x == 0) out[0] = s[0];
@@ -334,13 +335,13 @@ int mgb_fas_residual(const mgb_level *fine, const mgb_level *coarse, void *strea
     return tab->fas_residual(L, G, st);
 }
 
-int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t f_relax, void *stream) {
+int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t flags, void *stream) {
     MGB_PROLOGUE(fine)
     const SweepTable *tab2 = nullptr;
     LevelDev G;
     if (int rc = check_level(coarse, &tab2, &G)) return rc;
     if (int rc = check_pair(fine, coarse)) return rc;
-    return tab->correct(L, G, f_relax, st);
+    return tab->correct(L, G, (flags & MGB_CORRECT_F_RELAX) ? 1 : 0, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
 }
 
 int mgb_forward_solve(const mgb_level *lvl, void *stream) {

@@ -71,12 +71,12 @@ struct Launch {
         return cuda_fail(cudaGetLastError(), "fas_residual");
     }
 
-    static int correct(const LevelDev &L, const LevelDev &G, int frelax, cudaStream_t st) {
+    static int correct(const LevelDev &L, const LevelDev &G, int frelax, int kfirst, cudaStream_t st) {
         if (L.ncpts < 1) return 0;
         const int nin = 3 + rows_extra(L);
         int grid;
         if (int rc = grid_for(k_correct<Phi>, L.ncpts, nin, &grid)) return rc;
-        k_correct<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, frelax, nin);
+        k_correct<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, frelax, kfirst, nin);
         return cuda_fail(cudaGetLastError(), "error_correction");
     }
 

@@ -119,16 +119,31 @@ struct Heat1D {
 #pragma unroll
         for (int s = 1; s < SUB; ++s) a = fma(c.bsl, a, e[s]);
         double in = team.scan_fwd(a, c.Bd, c.B32, c.blf);
-        // add the inflow, zero the padding
+        // add the inflow; everything beyond element n-1 must stay exactly 0 for the backward recurrence
+        if (L.n % E == 0) {
+            // no thread holds a partially valid chunk (e.g. n = 1023 = 31 x 33): threads beyond n have zero data, so
+            // cutting their inflow keeps them at 0 without a select per element
+            in = (nv > 0) ? in : 0.0;
 #pragma unroll
-        for (int s = 0; s < SUB; ++s) {
+            for (int s = 0; s < SUB; ++s) {
 #pragma unroll
-            for (int jj = 0; jj < SL; ++jj) {
-                const int j = s * SL + jj;
-                const double y = fma(c.pw[jj], in, x[j]);
-                x[j] = (j < nv) ? y : 0.0;
+                for (int jj = 0; jj < SL; ++jj) {
+                    const int j = s * SL + jj;
+                    x[j] = fma(c.pw[jj], in, x[j]);
+                }
+                in = fma(c.bsl, in, e[s]);
             }
-            in = fma(c.bsl, in, e[s]);
+        } else {
+#pragma unroll
+            for (int s = 0; s < SUB; ++s) {
+#pragma unroll
+                for (int jj = 0; jj < SL; ++jj) {
+                    const int j = s * SL + jj;
+                    const double y = fma(c.pw[jj], in, x[j]);
+                    x[j] = (j < nv) ? y : 0.0;
+                }
+                in = fma(c.bsl, in, e[s]);
+            }
         }
         // backward recurrence z = y + beta z_next
         double f[SUB];

@@ -303,22 +303,27 @@ __global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const
 
 // ------------------------------------------------------------------------------------------------
 // Coarse-grid correction (mgrit.py:722-726) fused with the F-relaxation that follows (mgrit.py:287):
-//   for interval k:  if k >= 1: u[c] = u[c] + (G.u[k] - u[c]);   then, if f_relax, the chain from u[c]
+//   for interval k:  if k >= kfirst: u[c] = u[c] + (G.u[k] - u[c]);   then, if f_relax, the chain from u[c].
+// kfirst = 1 on time rank 0 (point 0 is the initial condition).  On the other ranks point 0 is the ghost copy of the
+// previous rank's last C-point and kfirst = 0: the ghost is corrected here with the same arithmetic its owner uses
+// (the coarse ghost row is already current), so the F-relaxation of the first interval starts from the corrected
+// value without waiting for an exchange.
 // ------------------------------------------------------------------------------------------------
 struct GenCorrect {
     LevelDev L, G;
     int item, nitems, stride;
     int s, e, i, stage;
     bool frelax;
-    __device__ GenCorrect(const LevelDev &L_, const LevelDev &G_, int first, int nitems_, int stride_, bool fr)
-        : L(L_), G(G_), item(first), nitems(nitems_), stride(stride_), s(0), e(0), i(0), stage(-2), frelax(fr) {}
+    int kfirst;
+    __device__ GenCorrect(const LevelDev &L_, const LevelDev &G_, int first, int nitems_, int stride_, bool fr, int kf)
+        : L(L_), G(G_), item(first), nitems(nitems_), stride(stride_), s(0), e(0), i(0), stage(-2), frelax(fr), kfirst(kf) {}
     __device__ bool next(const double *&p) {
         for (;;) {
             if (item >= nitems) return false;
             if (stage == -2) {
                 interval_of(L, item, s, e);
                 const bool chain = frelax && (e - s > 1);
-                if (item == 0 && !chain) {
+                if (item < kfirst && !chain) {
                     item += stride;
                     continue;
                 }
@@ -329,7 +334,7 @@ struct GenCorrect {
             if (stage == -1) {
                 stage = 0;
                 i = s + 1;
-                if (item >= 1) {
+                if (item >= kfirst) {
                     p = G.u + (size_t)item * G.pitch;
                     return true;
                 }
@@ -347,11 +352,12 @@ struct GenCorrect {
 };
 
 template <class Phi>
-__global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const LevelDev G, const int frelax, const int nin) {
+__global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const LevelDev G, const int frelax, const int kfirst,
+                                                    const int nin) {
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenCorrect> pipe(g_smem, nin, L.pitch, L.n, GenCorrect(L, G, blockIdx.x, L.ncpts, gridDim.x, frelax != 0));
+    RowPipe<SH, GenCorrect> pipe(g_smem, nin, L.pitch, L.n, GenCorrect(L, G, blockIdx.x, L.ncpts, gridDim.x, frelax != 0, kfirst));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
@@ -359,10 +365,10 @@ __global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const Leve
         int s, e;
         interval_of(L, k, s, e);
         const bool chain = frelax && (e - s > 1);
-        if (k == 0 && !chain) continue;
+        if (k < kfirst && !chain) continue;
         double x[E];
         pipe.pop(x, team);
-        if (k >= 1) {
+        if (k >= kfirst) {
             double cu[E];
             pipe.pop(cu, team);
 #pragma unroll

@@ -20,7 +20,7 @@ struct SweepTable {
     int (*forward_solve)(const LevelDev &, cudaStream_t);
     int (*c_relax)(const LevelDev &, double, cudaStream_t);
     int (*fas_residual)(const LevelDev &, const LevelDev &, cudaStream_t);
-    int (*correct)(const LevelDev &, const LevelDev &, int, cudaStream_t);
+    int (*correct)(const LevelDev &, const LevelDev &, int, int, cudaStream_t);
     int (*residual)(const LevelDev &, double *, cudaStream_t);
     int (*step)(const LevelDev &, int, const double *, double *, cudaStream_t);
 };

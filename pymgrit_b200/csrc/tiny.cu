@@ -151,13 +151,13 @@ __global__ void kt_fas(const LevelDev L, const LevelDev G) {
 }
 
 template <class P>
-__global__ void kt_correct(const LevelDev L, const LevelDev G, int frelax) {
+__global__ void kt_correct(const LevelDev L, const LevelDev G, int frelax, int kfirst) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.ncpts; k += gridDim.x * blockDim.x) {
         int s, e;
         tiny_interval(L, k, s, e);
         double x[P::N];
         ld<P>(x, L.u, s, L.pitch);
-        if (k >= 1) {
+        if (k >= kfirst) {
 #pragma unroll
             for (int q = 0; q < P::N; ++q) x[q] = ADD(x[q], SUB(G.u[(size_t)k * G.pitch + q], x[q]));
             st<P>(x, L.u, s, L.pitch);
@@ -233,9 +233,9 @@ struct TinyLaunch {
         kt_fas<P><<<grid(L.ncpts), 128, 0, st>>>(L, G);
         return cuda_fail(cudaGetLastError(), "fas_residual");
     }
-    static int correct(const LevelDev &L, const LevelDev &G, int fr, cudaStream_t st) {
+    static int correct(const LevelDev &L, const LevelDev &G, int fr, int kfirst, cudaStream_t st) {
         if (device_info() == nullptr) return MGB_ECUDA;
-        kt_correct<P><<<grid(L.ncpts), 128, 0, st>>>(L, G, fr);
+        kt_correct<P><<<grid(L.ncpts), 128, 0, st>>>(L, G, fr, kfirst);
         return cuda_fail(cudaGetLastError(), "error_correction");
     }
     static int residual(const LevelDev &L, double *out, cudaStream_t st) {

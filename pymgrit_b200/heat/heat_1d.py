@@ -39,7 +39,9 @@ class Heat1D(DeviceApplication):
         self.init_cond = init_cond
         self.vector_t_start = VectorHeat1D(self.nx)
         self.vector_t_start.set_values(np.asarray(self.init_cond(self.x), dtype=float))
-        self._rhs_split = None
+        # device representation of rhs(x, t), analysed once here so that the deep copies made by
+        # simple_setup_problem share it
+        self._rhs_split = RhsSplit(self.rhs, self.x).analyse(self.t)
 
     def level_tables(self, t, team_threads, chunk):
         fac = self.a / self.dx ** 2                                   # heat_1d.py:185
@@ -47,8 +49,6 @@ class Heat1D(DeviceApplication):
         tab = dict(ndt=len(dts), dtidx=dtidx,
                    sconst=dl.step_const_table(self.kind, dts * fac, self.nx, team_threads, chunk))
         tab['cw'] = tab['sconst'].shape[1]
-        if self._rhs_split is None:
-            self._rhs_split = RhsSplit(self.rhs, self.x).analyse(t)
         split = self._rhs_split
         dt_full = np.zeros(len(t))
         dt_full[1:] = np.diff(t)
