@@ -34,14 +34,15 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 1
+#define MGB_ABI_VERSION 2
 
 /* application kinds (which Phi) */
 #define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
 #define MGB_APP_ADVECTION1D 2 /* advection/advection_1d.py:129-143   implicit upwind, cyclic bidiagonal     */
 #define MGB_APP_DAHLQUIST 3   /* dahlquist/dahlquist.py:88-111       scalar BE / FE / TR / MR                */
 #define MGB_APP_BRUSSELATOR 4 /* brusselator/brusselator.py:105-132  classical RK4 on 2 components           */
-#define MGB_APP_HEAT2D 5      /* heat/heat_2d.py:322-366 (BE branch) 5-point Laplacian, Dirichlet data      */
+#define MGB_APP_HEAT2D 5      /* heat/heat_2d.py:322-366 (BE branch) 5-point Laplacian, Dirichlet data;     */
+                              /* rows are kept in sine space (see mgb_heat2d_to_rows)                         */
 
 /* error codes */
 #define MGB_OK 0
@@ -85,14 +86,19 @@ typedef struct mgb_level {
 
     /* right-hand side of the PDE, b(x, t_i) * dt_i = sum_k rhs_t[i][k] * rhs_x[k][x]  (heat only) */
     int32_t nrhs;           /* number of separable terms; 0 = homogeneous                         */
-    int32_t reserved0;
+    int32_t nsys;           /* independent systems per row: 0/1 for the 1-D applications; HEAT2D: */
+                            /* tiles of pitch/nsys doubles (mgb_heat2d_layout)                    */
     const double *rhs_x_dev;/* [nrhs][chunk][team_threads]: spatial factors, thread-transposed    */
+                            /* (HEAT2D: [nrhs][pitch] in row layout, at most 3 terms)             */
     const double *rhs_t_dev;/* [npts][nrhs]: time factors already multiplied by dt_i              */
     const double *rhs_dense_dev; /* [npts][pitch] b(x,t_i)*dt_i for non-separable data, or NULL   */
 
     const double *t_dev;    /* [npts] time values of the level's points (needed by the ODE apps)  */
     double p[8];            /* application scalars (dahlquist: p[0] = lambda)                     */
-    int32_t ip[4];          /* application integers (dahlquist: ip[0] = method)                   */
+    int32_t ip[4];          /* application integers (dahlquist: ip[0] = method; heat2d: ip[0] =   */
+                            /* first tile of boundary nodes)                                      */
+    const double *sig_dev;  /* HEAT2D: [pitch] fx*lambda_k + fy*mu_l per sine coefficient, the    */
+                            /* Dirichlet value per boundary node, 0 in the padding; else NULL     */
 } mgb_level;
 
 int mgb_abi_version(void);
@@ -114,8 +120,13 @@ int mgb_advection1d_step_consts(double nu, int32_t n, int32_t team_threads, int3
 /* ---- sweeps (one launch covers every coarse interval of the level) -------------------------- */
 
 /* F-relaxation, mgrit.py:292-333: for every C-point c and every F-point i that follows it,
- * u[i] = (g[i] +) Phi(u[i-1]). */
-int mgb_f_relax(const mgb_level *lvl, void *stream);
+ * u[i] = (g[i] +) Phi(u[i-1]).  flags:
+ *   MGB_F_RELAX_LAST_ONLY  store only the last F-point of every interval.  In the down-sweep of a cycle
+ *                          (mgrit.py:274-281) nothing reads the other F-points before the F-relaxation after the
+ *                          coarse-grid correction (mgrit.py:287) overwrites them, so their stores are skipped;
+ *                          the values that are stored are bit-identical. */
+#define MGB_F_RELAX_LAST_ONLY 1
+int mgb_f_relax(const mgb_level *lvl, int32_t flags, void *stream);
 
 /* C-relaxation, mgrit.py:335-370: for every C-point c != 0,
  * u[c] = w * ((g[c] +) Phi(u[c-1])) + (1 - w) * u[c]. */
@@ -141,7 +152,8 @@ int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t
 int mgb_forward_solve(const mgb_level *lvl, void *stream);
 
 /* Space-time residual at the C-points of level 0, mgrit.py:387-413: out_sq_dev[j] = ||Phi(u[c_j-1]) -
- * u[c_j]||_2^2 for j >= 1 (out_sq_dev[0] = 0). */
+ * u[c_j]||_2^2 for j >= 1 (out_sq_dev[0] = 0).  out_sq_dev holds ncpts doubles, or ncpts * (1 + nsys) when the
+ * level has nsys > 1 systems per row (the per-system partial sums are kept behind the results). */
 int mgb_residual_norms(const mgb_level *lvl, double *out_sq_dev, void *stream);
 
 /* Jump criterion, mgrit.py:372-385: out_sq_dev[j] = ||u[c_j] - last[c_j]||_2^2 for j >= 1, then
@@ -156,8 +168,25 @@ int mgb_temporal_norm(const double *sq_dev, int32_t count, int32_t t_norm, doubl
 int mgb_inject_up(const mgb_level *fine, const mgb_level *coarse, void *stream);
 
 /* One application of Phi for Application.step (heat_1d.py:198 etc.): out = Phi(in) for the step that
- * produces point `point` of the level (its dt and right-hand side). */
+ * produces point `point` of the level (its dt and right-hand side).  in/out are rows in the level's layout. */
 int mgb_step(const mgb_level *lvl, int32_t point, const double *in_dev, double *out_dev, void *stream);
+
+/* ---- Heat2D: node arrays <-> level rows (heat/heat_2d.py:20-136, 322-366) --------------------- */
+/* Row layout for an (nx, ny) node grid: (nx-2)(ny-2) sine coefficients, zero padding to a whole tile, the
+ * 2 ny + 2 (nx-2) boundary values (row i = 0, row i = nx-1, column j = 0, column j = ny-1), zero padding.
+ * tile = doubles per system, nsys = tiles per row, first_boundary_sys = first tile of boundary values,
+ * pitch = nsys * tile. */
+int mgb_heat2d_layout(int32_t nx, int32_t ny, int32_t *tile, int32_t *nsys, int32_t *first_boundary_sys, int32_t *pitch);
+
+/* rows[b] = layout( Sx * nodes[b]_interior * Sy, nodes[b]_boundary ), b < count.  sx_dev [(nx-2)^2] and sy_dev
+ * [(ny-2)^2] are the orthonormal sine matrices S[j][k] = sqrt(2/(n+1)) sin(pi (j+1)(k+1)/(n+1)); nodes_dev is
+ * [count][nx*ny] (VectorHeat2D.get_values(), heat_2d.py:105-110), rows_dev [count][pitch], work_dev
+ * [count][(nx-2)(ny-2)] scratch. */
+int mgb_heat2d_to_rows(int32_t nx, int32_t ny, const double *sx_dev, const double *sy_dev, const double *nodes_dev,
+                       double *rows_dev, int32_t count, double *work_dev, void *stream);
+/* The inverse: nodes[b] from rows[b]. */
+int mgb_heat2d_from_rows(int32_t nx, int32_t ny, const double *sx_dev, const double *sy_dev, const double *rows_dev,
+                         double *nodes_dev, int32_t count, double *work_dev, void *stream);
 
 /* ---- Vector arithmetic (core/vector.py:38-110) ---------------------------------------------- */
 /* out = a*x + b*y on n doubles */

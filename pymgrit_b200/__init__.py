@@ -12,6 +12,7 @@ from pymgrit_b200.core.grid_transfer_copy import GridTransferCopy
 from pymgrit_b200.core.simple_setup_problem import simple_setup_problem
 from pymgrit_b200.core.mgrit import Mgrit
 from pymgrit_b200.heat.heat_1d import Heat1D, VectorHeat1D
+from pymgrit_b200.heat.heat_2d import Heat2D, VectorHeat2D
 from pymgrit_b200.advection.advection_1d import Advection1D, VectorAdvection1D
 from pymgrit_b200.dahlquist.dahlquist import Dahlquist, VectorDahlquist
 from pymgrit_b200.brusselator.brusselator import Brusselator, VectorBrusselator

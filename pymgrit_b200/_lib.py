@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libmgrit_b200.so')
 
 APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D = 1, 2, 3, 4, 5
 TNORM_ONE, TNORM_TWO, TNORM_INF = 1, 2, 3
+ABI_VERSION = 2
+F_RELAX_LAST_ONLY = 1
 DAHLQUIST_METHODS = {'BE': 0, 'FE': 1, 'TR': 2, 'MR': 3}
 
 c_double_p = C.POINTER(C.c_double)
@@ -26,10 +28,11 @@ class MgbLevel(C.Structure):
         ('ncpts', C.c_int32), ('team_threads', C.c_int32), ('chunk', C.c_int32),
         ('ndt', C.c_int32), ('cw', C.c_int32),
         ('dtidx_dev', C.c_void_p), ('sconst_dev', C.c_void_p),
-        ('nrhs', C.c_int32), ('reserved0', C.c_int32),
+        ('nrhs', C.c_int32), ('nsys', C.c_int32),
         ('rhs_x_dev', C.c_void_p), ('rhs_t_dev', C.c_void_p), ('rhs_dense_dev', C.c_void_p),
         ('t_dev', C.c_void_p),
         ('p', C.c_double * 8), ('ip', C.c_int32 * 4),
+        ('sig_dev', C.c_void_p),
     ]
 
 
@@ -42,7 +45,7 @@ SYMBOLS = {
     'mgb_step_consts_width': (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     'mgb_heat1d_step_consts': (C.c_int, [C.c_double, C.c_int32, C.c_int32, C.c_int32, c_double_p]),
     'mgb_advection1d_step_consts': (C.c_int, [C.c_double, C.c_int32, C.c_int32, C.c_int32, c_double_p]),
-    'mgb_f_relax': (C.c_int, [_LP, C.c_void_p]),
+    'mgb_f_relax': (C.c_int, [_LP, C.c_int32, C.c_void_p]),
     'mgb_c_relax': (C.c_int, [_LP, C.c_double, C.c_void_p]),
     'mgb_fas_residual': (C.c_int, [_LP, _LP, C.c_void_p]),
     'mgb_error_correction': (C.c_int, [_LP, _LP, C.c_int32, C.c_void_p]),
@@ -52,6 +55,11 @@ SYMBOLS = {
     'mgb_temporal_norm': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'mgb_inject_up': (C.c_int, [_LP, _LP, C.c_void_p]),
     'mgb_step': (C.c_int, [_LP, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mgb_heat2d_layout': (C.c_int, [C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
+    'mgb_heat2d_to_rows': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.c_void_p, C.c_void_p]),
+    'mgb_heat2d_from_rows': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_void_p]),
     'mgb_vec_axpby': (C.c_int, [C.c_int32, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_vec_sumsq': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
@@ -71,7 +79,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.mgb_abi_version() != 1:
+        if handle.mgb_abi_version() != ABI_VERSION:
             raise ImportError('libmgrit_b200.so has an unexpected ABI version')
         _lib = handle
     return _lib

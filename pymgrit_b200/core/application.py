@@ -80,6 +80,15 @@ class DeviceApplication(Application):
     def level_tables(self, t: np.ndarray, team_threads: int, chunk: int) -> dict:
         raise NotImplementedError
 
+    # values <-> level rows.  rows: [count, pitch] tensor; values: [count, *vector shape] tensor.  The 1-D and ODE
+    # applications store the values themselves at the start of a row.
+    def rows_to_values(self, rows):
+        shape = tuple(self.vector_template.shape)
+        return rows[:, :self.ndof].view((rows.shape[0],) + shape)
+
+    def values_to_rows(self, values, rows) -> None:
+        rows[:, :self.ndof].copy_(values.reshape(rows.shape[0], self.ndof))
+
     def step(self, u_start, t_start: float, t_stop: float):
         from pymgrit_b200.core.device_level import single_step
         return single_step(self, u_start, t_start, t_stop)

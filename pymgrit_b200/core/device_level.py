@@ -40,9 +40,9 @@ class DeviceLevel:
         self.app = app
         self.t = np.asarray(t, dtype=float)
         self.npts = len(self.t)
-        self.n = int(app.ndof)
+        self.n = int(app.ndof)                            # doubles of a row that carry values
         tiny = app.kind in (_lib.APP_DAHLQUIST, _lib.APP_BRUSSELATOR)
-        self.pitch = self.n if tiny else self.n + (self.n & 1)
+        self.pitch = int(app.row_pitch()) if hasattr(app, 'row_pitch') else (self.n if tiny else self.n + (self.n & 1))
         self.team_threads, self.chunk = team_shape(app.kind, self.n)
         tab = app.level_tables(self.t, self.team_threads, self.chunk)
         self._keep = []                                   # tensors referenced by the struct
@@ -64,10 +64,16 @@ class DeviceLevel:
         self.t_dev = up(self.t, np.float64)
         sconst = up(tab.get('sconst'), np.float64)
         dtidx = up(tab.get('dtidx'), np.int32)
-        rhs_x = up(tab.get('rhs_x'), np.float64)
+        # tables an application family shares between its levels are handed over as device tensors
+        rhs_x = tab['rhs_x_dev'] if tab.get('rhs_x_dev') is not None else up(tab.get('rhs_x'), np.float64)
         rhs_t = up(tab.get('rhs_t'), np.float64)
+        sig = tab.get('sig_dev')
+        self._keep += [t_ for t_ in (rhs_x, sig) if t_ is not None]
         rhs_dense = None
-        if tab.get('rhs_dense') is not None:
+        if tab.get('rhs_dense_dev') is not None:
+            rhs_dense = tab['rhs_dense_dev']
+            self._keep.append(rhs_dense)
+        elif tab.get('rhs_dense') is not None:
             dense = np.zeros((self.npts, self.pitch))
             dense[:, :self.n] = tab['rhs_dense']
             rhs_dense = up(dense, np.float64)
@@ -83,6 +89,9 @@ class DeviceLevel:
         c.ndt, c.cw = int(tab.get('ndt', 1)), int(tab.get('cw', 0))
         c.dtidx_dev, c.sconst_dev = ptr(dtidx), ptr(sconst)
         c.nrhs = int(tab.get('nrhs', 0))
+        c.nsys = int(tab.get('nsys', 1))
+        c.sig_dev = ptr(sig)
+        self.nsys = c.nsys
         c.rhs_x_dev, c.rhs_t_dev, c.rhs_dense_dev = ptr(rhs_x), ptr(rhs_t), ptr(rhs_dense)
         c.t_dev = ptr(self.t_dev)
         for k, v in enumerate(tab.get('p', [])):
@@ -95,10 +104,26 @@ class DeviceLevel:
     def ref(self):
         return C.byref(self.c)
 
-    def row(self, arr, i):
-        """View of time point i as a tensor of the application's vector shape."""
+    # -- values <-> rows (identity for every application except Heat2D, whose rows are in sine space) ----------
+    def get_vector(self, arr, i):
+        """Time point i of a level array as a Vector of the application (a view where the layout allows it)."""
+        return self.app.vector_template._new(self.app.rows_to_values(arr[i:i + 1])[0])
+
+    def set_vector(self, arr, i, vec):
         shape = self.app.vector_template.shape
-        return arr[i, :self.n].view(shape if shape else ())
+        self.app.values_to_rows(vec.device_values.reshape((1,) + tuple(shape)), arr[i:i + 1])
+
+    def values(self, arr=None, idx=None, chunk=64):
+        """Host array [points, *vector shape] of the values at points idx (all by default)."""
+        arr = self.u if arr is None else arr
+        idx = np.arange(self.npts) if idx is None else np.atleast_1d(np.asarray(idx))
+        shape = tuple(self.app.vector_template.shape)
+        out = np.empty((len(idx),) + shape)
+        torch = _torch()
+        for a in range(0, len(idx), chunk):
+            sel = torch.as_tensor(idx[a:a + chunk], device=arr.device, dtype=torch.long)
+            out[a:a + chunk] = self.app.rows_to_values(arr.index_select(0, sel)).cpu().numpy()
+        return out
 
 
 def dt_classes(t):
@@ -134,10 +159,10 @@ def single_step(app, u_start, t_start, t_stop):
             cache.clear()
         lvl = DeviceLevel(app, np.array(key))
         cache[key] = lvl
-    x = u_start.device_values.reshape(-1)
-    buf_in = torch.zeros(lvl.pitch, dtype=torch.float64, device=x.device)
-    buf_in[:lvl.n] = x
+    shape = tuple(app.vector_template.shape)
+    x = u_start.device_values
+    buf_in = torch.zeros((1, lvl.pitch), dtype=torch.float64, device=x.device)
+    app.values_to_rows(x.reshape((1,) + shape), buf_in)
     buf_out = torch.zeros_like(buf_in)
     _lib.check(_lib.lib().mgb_step(lvl.ref, 1, buf_in.data_ptr(), buf_out.data_ptr(), _lib.current_stream_ptr()), 'step')
-    shape = app.vector_template.shape
-    return app.vector_template._new(buf_out[:lvl.n].view(shape if shape else ()))
+    return app.vector_template._new(app.rows_to_values(buf_out)[0])

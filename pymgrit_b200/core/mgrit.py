@@ -45,13 +45,13 @@ class _LevelVectors:
             i += len(self)
         if not 0 <= i < len(self):
             raise IndexError(i)
-        return self._level.app.vector_template._new(self._level.row(self._array(), i))
+        return self._level.get_vector(self._array(), i)
 
     def __setitem__(self, i, vec):
         i = int(i)
         if i < 0:
             i += len(self)
-        self._level.row(self._array(), i).copy_(vec.device_values.reshape(self._level.app.vector_template.shape))
+        self._level.set_vector(self._array(), i, vec)
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
@@ -183,7 +183,8 @@ class Mgrit:
         torch = _lib_torch()
         dev = self._lv[0].u.device
         ncp0 = len(self._lv[0].cpts) if self._lv[0].cpts is not None else 1
-        self._sq = torch.zeros(max(ncp0, 1), dtype=torch.float64, device=dev)
+        nsys0 = self._lv[0].nsys
+        self._sq = torch.zeros(max(ncp0, 1) * (1 + nsys0 if nsys0 > 1 else 1), dtype=torch.float64, device=dev)
         self._norm_out = torch.zeros(1, dtype=torch.float64, device=dev)
         self._norm_host = torch.zeros(1, dtype=torch.float64).pin_memory()
 
@@ -209,13 +210,13 @@ class Mgrit:
         if self.random_init_guess:
             lv = self._lv[0]
             shape = lv.app.vector_template.shape
-            vals = np.stack([np.random.rand(*shape).reshape(-1) if shape else np.random.rand(1)
-                             for _ in range(lv.npts)])
-            lv.u[:, :lv.n] = _lib_torch().as_tensor(vals).to(lv.u.device)
+            vals = np.stack([np.random.rand(*shape) if shape else np.random.rand(1) for _ in range(lv.npts)])
+            for a in range(0, lv.npts, 64):
+                lv.app.values_to_rows(_lib_torch().as_tensor(vals[a:a + 64]).to(lv.u.device), lv.u[a:a + 64])
         if self.comm_time_rank == 0:
             for lv in self._lv:
                 if lv.npts > 0:
-                    lv.row(lv.u, 0).copy_(lv.app.vector_t_start.device_values.reshape(lv.app.vector_template.shape))
+                    lv.set_vector(lv.u, 0, lv.app.vector_t_start)
 
     def log_info(self, message: str) -> None:
         """Only the last time rank logs (mgrit.py:247-259)."""
@@ -297,9 +298,11 @@ class Mgrit:
         if lvl != 0 and cycle_type == 'F':
             self.iteration(lvl=lvl, cycle_type='V', iteration=iteration, first_f=False)
 
-    def f_relax(self, lvl: int) -> None:
-        """F-relaxation (mgrit.py:292-333): one launch over all coarse intervals."""
-        _lib.check(_lib.lib().mgb_f_relax(self._lv[lvl].ref, self._stream()), 'f_relax')
+    def f_relax(self, lvl: int, last_only: bool = False) -> None:
+        """F-relaxation (mgrit.py:292-333): one launch over all coarse intervals.  last_only: store only the last
+        F-point of every interval (down-sweep of a cycle, where the other F-points are never read)."""
+        flags = _lib.F_RELAX_LAST_ONLY if last_only else 0
+        _lib.check(_lib.lib().mgb_f_relax(self._lv[lvl].ref, flags, self._stream()), 'f_relax')
 
     def c_relax(self, lvl: int) -> None:
         """C-relaxation (mgrit.py:335-370)."""

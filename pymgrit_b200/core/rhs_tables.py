@@ -19,37 +19,69 @@ MAX_TERMS = 4
 _SAMPLES = 12
 
 
-def _eval(rhs, x, t):
-    val = np.asarray(rhs(x, t), dtype=float)
-    return np.broadcast_to(val, np.shape(x)).astype(float)
+class Sampler1D:
+    """b(x, t) on the 1-D grid x (heat/heat_1d.py:214: rhs(self.x, t_stop))."""
+
+    def __init__(self, rhs, x):
+        self.rhs, self.x = rhs, np.asarray(x, dtype=float)
+        self.size = len(self.x)
+
+    def full(self, t):
+        val = np.asarray(self.rhs(self.x, t), dtype=float)
+        return np.broadcast_to(val, np.shape(self.x)).astype(float)
+
+    def subset(self, sel, t):
+        """b at the points sel for all times t in one broadcast call: [len(t), len(sel)]."""
+        return np.asarray(self.rhs(self.x[sel][None, :], t[:, None]), dtype=float)
 
 
-def _rows(rhs, x, times):
-    return np.stack([_eval(rhs, x, float(tt)) for tt in times]) if len(times) else np.zeros((0, len(x)))
+class Sampler2D:
+    """b(x, y, t) on the interior nodes, flattened row-major (heat/heat_2d.py:301-303:
+    rhs(x=self.x_2d[1:-1], y=self.y_2d[:, 1:-1], t=t_stop))."""
+
+    def __init__(self, rhs, x, y):
+        self.rhs = rhs
+        self.xi, self.yi = np.asarray(x, dtype=float)[1:-1], np.asarray(y, dtype=float)[1:-1]
+        self.shape = (len(self.xi), len(self.yi))
+        self.size = self.shape[0] * self.shape[1]
+
+    def full(self, t):
+        val = np.asarray(self.rhs(x=self.xi[:, None], y=self.yi[None, :], t=t), dtype=float)
+        return np.broadcast_to(val, self.shape).astype(float).reshape(-1)
+
+    def subset(self, sel, t):
+        xs, ys = self.xi[sel // self.shape[1]], self.yi[sel % self.shape[1]]
+        return np.asarray(self.rhs(x=xs[None, :], y=ys[None, :], t=t[:, None]), dtype=float)
 
 
 class RhsSplit:
     """kind: 'zero' | 'separable' | 'dense'."""
 
-    def __init__(self, rhs, x):
-        self.rhs, self.x = rhs, np.asarray(x, dtype=float)
+    def __init__(self, rhs, x=None, sampler=None, max_terms=MAX_TERMS):
+        self.sampler = sampler if sampler is not None else Sampler1D(rhs, x)
+        self.max_terms = max_terms
         self.kind, self.basis, self.sel = None, None, None
+
+    def _rows(self, times):
+        if len(times) == 0:
+            return np.zeros((0, self.sampler.size))
+        return np.stack([self.sampler.full(float(tt)) for tt in times])
 
     def analyse(self, t):
         t = np.asarray(t, dtype=float)
         pick = np.unique(np.round(np.linspace(0, len(t) - 1, min(len(t), _SAMPLES))).astype(int))
         sample_t = t[pick]
         mid = 0.5 * (sample_t[:-1] + sample_t[1:]) if len(sample_t) > 1 else sample_t
-        R = _rows(self.rhs, self.x, sample_t)
+        R = self._rows(sample_t)
         scale = np.max(np.abs(R)) if R.size else 0.0
-        if scale == 0.0 and not np.any(_rows(self.rhs, self.x, mid)):
+        if scale == 0.0 and not np.any(self._rows(mid)):
             self.kind = 'zero'
             return self
         # row space of the samples by pivoted QR (rank-revealing enough here, and far cheaper than an SVD)
         qmat, rmat, _ = qr(R.T, mode='economic', pivoting=True)
         diag = np.abs(np.diag(rmat))
         q = int(np.sum(diag > 1e-13 * diag[0]))
-        if q > MAX_TERMS or q >= len(sample_t):
+        if q > self.max_terms or q >= len(sample_t):
             self.kind = 'dense'
             return self
         basis = np.ascontiguousarray(qmat[:, :q].T)              # orthonormal rows spanning b(., t)
@@ -57,7 +89,7 @@ class RhsSplit:
         sel = np.sort(piv[:q])
         self.basis, self.sel = basis, sel
         # verify on times that were not used to build the basis
-        check = _rows(self.rhs, self.x, mid)
+        check = self._rows(mid)
         coef = self.coefficients(mid)
         err = np.max(np.abs(coef @ basis - check)) if check.size else 0.0
         self.kind = 'separable' if err <= 1e-13 * max(scale, np.max(np.abs(check)) if check.size else 0.0) else 'dense'
@@ -66,19 +98,29 @@ class RhsSplit:
     def coefficients(self, t):
         """T_k(t_i) for every t_i: shape (len(t), q)."""
         t = np.asarray(t, dtype=float)
-        xs = self.x[self.sel]
         vals = None
         try:                                   # one broadcast call when the callable allows it
-            cand = np.asarray(self.rhs(xs[None, :], t[:, None]), dtype=float)
-            if cand.shape == (len(t), len(xs)):
+            cand = self.sampler.subset(self.sel, t)
+            if cand.shape == (len(t), len(self.sel)):
                 probe = np.unique(np.array([0, len(t) // 2, len(t) - 1]))
-                ok = all(np.array_equal(cand[i], _eval(self.rhs, self.x, float(t[i]))[self.sel]) for i in probe)
+                ok = all(np.array_equal(cand[i], self.sampler.full(float(t[i]))[self.sel]) for i in probe)
                 vals = cand if ok else None
         except Exception:
             vals = None
         if vals is None:
-            vals = np.stack([_eval(self.rhs, self.x, float(tt))[self.sel] for tt in t])
+            vals = np.stack([self.sampler.full(float(tt))[self.sel] for tt in t])
         return vals @ np.linalg.inv(self.basis[:, self.sel])      # q x q system, q <= MAX_TERMS
 
     def dense(self, t):
-        return _rows(self.rhs, self.x, np.asarray(t, dtype=float))
+        return self._rows(np.asarray(t, dtype=float))
+
+    def reproduces(self, t, samples=3):
+        """True if the separable form matches direct evaluations at a few of the times t (used when a level adopts
+        the split another level of the same problem has analysed)."""
+        if self.kind != 'separable':
+            return False
+        t = np.asarray(t, dtype=float)
+        pick = t[np.unique(np.round(np.linspace(0, len(t) - 1, min(len(t), samples))).astype(int))]
+        direct = self._rows(pick)
+        scale = max(np.max(np.abs(direct)), 1e-300)
+        return bool(np.max(np.abs(self.coefficients(pick) @ self.basis - direct)) <= 1e-12 * scale)

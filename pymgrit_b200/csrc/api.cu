@@ -19,6 +19,8 @@ static int fail(int code, const char *fmt, const char *a = "", long b = 0, long 
     return code;
 }
 
+int heat2d_fail(const char *msg) { return fail(MGB_EINVAL, "%s", msg); }
+
 int cuda_fail(cudaError_t e, const char *what) {
     if (e == cudaSuccess) return MGB_OK;
     snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
@@ -48,6 +50,7 @@ const DeviceInfo *device_info() {
 // ---- compiled shapes --------------------------------------------------------------------------------
 #define MGB_APP_Heat1D MGB_APP_HEAT1D
 #define MGB_APP_Advection1D MGB_APP_ADVECTION1D
+#define MGB_APP_Heat2D MGB_APP_HEAT2D
 #define MGB_SHAPE(APP, T, E) const SweepTable *mgb_table_##APP##_##T##_##E();
 #include "shapes.inc"
 #undef MGB_SHAPE
@@ -75,7 +78,16 @@ static int check_level(const mgb_level *l, const SweepTable **tab, LevelDev *out
     if (l->n < 1 || l->pitch < l->n || l->npts < 1 || l->u_dev == nullptr)
         return fail(MGB_EINVAL, "bad level geometry%s (n=%ld, npts=%ld)", "", l->n, l->npts);
     const bool tiny = (l->app == MGB_APP_DAHLQUIST || l->app == MGB_APP_BRUSSELATOR);
-    if (!tiny) {
+    const bool multi = (l->app == MGB_APP_HEAT2D);
+    if (multi) {
+        const long tl = (long)l->team_threads * l->chunk;
+        if (l->nsys < 1 || (long)l->nsys * tl != l->pitch || l->n != l->pitch)
+            return fail(MGB_EINVAL, "heat2d rows must be whole tiles%s (pitch %ld, nsys %ld)", "", l->pitch, l->nsys);
+        if (l->sig_dev == nullptr || l->sconst_dev == nullptr || l->ndt < 1 || (l->ndt > 1 && l->dtidx_dev == nullptr))
+            return fail(MGB_EINVAL, "missing heat2d symbol or step-constant table%s");
+        if (l->nrhs < 0 || l->nrhs > kHeat2DMaxTerms || (l->nrhs > 0 && (l->rhs_x_dev == nullptr || l->rhs_t_dev == nullptr)))
+            return fail(MGB_EINVAL, "heat2d takes at most 3 separable right-hand-side terms%s (got %ld)", "", l->nrhs);
+    } else if (!tiny) {
         if (l->pitch % 2) return fail(MGB_EINVAL, "pitch must be even%s (got %ld)", "", l->pitch);
         if ((long)l->team_threads * l->chunk < l->pitch)
             return fail(MGB_EINVAL, "team shape%s %ld x %ld does not cover a row", "", l->team_threads, l->chunk);
@@ -105,6 +117,11 @@ static int check_level(const mgb_level *l, const SweepTable **tab, LevelDev *out
     out->t = l->t_dev;
     for (int k = 0; k < 8; ++k) out->p[k] = l->p[k];
     for (int k = 0; k < 4; ++k) out->ip[k] = l->ip[k];
+    out->nsys = multi ? l->nsys : 1;
+    out->tile = multi ? l->team_threads * l->chunk : l->pitch;
+    out->nrow = l->n;
+    out->sig = multi ? l->sig_dev : nullptr;
+    if (multi) out->n = out->tile;
     if (tiny && l->t_dev == nullptr) return fail(MGB_EINVAL, "ODE applications need the time grid t_dev%s");
     return MGB_OK;
 }
@@ -116,6 +133,13 @@ static int check_pair(const mgb_level *f, const mgb_level *c) {
     if (f->cpts_dev == nullptr || c->npts < f->ncpts)
         return fail(MGB_EINVAL, "coarse level has fewer points than the fine level has C-points%s");
     if (c->g_dev == nullptr) return fail(MGB_EINVAL, "coarse level needs a g array%s");
+    if (f->app == MGB_APP_HEAT2D) {
+        // one spatial operator for the whole hierarchy: the item data loaded for the fine step serves the coarse step
+        if (f->nsys != c->nsys || f->sig_dev != c->sig_dev || f->ip[0] != c->ip[0])
+            return fail(MGB_EINVAL, "heat2d levels must share the symbol table%s");
+        if (c->nrhs != 0 && (c->nrhs != f->nrhs || c->rhs_x_dev != f->rhs_x_dev))
+            return fail(MGB_EINVAL, "heat2d levels must share the right-hand-side factors%s");
+    }
     return MGB_OK;
 }
 
@@ -228,6 +252,15 @@ int mgb_team_shape(int32_t app, int32_t n, int32_t *team_threads, int32_t *chunk
         *chunk = n;
         return MGB_OK;
     }
+    if (app == MGB_APP_HEAT2D) {  // elementwise in sine space: one tile shape for every grid size
+        for (const ShapeEntry &s : g_shapes)
+            if (s.app == app) {
+                *team_threads = s.T;
+                *chunk = s.E;
+                return MGB_OK;
+            }
+        return fail(MGB_ENOSHAPE, "no heat2d kernels compiled%s");
+    }
     const int pitch = n + (n & 1);
     long best = -1;
     for (const ShapeEntry &s : g_shapes) {
@@ -245,7 +278,7 @@ int mgb_team_shape(int32_t app, int32_t n, int32_t *team_threads, int32_t *chunk
 }
 
 int mgb_step_consts_width(int32_t app, int32_t team_threads, int32_t chunk) {
-    (void)app;
+    if (app == MGB_APP_HEAT2D) return 8;  // [0] dt
     const int sub = (chunk % 3 == 0) ? 3 : 1;
     return kScalarConsts + team_threads * (2 + 2 * sub);
 }
@@ -314,10 +347,10 @@ int mgb_advection1d_step_consts(double nu_, int32_t n, int32_t T, int32_t E, dou
     if (int rc = check_level(lvl, &tab, &L)) return rc; \
     cudaStream_t st = (cudaStream_t)stream;
 
-int mgb_f_relax(const mgb_level *lvl, void *stream) {
+int mgb_f_relax(const mgb_level *lvl, int32_t flags, void *stream) {
     MGB_PROLOGUE(lvl)
     if (L.cpts == nullptr) return fail(MGB_EINVAL, "f_relax needs the C-point table%s");
-    return tab->f_relax(L, st);
+    return tab->f_relax(L, flags, st);
 }
 
 int mgb_c_relax(const mgb_level *lvl, double weight, void *stream) {
@@ -361,10 +394,10 @@ int mgb_jump_norms(const mgb_level *lvl, double *last_dev, double *out_sq_dev, v
     if (L.cpts == nullptr || last_dev == nullptr || out_sq_dev == nullptr) return fail(MGB_EINVAL, "bad argument%s");
     const DeviceInfo *di = device_info();
     if (di == nullptr) return MGB_ECUDA;
-    const int threads = L.n >= 256 ? 256 : 32 * ((L.n + 31) / 32);
+    const int threads = L.nrow >= 256 ? 256 : 32 * ((L.nrow + 31) / 32);
     int grid = L.ncpts - 1 < 8 * di->sms ? L.ncpts - 1 : 8 * di->sms;
     if (grid < 1) grid = 1;
-    k_jump<<<grid, threads, 0, st>>>(L.u, last_dev, L.cpts, L.ncpts, L.npts, L.n, L.pitch, out_sq_dev);
+    k_jump<<<grid, threads, 0, st>>>(L.u, last_dev, L.cpts, L.ncpts, L.npts, L.nrow, L.pitch, out_sq_dev);
     const size_t count = (size_t)L.npts * L.pitch;
     k_copy_rows<<<4 * di->sms, 256, 0, st>>>(L.u, last_dev, count);
     return cuda_fail(cudaGetLastError(), "jump_norms");
@@ -387,9 +420,9 @@ int mgb_inject_up(const mgb_level *fine, const mgb_level *coarse, void *stream) 
     const DeviceInfo *di = device_info();
     if (di == nullptr) return MGB_ECUDA;
     if (L.ncpts < 2) return MGB_OK;
-    const int threads = L.n >= 256 ? 256 : 32 * ((L.n + 31) / 32);
+    const int threads = L.nrow >= 256 ? 256 : 32 * ((L.nrow + 31) / 32);
     const int grid = L.ncpts - 1 < 8 * di->sms ? L.ncpts - 1 : 8 * di->sms;
-    k_inject_up<<<grid, threads, 0, st>>>(L.u, coarse->u_dev, L.cpts, L.ncpts, L.n, L.pitch);
+    k_inject_up<<<grid, threads, 0, st>>>(L.u, coarse->u_dev, L.cpts, L.ncpts, L.nrow, L.pitch);
     return cuda_fail(cudaGetLastError(), "inject_up");
 }
 

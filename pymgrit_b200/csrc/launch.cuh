@@ -31,13 +31,15 @@ struct Launch {
     }
 
     static int rows_extra(const LevelDev &L) { return (L.g ? 1 : 0) + (L.rhs_dense ? 1 : 0); }
+    static int nsys(const LevelDev &L) { return L.nsys > 1 ? L.nsys : 1; }
 
-    static int f_relax(const LevelDev &L, cudaStream_t st) {
+    // flags & 1: store only the last point of every interval (the other F-points are dead in a down-sweep)
+    static int f_relax(const LevelDev &L, int flags, cudaStream_t st) {
         if (L.ncpts < 1) return 0;
-        const int nin = 2 + rows_extra(L);
+        const int nin = 2 + rows_extra(L), nw = L.ncpts * nsys(L);
         int grid;
-        if (int rc = grid_for(k_chain<Phi>, L.ncpts, nin, &grid)) return rc;
-        k_chain<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, L.ncpts, nin);
+        if (int rc = grid_for(k_chain<Phi>, nw, nin, &grid)) return rc;
+        k_chain<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, nw, flags & 1, nin);
         return cuda_fail(cudaGetLastError(), "f_relax");
     }
 
@@ -46,54 +48,57 @@ struct Launch {
         L.cpts = nullptr;  // one interval [0, npts)
         L.ncpts = 0;
         if (L.npts < 2) return 0;
-        const int nin = 4;
+        const int nin = 4, nw = nsys(L);
         int grid;
-        if (int rc = grid_for(k_chain<Phi>, 1, nin, &grid)) return rc;
-        k_chain<Phi><<<1, Phi::T, smem_bytes(nin), st>>>(L, 1, nin);
+        if (int rc = grid_for(k_chain<Phi>, nw, nin, &grid)) return rc;
+        k_chain<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, nw, 0, nin);
         return cuda_fail(cudaGetLastError(), "forward_solve");
     }
 
     static int c_relax(const LevelDev &L, double w, cudaStream_t st) {
         if (L.ncpts < 2) return 0;
-        const int nin = 3;
+        const int nin = 3, nw = (L.ncpts - 1) * nsys(L);
         int grid;
-        if (int rc = grid_for(k_c_relax<Phi>, L.ncpts - 1, nin, &grid)) return rc;
-        k_c_relax<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, w, nin);
+        if (int rc = grid_for(k_c_relax<Phi>, nw, nin, &grid)) return rc;
+        k_c_relax<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, w, nw, nin);
         return cuda_fail(cudaGetLastError(), "c_relax");
     }
 
     static int fas_residual(const LevelDev &L, const LevelDev &G, cudaStream_t st) {
         if (L.ncpts < 2) return 0;
-        const int nin = 4;
+        const int nin = 4, nw = (L.ncpts - 1) * nsys(L);
         int grid;
-        if (int rc = grid_for(k_fas_residual<Phi>, L.ncpts - 1, nin, &grid)) return rc;
-        k_fas_residual<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, nin);
+        if (int rc = grid_for(k_fas_residual<Phi>, nw, nin, &grid)) return rc;
+        k_fas_residual<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, nw, nin);
         return cuda_fail(cudaGetLastError(), "fas_residual");
     }
 
     static int correct(const LevelDev &L, const LevelDev &G, int frelax, int kfirst, cudaStream_t st) {
         if (L.ncpts < 1) return 0;
-        const int nin = 3 + rows_extra(L);
+        const int nin = 3 + rows_extra(L), nw = L.ncpts * nsys(L);
         int grid;
-        if (int rc = grid_for(k_correct<Phi>, L.ncpts, nin, &grid)) return rc;
-        k_correct<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, frelax, kfirst, nin);
+        if (int rc = grid_for(k_correct<Phi>, nw, nin, &grid)) return rc;
+        k_correct<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, frelax, kfirst, nw, nin);
         return cuda_fail(cudaGetLastError(), "error_correction");
     }
 
+    // out_sq holds ncpts doubles; with several systems per row, ncpts * (1 + nsys) (partials behind the results)
     static int residual(const LevelDev &L, double *out_sq, cudaStream_t st) {
         if (L.ncpts < 1) return 0;
-        const int nin = 3;
+        const int nin = 3, nw = (L.ncpts > 1 ? L.ncpts - 1 : 0) * nsys(L);
         int grid;
-        if (int rc = grid_for(k_residual<Phi>, L.ncpts > 1 ? L.ncpts - 1 : 1, nin, &grid)) return rc;
-        k_residual<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, out_sq, nin);
+        if (int rc = grid_for(k_residual<Phi>, nw > 0 ? nw : 1, nin, &grid)) return rc;
+        k_residual<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, out_sq, nw, nin);
+        if (nsys(L) > 1 && L.ncpts > 1) k_sum_systems<Phi><<<(L.ncpts + 127) / 128, 128, 0, st>>>(out_sq, L.ncpts, L.nsys);
         return cuda_fail(cudaGetLastError(), "residual_norms");
     }
 
+    // in / out: rows in the level's layout
     static int step(const LevelDev &L, int point, const double *in, double *out, cudaStream_t st) {
-        const int nin = 2;
+        const int nin = 2, nw = nsys(L);
         int grid;
-        if (int rc = grid_for(k_step<Phi>, 1, nin, &grid)) return rc;
-        k_step<Phi><<<1, Phi::T, smem_bytes(nin), st>>>(L, point, in, out, nin);
+        if (int rc = grid_for(k_step<Phi>, nw, nin, &grid)) return rc;
+        k_step<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, point, in, out, nw, nin);
         return cuda_fail(cudaGetLastError(), "step");
     }
 

@@ -39,7 +39,16 @@ struct LevelDev {
     const double *t;  // [npts] time values (ODE applications)
     double p[8];
     int ip[4];
+    // independent spatial systems per row (sweeps.cuh: work items).  n = dofs of ONE system, tile = doubles between two
+    // systems of a row = length of the slice a team moves, nrow = dofs of the whole row (n for the 1-D applications)
+    int nsys;
+    int tile;
+    int nrow;
+    const double *sig;  // [pitch] per-element symbol of the spatial operator (Heat2D), row layout; NULL otherwise
 };
+
+// Applications without per-element item data
+struct NoItem {};
 
 constexpr int kScalarConsts = 24;  // doubles before the per-thread part of a step-constant row
 
@@ -91,8 +100,13 @@ struct Heat1D {
 
     // x <- Phi(x) for the step that produces point i.  (the separable right-hand side is added here;
     // a dense right-hand-side row is added by the caller before.)
+    using Item = NoItem;
+    template <class Pipe, class TeamT>
+    __device__ static __forceinline__ void begin_item(Item &, const LevelDev &, int, Pipe &, TeamT &) {}
+
     template <class TeamT>
-    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const LevelDev &L, int i, TeamT &team) {
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &, const LevelDev &L, int i,
+                                                 TeamT &team) {
         const int tid = team.tid;
         const int nv = L.n - tid * E;
         // b = u + dt * rhs(x, t_i)                                           heat_1d.py:214
@@ -214,8 +228,13 @@ struct Advection1D {
         for (int s = 0; s < SUB; ++s) c.RH[s] = __ldg(pt + 2 + s);
     }
 
+    using Item = NoItem;
+    template <class Pipe, class TeamT>
+    __device__ static __forceinline__ void begin_item(Item &, const LevelDev &, int, Pipe &, TeamT &) {}
+
     template <class TeamT>
-    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const LevelDev &L, int i, TeamT &team) {
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &, const LevelDev &L, int i,
+                                                 TeamT &team) {
         const int tid = team.tid;
         const int last = L.n - 1;
         const int jstar = last - tid * E;  // position of element n-1 in this thread's chunk (if 0 <= jstar < E)
@@ -259,6 +278,71 @@ struct Advection1D {
                 x[j] = fma(c.pw[jj], cf, x[j]);
             }
         }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Heat2D (backward Euler), heat/heat_2d.py:289-320, 360-366, in sine space.
+//
+// The reference solves (I + dt L) y = b with the 5-point Laplacian L on the interior nodes and identity rows on the
+// boundary nodes (whose values are the Dirichlet data, whatever the input was).  L = fx Tx (x) I + fy I (x) Ty with
+// Toeplitz tridiag(-1, 2, -1) factors, which the orthonormal sine transforms Sx, Sy diagonalise exactly.  Every other
+// operation of MGRIT (sums, differences, injection, 2-norms) is linear or orthogonally invariant, so the whole
+// hierarchy is kept in sine space: a level row holds  [Sx U_interior Sy | padding | boundary values | padding]  and
+//     Phi(x)_e = (x_e + sum_k ct_k(i) rx_k,e) / (1 + dt_i sig_e)            interior coefficient e = (k, l)
+//     Phi(x)_e = bc_e                                                        boundary node
+// with sig_e = fx lambda_k + fy mu_l, rx = the transformed spatial factors of the right-hand side (plus the constant
+// coupling of the interior to the boundary data), ct_k(i) = dt_i T_k(t_i).  Rows are cut into tiles of T*E elements;
+// a tile is one "system" (no coupling between elements), tiles >= ip[0] hold boundary nodes and `sig` holds bc there.
+// Transforms happen only where values enter or leave the solver (csrc/heat2d.cu).
+//   step-constant row: [0] dt
+// ---------------------------------------------------------------------------------------------
+constexpr int kHeat2DMaxTerms = 3;
+
+template <int T_, int E_>
+struct Heat2D {
+    using SH = Shape<T_, E_>;
+    static constexpr int T = T_, E = E_;
+    static constexpr int QMAX = kHeat2DMaxTerms;
+
+    struct C {
+        double dt;
+    };
+    struct Item {
+        double sig[E];
+        double rx[QMAX][E];
+        bool boundary;
+    };
+
+    __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int) { c.dt = __ldg(row); }
+
+    template <class Pipe, class TeamT>
+    __device__ static __forceinline__ void begin_item(Item &it, const LevelDev &L, int sys, Pipe &pipe, TeamT &team) {
+        pipe.pop(it.sig, team);
+#pragma unroll
+        for (int k = 0; k < QMAX; ++k)
+            if (k < L.nrhs) pipe.pop(it.rx[k], team);
+        it.boundary = sys >= L.ip[0];
+    }
+
+    template <class TeamT>
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &it, const LevelDev &L, int i,
+                                                 TeamT &) {
+        if (it.boundary) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) x[j] = it.sig[j];
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < QMAX; ++k) {
+            if (k < L.nrhs) {
+                const double ct = __ldg(L.rhs_t + (size_t)i * L.nrhs + k);
+#pragma unroll
+                for (int j = 0; j < E; ++j) x[j] = fma(ct, it.rx[k][j], x[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < E; ++j) x[j] = __ddiv_rn(x[j], fma(c.dt, it.sig[j], 1.0));
     }
 };
 

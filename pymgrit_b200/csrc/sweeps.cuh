@@ -27,6 +27,35 @@ __device__ __forceinline__ void interval_of(const LevelDev &L, int k, int &s, in
     }
 }
 
+// Work items.  A row of a level holds `nsys` independent spatial systems of `tile` doubles each (1 for the 1-D
+// applications; the sine-space tiles of Heat2D).  Work item w of a sweep = (interval or C-point kbase + w / nsys,
+// system w % nsys); `soff` is the offset of the system inside a row.
+struct ItemPos {
+    int k, sys;
+    size_t soff;
+};
+__device__ __forceinline__ ItemPos item_pos(const LevelDev &L, int w, int kbase = 0) {
+    ItemPos ip;
+    if (L.nsys <= 1) {
+        ip.k = kbase + w;
+        ip.sys = 0;
+        ip.soff = 0;
+    } else {
+        const int q = w / L.nsys;
+        ip.k = kbase + q;
+        ip.sys = w - q * L.nsys;
+        ip.soff = (size_t)ip.sys * L.tile;
+    }
+    return ip;
+}
+
+// Item prologue: per-element Phi data an item keeps in registers (Heat2D: the symbol tile, then the tiles of the
+// separable right-hand-side factors).  They come through the row pipe like any other row, ahead of the item's rows.
+__device__ __forceinline__ int n_prologue(const LevelDev &L) { return L.sig ? 1 + L.nrhs : 0; }
+__device__ __forceinline__ const double *prologue_row(const LevelDev &L, int q, size_t soff) {
+    return (q == 0 ? L.sig : L.rhs_x + (size_t)(q - 1) * L.pitch) + soff;
+}
+
 template <class Phi>
 __device__ __forceinline__ void step_consts(typename Phi::C &c, const LevelDev &L, int i, int tid) {
     if (L.ndt > 1) Phi::load_consts(c, L.sconst + (size_t)__ldg(L.dtidx + i) * L.cw, tid);
@@ -34,15 +63,15 @@ __device__ __forceinline__ void step_consts(typename Phi::C &c, const LevelDev &
 
 // x <- (g_i +) Phi_i(x): pops the dense right-hand-side row and the g row if the level has them
 template <class Phi, class Pipe, class TeamT>
-__device__ __forceinline__ void advance(double (&x)[Phi::E], typename Phi::C &c, const LevelDev &L, int i, Pipe &pipe,
-                                        TeamT &team, bool add_g = true) {
+__device__ __forceinline__ void advance(double (&x)[Phi::E], typename Phi::C &c, const typename Phi::Item &it,
+                                        const LevelDev &L, int i, Pipe &pipe, TeamT &team, bool add_g = true) {
     step_consts<Phi>(c, L, i, team.tid);
     if (L.rhs_dense) {
         double b[Phi::E];
         pipe.pop(b, team);
         vadd(x, b);
     }
-    Phi::apply(x, c, L, i, team);
+    Phi::apply(x, c, it, L, i, team);
     if (add_g && L.g) {
         double gg[Phi::E];
         pipe.pop(gg, team);
@@ -53,18 +82,19 @@ __device__ __forceinline__ void advance(double (&x)[Phi::E], typename Phi::C &c,
 // rows `advance` pops for step i, in order: returns false when stage runs past them
 struct StepRows {
     // stage 0: dense rhs row, stage 1: g row
-    __device__ static __forceinline__ bool next(const LevelDev &L, int i, int &stage, const double *&p, bool with_g = true) {
+    __device__ static __forceinline__ bool next(const LevelDev &L, int i, int &stage, const double *&p, size_t soff,
+                                                bool with_g = true) {
         if (stage == 0) {
             stage = 1;
             if (L.rhs_dense) {
-                p = L.rhs_dense + (size_t)i * L.pitch;
+                p = L.rhs_dense + (size_t)i * L.pitch + soff;
                 return true;
             }
         }
         if (stage == 1) {
             stage = 2;
             if (with_g && L.g) {
-                p = L.g + (size_t)i * L.pitch;
+                p = L.g + (size_t)i * L.pitch + soff;
                 return true;
             }
         }
@@ -75,33 +105,47 @@ struct StepRows {
 // ------------------------------------------------------------------------------------------------
 // F-relaxation / forward solve (mgrit.py:312-327, 471-481):  for each interval [s, e):
 //   x = u[s];  for i = s+1 .. e-1:  x = (g[i] +) Phi_i(x);  u[i] = x
+// With last_only != 0 only the last point of each interval is stored: in the down-sweep of a cycle the other F-points
+// are dead values (nothing reads them before the F-relaxation after the coarse-grid correction rewrites them), so the
+// kernel computes the same chain and skips the dead stores.
 // ------------------------------------------------------------------------------------------------
 struct GenChain {
     LevelDev L;
-    int item, nitems, stride;
-    int s, e, i, stage;
-    __device__ GenChain(const LevelDev &L_, int first, int nitems_, int stride_)
-        : L(L_), item(first), nitems(nitems_), stride(stride_), s(0), e(0), i(0), stage(-1) {}
+    int w, nw, stride;
+    int s, e, i, stage, pro;
+    size_t soff;
+    __device__ GenChain(const LevelDev &L_, int first, int nw_, int stride_)
+        : L(L_), w(first), nw(nw_), stride(stride_), s(0), e(0), i(0), stage(-2), pro(0), soff(0) {}
     __device__ bool next(const double *&p) {
         for (;;) {
-            if (item >= nitems) return false;
-            if (stage < 0) {
-                interval_of(L, item, s, e);
+            if (w >= nw) return false;
+            if (stage == -2) {
+                const ItemPos ip = item_pos(L, w);
+                interval_of(L, ip.k, s, e);
                 if (e - s <= 1) {
-                    item += stride;
+                    w += stride;
                     continue;
                 }
-                p = L.u + (size_t)s * L.pitch;
+                soff = ip.soff;
+                pro = 0;
+                stage = -1;
+            }
+            if (stage == -1) {
+                if (pro < n_prologue(L)) {
+                    p = prologue_row(L, pro++, soff);
+                    return true;
+                }
+                p = L.u + (size_t)s * L.pitch + soff;
                 i = s + 1;
                 stage = 0;
                 return true;
             }
             if (i >= e) {
-                item += stride;
-                stage = -1;
+                w += stride;
+                stage = -2;
                 continue;
             }
-            if (StepRows::next(L, i, stage, p)) return true;
+            if (StepRows::next(L, i, stage, p, soff)) return true;
             ++i;
             stage = 0;
         }
@@ -109,22 +153,25 @@ struct GenChain {
 };
 
 template <class Phi>
-__global__ void __launch_bounds__(Phi::T) k_chain(const LevelDev L, const int nitems, const int nin) {
+__global__ void __launch_bounds__(Phi::T) k_chain(const LevelDev L, const int nw, const int last_only, const int nin) {
     using SH = typename Phi::SH;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenChain> pipe(g_smem, nin, L.pitch, L.n, GenChain(L, blockIdx.x, nitems, gridDim.x));
+    RowPipe<SH, GenChain> pipe(g_smem, nin, L.tile, L.n, GenChain(L, blockIdx.x, nw, gridDim.x));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(L, w);
         int s, e;
-        interval_of(L, item, s, e);
+        interval_of(L, ip.k, s, e);
         if (e - s <= 1) continue;
+        typename Phi::Item it;
+        Phi::begin_item(it, L, ip.sys, pipe, team);
         double x[Phi::E];
         pipe.pop(x, team);
         for (int i = s + 1; i < e; ++i) {
-            advance<Phi>(x, c, L, i, pipe, team);
-            pipe.push(x, L.u + (size_t)i * L.pitch, team);
+            advance<Phi>(x, c, it, L, i, pipe, team);
+            if (!last_only || i == e - 1) pipe.push(x, L.u + (size_t)i * L.pitch + ip.soff, team);
         }
     }
     pipe.finish(team);
@@ -146,29 +193,40 @@ __device__ __forceinline__ bool c_run_continues(const LevelDev &L, int kk) {
 
 struct GenCRelax {
     LevelDev L;
-    int item, nitems, stride, stage, kk;
+    int w, nw, stride, stage, kk, pro;
+    size_t soff;
     bool weighted;
-    __device__ GenCRelax(const LevelDev &L_, int first, int nitems_, int stride_, bool weighted_)
-        : L(L_), item(first), nitems(nitems_), stride(stride_), stage(-1), kk(0), weighted(weighted_) {}
+    __device__ GenCRelax(const LevelDev &L_, int first, int nw_, int stride_, bool weighted_)
+        : L(L_), w(first), nw(nw_), stride(stride_), stage(-2), kk(0), pro(0), soff(0), weighted(weighted_) {}
     __device__ bool next(const double *&p) {
         for (;;) {
-            if (item >= nitems) return false;
-            if (stage < 0) {
-                if (!c_run_leader(L, item)) {
-                    item += stride;
+            if (w >= nw) return false;
+            if (stage == -2) {
+                const ItemPos ip = item_pos(L, w, 1);
+                if (!c_run_leader(L, ip.k)) {
+                    w += stride;
                     continue;
                 }
-                kk = item;
-                p = L.u + (size_t)(__ldg(L.cpts + kk) - 1) * L.pitch;
+                kk = ip.k;
+                soff = ip.soff;
+                pro = 0;
+                stage = -1;
+            }
+            if (stage == -1) {
+                if (pro < n_prologue(L)) {
+                    p = prologue_row(L, pro++, soff);
+                    return true;
+                }
+                p = L.u + (size_t)(__ldg(L.cpts + kk) - 1) * L.pitch + soff;
                 stage = 0;
                 return true;
             }
             const int c = __ldg(L.cpts + kk);
-            if (stage < 2 && StepRows::next(L, c, stage, p)) return true;
+            if (stage < 2 && StepRows::next(L, c, stage, p, soff)) return true;
             if (stage == 2) {
                 stage = 3;
                 if (weighted) {
-                    p = L.u + (size_t)c * L.pitch;
+                    p = L.u + (size_t)c * L.pitch + soff;
                     return true;
                 }
             }
@@ -177,36 +235,39 @@ struct GenCRelax {
                 stage = 0;
                 continue;
             }
-            item += stride;
-            stage = -1;
+            w += stride;
+            stage = -2;
         }
     }
 };
 
 template <class Phi>
-__global__ void __launch_bounds__(Phi::T) k_c_relax(const LevelDev L, const double w, const int nin) {
+__global__ void __launch_bounds__(Phi::T) k_c_relax(const LevelDev L, const double wgt, const int nw, const int nin) {
     using SH = typename Phi::SH;
-    const bool weighted = (w != 1.0);
+    const bool weighted = (wgt != 1.0);
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenCRelax> pipe(g_smem, nin, L.pitch, L.n, GenCRelax(L, 1 + blockIdx.x, L.ncpts, gridDim.x, weighted));
+    RowPipe<SH, GenCRelax> pipe(g_smem, nin, L.tile, L.n, GenCRelax(L, blockIdx.x, nw, gridDim.x, weighted));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
-    for (int k = 1 + blockIdx.x; k < L.ncpts; k += gridDim.x) {
-        if (!c_run_leader(L, k)) continue;
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(L, w, 1);
+        if (!c_run_leader(L, ip.k)) continue;
+        typename Phi::Item it;
+        Phi::begin_item(it, L, ip.sys, pipe, team);
         double x[Phi::E];
         pipe.pop(x, team);
-        for (int kk = k;; ++kk) {
+        for (int kk = ip.k;; ++kk) {
             const int cp = __ldg(L.cpts + kk);
-            advance<Phi>(x, c, L, cp, pipe, team);
+            advance<Phi>(x, c, it, L, cp, pipe, team);
             if (weighted) {
                 double old[Phi::E];
                 pipe.pop(old, team);
-                const double w1 = 1.0 - w;
+                const double w1 = 1.0 - wgt;
 #pragma unroll
-                for (int j = 0; j < Phi::E; ++j) x[j] = __dadd_rn(__dmul_rn(x[j], w), __dmul_rn(old[j], w1));
+                for (int j = 0; j < Phi::E; ++j) x[j] = __dadd_rn(__dmul_rn(x[j], wgt), __dmul_rn(old[j], w1));
             }
-            pipe.push(x, L.u + (size_t)cp * L.pitch, team);
+            pipe.push(x, L.u + (size_t)cp * L.pitch + ip.soff, team);
             if (!c_run_continues(L, kk)) break;
         }
     }
@@ -221,67 +282,86 @@ __global__ void __launch_bounds__(Phi::T) k_c_relax(const LevelDev L, const doub
 // ------------------------------------------------------------------------------------------------
 struct GenFas {
     LevelDev L, G;
-    int item, nitems, stride, stage, sub;
-    __device__ GenFas(const LevelDev &L_, const LevelDev &G_, int first, int nitems_, int stride_)
-        : L(L_), G(G_), item(first), nitems(nitems_), stride(stride_), stage(0), sub(0) {}
+    int w, nw, stride, stage, sub, j, pro;
+    size_t soff;
+    __device__ GenFas(const LevelDev &L_, const LevelDev &G_, int first, int nw_, int stride_)
+        : L(L_), G(G_), w(first), nw(nw_), stride(stride_), stage(-2), sub(0), j(0), pro(0), soff(0) {}
     __device__ bool next(const double *&p) {
         for (;;) {
-            if (item >= nitems) return false;
-            const int c = __ldg(L.cpts + item);
+            if (w >= nw) return false;
+            if (stage == -2) {
+                const ItemPos ip = item_pos(L, w, 1);
+                j = ip.k;
+                soff = ip.soff;
+                pro = 0;
+                stage = -1;
+            }
+            const int c = __ldg(L.cpts + j);
             switch (stage) {
+                case -1:
+                    if (pro < n_prologue(L)) {
+                        p = prologue_row(L, pro++, soff);
+                        return true;
+                    }
+                    stage = 0;
+                    break;
                 case 0:  // u[c-1]
-                    p = L.u + (size_t)(c - 1) * L.pitch;
+                    p = L.u + (size_t)(c - 1) * L.pitch + soff;
                     stage = 1;
                     sub = 0;
                     return true;
                 case 1:  // dense rhs row of the fine step (no g: it is combined by hand below)
                     stage = 2;
-                    if (StepRows::next(L, c, sub, p, false)) return true;
+                    if (StepRows::next(L, c, sub, p, soff, false)) return true;
                     break;
                 case 2:  // u[c]
-                    p = L.u + (size_t)c * L.pitch;
+                    p = L.u + (size_t)c * L.pitch + soff;
                     stage = 3;
                     return true;
                 case 3:  // g[c]
                     stage = 4;
                     if (L.g) {
-                        p = L.g + (size_t)c * L.pitch;
+                        p = L.g + (size_t)c * L.pitch + soff;
                         return true;
                     }
                     break;
                 case 4:  // v[j-1] = u[cpts[j-1]]
-                    p = L.u + (size_t)__ldg(L.cpts + item - 1) * L.pitch;
+                    p = L.u + (size_t)__ldg(L.cpts + j - 1) * L.pitch + soff;
                     stage = 5;
                     sub = 0;
                     return true;
                 case 5:  // dense rhs row of the coarse step
                     stage = 6;
-                    if (StepRows::next(G, item, sub, p, false)) return true;
+                    if (StepRows::next(G, j, sub, p, soff, false)) return true;
                     break;
                 default:
-                    item += stride;
-                    stage = 0;
+                    w += stride;
+                    stage = -2;
             }
         }
     }
 };
 
 template <class Phi>
-__global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const LevelDev G, const int nin) {
+__global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const LevelDev G, const int nw, const int nin) {
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenFas> pipe(g_smem, nin, L.pitch, L.n, GenFas(L, G, 1 + blockIdx.x, L.ncpts, gridDim.x));
+    RowPipe<SH, GenFas> pipe(g_smem, nin, L.tile, L.n, GenFas(L, G, blockIdx.x, nw, gridDim.x));
     pipe.start(team);
     typename Phi::C c;  // reloaded before each Phi: fine and coarse steps use different constants
-    for (int j = 1 + blockIdx.x; j < L.ncpts; j += gridDim.x) {
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(L, w, 1);
+        const int j = ip.k;
         const int cp = __ldg(L.cpts + j);
+        typename Phi::Item it;  // per-element data: the same spatial operator on both levels
+        Phi::begin_item(it, L, ip.sys, pipe, team);
         double x[E], y[E];
         pipe.pop(x, team);
         Phi::load_consts(c, L.sconst + (L.ndt > 1 ? (size_t)__ldg(L.dtidx + cp) * L.cw : 0), team.tid);
-        advance<Phi>(x, c, L, cp, pipe, team, false);  // Phi_f(u[c-1])
-        pipe.pop(y, team);                               // u[c]
-        pipe.push(y, G.u + (size_t)j * G.pitch, team);   // injection
+        advance<Phi>(x, c, it, L, cp, pipe, team, false);            // Phi_f(u[c-1])
+        pipe.pop(y, team);                                           // u[c]
+        pipe.push(y, G.u + (size_t)j * G.pitch + ip.soff, team);     // injection
         if (L.g) {
             double gg[E];
             pipe.pop(gg, team);
@@ -291,12 +371,12 @@ __global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const
 #pragma unroll
             for (int q = 0; q < E; ++q) x[q] = (x[q] - y[q]) + y[q];
         }
-        pipe.pop(y, team);                               // v[j-1]
+        pipe.pop(y, team);                                           // v[j-1]
         Phi::load_consts(c, G.sconst + (G.ndt > 1 ? (size_t)__ldg(G.dtidx + j) * G.cw : 0), team.tid);
-        advance<Phi>(y, c, G, j, pipe, team, false);     // Phi_c(v[j-1])
+        advance<Phi>(y, c, it, G, j, pipe, team, false);             // Phi_c(v[j-1])
 #pragma unroll
         for (int q = 0; q < E; ++q) x[q] = x[q] - y[q];
-        pipe.push(x, G.g + (size_t)j * G.pitch, team);
+        pipe.push(x, G.g + (size_t)j * G.pitch + ip.soff, team);
     }
     pipe.finish(team);
 }
@@ -311,40 +391,54 @@ __global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const
 // ------------------------------------------------------------------------------------------------
 struct GenCorrect {
     LevelDev L, G;
-    int item, nitems, stride;
-    int s, e, i, stage;
+    int w, nw, stride;
+    int k, s, e, i, stage, pro;
+    size_t soff;
     bool frelax;
     int kfirst;
-    __device__ GenCorrect(const LevelDev &L_, const LevelDev &G_, int first, int nitems_, int stride_, bool fr, int kf)
-        : L(L_), G(G_), item(first), nitems(nitems_), stride(stride_), s(0), e(0), i(0), stage(-2), frelax(fr), kfirst(kf) {}
+    __device__ GenCorrect(const LevelDev &L_, const LevelDev &G_, int first, int nw_, int stride_, bool fr, int kf)
+        : L(L_), G(G_), w(first), nw(nw_), stride(stride_), k(0), s(0), e(0), i(0), stage(-3), pro(0), soff(0),
+          frelax(fr), kfirst(kf) {}
     __device__ bool next(const double *&p) {
         for (;;) {
-            if (item >= nitems) return false;
-            if (stage == -2) {
-                interval_of(L, item, s, e);
+            if (w >= nw) return false;
+            if (stage == -3) {
+                const ItemPos ip = item_pos(L, w);
+                k = ip.k;
+                interval_of(L, k, s, e);
                 const bool chain = frelax && (e - s > 1);
-                if (item < kfirst && !chain) {
-                    item += stride;
+                if (k < kfirst && !chain) {
+                    w += stride;
                     continue;
                 }
-                p = L.u + (size_t)s * L.pitch;
+                soff = ip.soff;
+                pro = 0;
+                stage = -2;
+            }
+            if (stage == -2) {
+                const bool chain = frelax && (e - s > 1);
+                if (chain && pro < n_prologue(L)) {
+                    p = prologue_row(L, pro++, soff);
+                    return true;
+                }
+                p = L.u + (size_t)s * L.pitch + soff;
                 stage = -1;
                 return true;
             }
             if (stage == -1) {
                 stage = 0;
                 i = s + 1;
-                if (item >= kfirst) {
-                    p = G.u + (size_t)item * G.pitch;
+                if (k >= kfirst) {
+                    p = G.u + (size_t)k * G.pitch + soff;
                     return true;
                 }
             }
             if (!frelax || i >= e) {
-                item += stride;
-                stage = -2;
+                w += stride;
+                stage = -3;
                 continue;
             }
-            if (StepRows::next(L, i, stage, p)) return true;
+            if (StepRows::next(L, i, stage, p, soff)) return true;
             ++i;
             stage = 0;
         }
@@ -353,19 +447,23 @@ struct GenCorrect {
 
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const LevelDev G, const int frelax, const int kfirst,
-                                                    const int nin) {
+                                                    const int nw, const int nin) {
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenCorrect> pipe(g_smem, nin, L.pitch, L.n, GenCorrect(L, G, blockIdx.x, L.ncpts, gridDim.x, frelax != 0, kfirst));
+    RowPipe<SH, GenCorrect> pipe(g_smem, nin, L.tile, L.n, GenCorrect(L, G, blockIdx.x, nw, gridDim.x, frelax != 0, kfirst));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
-    for (int k = blockIdx.x; k < L.ncpts; k += gridDim.x) {
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(L, w);
+        const int k = ip.k;
         int s, e;
         interval_of(L, k, s, e);
         const bool chain = frelax && (e - s > 1);
         if (k < kfirst && !chain) continue;
+        typename Phi::Item it;
+        if (chain) Phi::begin_item(it, L, ip.sys, pipe, team);
         double x[E];
         pipe.pop(x, team);
         if (k >= kfirst) {
@@ -373,12 +471,12 @@ __global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const Leve
             pipe.pop(cu, team);
 #pragma unroll
             for (int q = 0; q < E; ++q) x[q] = x[q] + (cu[q] - x[q]);
-            pipe.push(x, L.u + (size_t)s * L.pitch, team);
+            pipe.push(x, L.u + (size_t)s * L.pitch + ip.soff, team);
         }
         if (chain) {
             for (int i = s + 1; i < e; ++i) {
-                advance<Phi>(x, c, L, i, pipe, team);
-                pipe.push(x, L.u + (size_t)i * L.pitch, team);
+                advance<Phi>(x, c, it, L, i, pipe, team);
+                pipe.push(x, L.u + (size_t)i * L.pitch + ip.soff, team);
             }
         }
     }
@@ -386,49 +484,67 @@ __global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const Leve
 }
 
 // ------------------------------------------------------------------------------------------------
-// Residual at C-points (mgrit.py:405-413): out[k] = || Phi(u[c-1]) - u[c] ||^2  (level 0: no g)
+// Residual at C-points (mgrit.py:405-413): out[k] = || Phi(u[c-1]) - u[c] ||^2  (level 0: no g).
+// With several systems per row each item writes its partial sum to out_sq[ncpts + k * nsys + sys] and
+// k_sum_systems adds them up in a fixed order.
 // ------------------------------------------------------------------------------------------------
 struct GenResidual {
     LevelDev L;
-    int item, nitems, stride, stage;
-    __device__ GenResidual(const LevelDev &L_, int first, int nitems_, int stride_)
-        : L(L_), item(first), nitems(nitems_), stride(stride_), stage(-1) {}
+    int w, nw, stride, stage, k, pro;
+    size_t soff;
+    __device__ GenResidual(const LevelDev &L_, int first, int nw_, int stride_)
+        : L(L_), w(first), nw(nw_), stride(stride_), stage(-2), k(0), pro(0), soff(0) {}
     __device__ bool next(const double *&p) {
         for (;;) {
-            if (item >= nitems) return false;
-            const int c = __ldg(L.cpts + item);
-            if (stage < 0) {
-                p = L.u + (size_t)(c - 1) * L.pitch;
+            if (w >= nw) return false;
+            if (stage == -2) {
+                const ItemPos ip = item_pos(L, w, 1);
+                k = ip.k;
+                soff = ip.soff;
+                pro = 0;
+                stage = -1;
+            }
+            const int c = __ldg(L.cpts + k);
+            if (stage == -1) {
+                if (pro < n_prologue(L)) {
+                    p = prologue_row(L, pro++, soff);
+                    return true;
+                }
+                p = L.u + (size_t)(c - 1) * L.pitch + soff;
                 stage = 0;
                 return true;
             }
-            if (stage < 2 && StepRows::next(L, c, stage, p)) return true;
+            if (stage < 2 && StepRows::next(L, c, stage, p, soff)) return true;
             if (stage == 2) {
                 stage = 3;
-                p = L.u + (size_t)c * L.pitch;
+                p = L.u + (size_t)c * L.pitch + soff;
                 return true;
             }
-            item += stride;
-            stage = -1;
+            w += stride;
+            stage = -2;
         }
     }
 };
 
 template <class Phi>
-__global__ void __launch_bounds__(Phi::T) k_residual(const LevelDev L, double *__restrict__ out_sq, const int nin) {
+__global__ void __launch_bounds__(Phi::T) k_residual(const LevelDev L, double *__restrict__ out_sq, const int nw,
+                                                     const int nin) {
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenResidual> pipe(g_smem, nin, L.pitch, L.n, GenResidual(L, 1 + blockIdx.x, L.ncpts, gridDim.x));
+    RowPipe<SH, GenResidual> pipe(g_smem, nin, L.tile, L.n, GenResidual(L, blockIdx.x, nw, gridDim.x));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
     if (blockIdx.x == 0 && team.tid == 0) out_sq[0] = 0.0;
-    for (int k = 1 + blockIdx.x; k < L.ncpts; k += gridDim.x) {
-        const int cp = __ldg(L.cpts + k);
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(L, w, 1);
+        const int cp = __ldg(L.cpts + ip.k);
+        typename Phi::Item it;
+        Phi::begin_item(it, L, ip.sys, pipe, team);
         double x[E], y[E];
         pipe.pop(x, team);
-        advance<Phi>(x, c, L, cp, pipe, team);
+        advance<Phi>(x, c, it, L, cp, pipe, team);
         pipe.pop(y, team);
         double acc = 0.0;
         const int nv = L.n - team.tid * E;
@@ -438,49 +554,80 @@ __global__ void __launch_bounds__(Phi::T) k_residual(const LevelDev L, double *_
             acc = (q < nv) ? fma(r, r, acc) : acc;
         }
         acc = team.sum(acc);
-        if (team.tid == 0) out_sq[k] = acc;
+        if (team.tid == 0) out_sq[L.nsys <= 1 ? ip.k : L.ncpts + ip.k * L.nsys + ip.sys] = acc;
     }
     pipe.finish(team);
 }
 
+// out_sq[k] = sum over the systems of a row, k = 1 .. ncpts-1 (fixed order: deterministic)
+template <class Phi>
+__global__ void k_sum_systems(double *__restrict__ out_sq, const int ncpts, const int nsys) {
+    const int k = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncpts) return;
+    const double *part = out_sq + ncpts + (size_t)k * nsys;
+    double acc = 0.0;
+    for (int s = 0; s < nsys; ++s) acc += part[s];
+    out_sq[k] = acc;
+}
+
 // ------------------------------------------------------------------------------------------------
-// One Phi for Application.step: out = Phi_point(in)
+// One Phi for Application.step: out = Phi_point(in)   (rows in the level's layout)
 // ------------------------------------------------------------------------------------------------
 struct GenStep {
     LevelDev L;
     const double *in;
-    int point, stage;
-    __device__ GenStep(const LevelDev &L_, const double *in_, int point_) : L(L_), in(in_), point(point_), stage(-1) {}
+    int point, w, nw, stride, stage, pro;
+    size_t soff;
+    __device__ GenStep(const LevelDev &L_, const double *in_, int point_, int first, int nw_, int stride_)
+        : L(L_), in(in_), point(point_), w(first), nw(nw_), stride(stride_), stage(-2), pro(0), soff(0) {}
     __device__ bool next(const double *&p) {
-        if (stage < 0) {
-            p = in;
-            stage = 0;
-            return true;
-        }
-        if (stage == 0) {
-            stage = 1;
-            if (L.rhs_dense) {
-                p = L.rhs_dense + (size_t)point * L.pitch;
+        for (;;) {
+            if (w >= nw) return false;
+            if (stage == -2) {
+                soff = item_pos(L, w).soff;
+                pro = 0;
+                stage = -1;
+            }
+            if (stage == -1) {
+                if (pro < n_prologue(L)) {
+                    p = prologue_row(L, pro++, soff);
+                    return true;
+                }
+                p = in + soff;
+                stage = 0;
                 return true;
             }
+            if (stage == 0) {
+                stage = 1;
+                if (L.rhs_dense) {
+                    p = L.rhs_dense + (size_t)point * L.pitch + soff;
+                    return true;
+                }
+            }
+            w += stride;
+            stage = -2;
         }
-        return false;
     }
 };
 
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_step(const LevelDev L, const int point, const double *in, double *out,
-                                                 const int nin) {
+                                                 const int nw, const int nin) {
     using SH = typename Phi::SH;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenStep> pipe(g_smem, nin, L.pitch, L.n, GenStep(L, in, point));
+    RowPipe<SH, GenStep> pipe(g_smem, nin, L.tile, L.n, GenStep(L, in, point, blockIdx.x, nw, gridDim.x));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
-    double x[Phi::E];
-    pipe.pop(x, team);
-    advance<Phi>(x, c, L, point, pipe, team, false);
-    pipe.push(x, out, team);
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(L, w);
+        typename Phi::Item it;
+        Phi::begin_item(it, L, ip.sys, pipe, team);
+        double x[Phi::E];
+        pipe.pop(x, team);
+        advance<Phi>(x, c, it, L, point, pipe, team, false);
+        pipe.push(x, out + ip.soff, team);
+    }
     pipe.finish(team);
 }
 

@@ -16,7 +16,7 @@ int cuda_fail(cudaError_t e, const char *what);  // api.cu: records the message,
 struct SweepTable {
     int team_threads;
     int chunk;
-    int (*f_relax)(const LevelDev &, cudaStream_t);
+    int (*f_relax)(const LevelDev &, int flags, cudaStream_t);
     int (*forward_solve)(const LevelDev &, cudaStream_t);
     int (*c_relax)(const LevelDev &, double, cudaStream_t);
     int (*fas_residual)(const LevelDev &, const LevelDev &, cudaStream_t);

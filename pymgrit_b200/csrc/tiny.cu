@@ -210,7 +210,7 @@ struct TinyLaunch {
         int g = (items + 127) / 128;
         return g < 1 ? 1 : (g > 1184 ? 1184 : g);
     }
-    static int f_relax(const LevelDev &L, cudaStream_t st) {
+    static int f_relax(const LevelDev &L, int /*flags*/, cudaStream_t st) {
         if (device_info() == nullptr) return MGB_ECUDA;
         kt_chain<P><<<grid(L.ncpts), 128, 0, st>>>(L, L.ncpts);
         return cuda_fail(cudaGetLastError(), "f_relax");

@@ -33,8 +33,7 @@ def run_b200(name, **extra):
 def solution_rows(solver, idx=None):
     """Level-0 solution as host arrays: (rows at idx, per-point 2-norms of all points)."""
     lv = solver._lv[0]
-    u = lv.u[:, :lv.n].detach().cpu().numpy()
-    shape = lv.app.vector_template.shape
-    norms = np.sqrt(np.sum(u * u, axis=1))
+    u = lv.values()                                    # [points, *vector shape], node values
+    norms = np.sqrt(np.sum(u.reshape(len(u), -1) ** 2, axis=1))
     rows = u if idx is None else u[idx]
-    return rows.reshape((rows.shape[0],) + tuple(shape)), norms
+    return rows, norms

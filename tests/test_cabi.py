@@ -25,7 +25,7 @@ def test_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.mgb_abi_version() == 1
+    assert lib.mgb_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header(lib):
@@ -94,3 +94,59 @@ def test_no_cpu_fallback(lib):
     import pymgrit_b200 as P
     with pytest.raises(Exception):
         P.Mgrit(problem=[P.Dahlquist(t_start=0, t_stop=5, nt=11)]).solve()
+
+
+@pytest.mark.parametrize('name', ['heat2d_bc', 'heat2d_example', 'heat2d_cfg3_small'])
+def test_heat2d_sine_space_tables_reproduce_the_oracle(lib, name):
+    """Host-side check of the Heat2D design (pymgrit_b200/heat/heat_2d.py, csrc/phi.cuh): the row layout, symbol row,
+    right-hand-side factors and boundary coupling the host builds, pushed through a numpy restatement of the kernel's
+    arithmetic, give the oracle's backward-Euler step (sparse direct solve) to rounding."""
+    import cases as CS
+    import pymgrit_b200 as P
+    from oracle import mgrit_oracle as O
+    case = CS.CASES[name]
+    kw = case['app_kw']
+    t = CS.case_time_grids(case)[0]
+    app, orc = P.Heat2D(t_interval=t, **kw), O.Heat2DOracle(t_interval=t, **kw)
+    fam = app.family()
+    nx, ny = app.nx, app.ny
+    assert fam.pitch == fam.nsys * fam.tile and fam.boff >= fam.nint
+    assert np.allclose(fam.sx @ fam.sx, np.eye(nx - 2), atol=1e-13)
+
+    def to_rows(nodes):
+        r = np.zeros(fam.pitch)
+        r[:fam.nint] = (fam.sx @ nodes[1:-1, 1:-1] @ fam.sy).reshape(-1)
+        r[fam.boff:fam.boff + len(fam.bnodes)] = nodes.reshape(-1)[fam.bnodes]
+        return r
+
+    def from_rows(r):
+        nodes = np.zeros((nx, ny))
+        nodes[1:-1, 1:-1] = fam.sx @ r[:fam.nint].reshape(nx - 2, ny - 2) @ fam.sy
+        nodes.reshape(-1)[fam.bnodes] = r[fam.boff:fam.boff + len(fam.bnodes)]
+        return nodes
+
+    assert np.array_equal(app.vector_t_start.get_values(), orc.u0)
+    fields = []
+    if fam.split.kind == 'separable':
+        for b in fam.split.basis:
+            f = np.zeros((nx, ny))
+            f[1:-1, 1:-1] = b.reshape(nx - 2, ny - 2)
+            fields.append(f)
+    if fam.coupling is not None:
+        fields.append(fam.coupling)
+    rx = [to_rows(f) for f in fields]
+    dt = np.zeros(len(t))
+    dt[1:] = np.diff(t)
+    cols = ([fam.split.coefficients(t) * dt[:, None]] if fam.split.kind == 'separable' else []) + \
+           ([dt[:, None]] if fam.coupling is not None else [])
+    rt = np.concatenate(cols, axis=1)
+    assert rt.shape[1] == len(rx) <= 3
+    row, u = to_rows(orc.u0), orc.u0
+    for i in range(1, 5):
+        x = row + sum(rt[i, k] * rx[k] for k in range(len(rx)))
+        x = x / (1 + dt[i] * fam.sig)
+        x[fam.boff:] = fam.sig[fam.boff:]              # boundary tiles: the Dirichlet values
+        x[fam.nint:fam.boff] = 0.0
+        row, u = x, orc.phi(u, t[i - 1], t[i])
+        assert np.max(np.abs(from_rows(row) - u)) <= 1e-12 * np.max(np.abs(u))
+        assert abs(np.linalg.norm(row) - np.linalg.norm(u)) <= 1e-12 * np.linalg.norm(u)      # Parseval

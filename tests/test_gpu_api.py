@@ -1,0 +1,163 @@
+"""GPU tests of the plugin API itself (run with -m gpu): Application.step and the Vector operations of every device
+application, against the reference's own known-answer vectors (tests/heat/test_heat_1d.py, test_heat_2d.py,
+tests/advection/test_advection_1d.py, tests/dahlquist/test_dahlquist.py, tests/brusselator/test_brusselator.py) and the
+single-Phi fixtures produced by the unmodified reference (tests/golden/phi_steps.npz).  Every call goes through
+pymgrit_b200 -> C ABI -> kernels."""
+import copy
+
+import numpy as np
+import pytest
+
+import cases as C
+from oracle_util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def P():
+    import pymgrit_b200
+    return pymgrit_b200
+
+
+def test_heat1d_step_known_answer(P):            # tests/heat/test_heat_1d.py:31-42
+    p = P.Heat1D(a=1, init_cond=lambda x: 2 * x, x_start=0, x_end=1, nx=6, t_start=0, t_stop=1, nt=11)
+    out = p.step(u_start=p.vector_t_start, t_start=0, t_stop=0.1)
+    np.testing.assert_almost_equal(out.get_values(), np.array([0.28164, 0.51593599, 0.63660638, 0.53191933]))
+
+
+def test_heat2d_step_known_answer(P):            # tests/heat/test_heat_2d.py:230-249
+    p = P.Heat2D(a=1, x_start=0, x_end=1, y_start=3, y_end=4, nx=5, ny=5, rhs=lambda x, y, t: 2 * x * y,
+                 t_start=0, t_stop=1, nt=11)
+    out = p.step(u_start=p.vector_t_start, t_start=0, t_stop=0.1)
+    want = np.array([[0., 0., 0., 0., 0.], [0., 0.06659024, 0.08719337, 0.07227713, 0.],
+                     [0., 0.11922399, 0.15502696, 0.12990086, 0.], [0., 0.12666875, 0.16193148, 0.1391124, 0.],
+                     [0., 0., 0., 0., 0.]])
+    np.testing.assert_almost_equal(out.get_values(), want)
+
+
+def test_heat2d_constructor_errors(P):           # tests/heat/test_heat_2d.py:200-227 (argument checks)
+    kw = dict(a=1, x_start=0, x_end=1, y_start=3, y_end=4, nx=5, ny=5, t_start=0, t_stop=1, nt=11)
+    with pytest.raises(Exception):
+        P.Heat2D(method='unknown', **kw)
+    with pytest.raises(Exception):
+        P.Heat2D(bc_left='0', **kw)
+    with pytest.raises(Exception):
+        P.Heat2D(method='CN', **kw)              # no device kernels for CN / FE: fails loudly, no fallback
+
+
+def test_advection_step_known_answer(P):         # tests/advection/test_advection_1d.py:33-45
+    p = P.Advection1D(c=1, x_start=0, x_end=1, nx=6, t_start=0, t_stop=1, nt=11)
+    out = p.step(u_start=p.vector_t_start, t_start=0, t_stop=0.1)
+    np.testing.assert_almost_equal(out.get_values(), np.array([0.868043, 0.92987396, 0.87805385, 0.75780217, 0.604129]))
+
+
+def test_dahlquist_step_known_answer(P):         # tests/dahlquist/test_dahlquist.py:55-62
+    p = P.Dahlquist(t_start=0, t_stop=1, nt=11)
+    out = p.step(u_start=p.vector_t_start, t_start=0, t_stop=0.1)
+    np.testing.assert_almost_equal(out.get_values(), 0.9090909090909091)
+
+
+def test_brusselator_step_known_answer(P):       # tests/brusselator/test_brusselator.py:24-31
+    p = P.Brusselator(t_start=0, t_stop=1, nt=11)
+    out = p.step(u_start=p.vector_template.clone_zero(), t_start=0, t_stop=0.1)
+    np.testing.assert_almost_equal(out.get_values(), np.array([0.08240173, 0.01319825]))
+
+
+def test_phi_step_fixtures(P):
+    """Single Phi at BASELINE sizes against the unmodified reference (1e-10 relative)."""
+    g = load_golden('phi_steps')
+    h = P.Heat1D(x_start=0, x_end=1, nx=1025, a=1, init_cond=C.heat_init, rhs=C.heat_rhs, t_start=0, t_stop=2, nt=5)
+    for k in range(5):
+        dt = float(g[f'heat1d_1025/dt{k}'][0])
+        got = h.step(u_start=h.vector_t_start, t_start=0.3, t_stop=0.3 + dt).get_values()
+        ref = g[f'heat1d_1025/out{k}']
+        assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    a = P.Advection1D(c=1, x_start=-1, x_end=1, nx=4096, t_start=0, t_stop=2, nt=5)
+    for k in range(3):
+        dt = float(g[f'advection_4096/dt{k}'][0])
+        got = a.step(u_start=a.vector_t_start, t_start=0.0, t_stop=dt).get_values()
+        ref = g[f'advection_4096/out{k}']
+        assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    h2 = P.Heat2D(x_start=0, x_end=1, y_start=0, y_end=1, nx=65, ny=49, a=1, rhs=C.heat2d_rhs, init_cond=C.heat2d_init,
+                  bc_left=1.0, bc_top=lambda y: 0.5 + 0 * y, t_start=0, t_stop=5, nt=5)
+    np.testing.assert_array_equal(h2.vector_t_start.get_values(), g['heat2d_65x49/in'])
+    for k in range(3):
+        dt = float(g[f'heat2d_65x49/dt{k}'][0])
+        got = h2.step(u_start=h2.vector_t_start, t_start=0.1, t_stop=0.1 + dt).get_values()
+        ref = g[f'heat2d_65x49/out{k}']
+        assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_heat2d_512_step_against_oracle(P):
+    """BASELINE.json configs[2] size (512 x 512): one backward-Euler step on level 0 and one with the coarsest
+    level's dt, GPU (sine space) against the CPU oracle (sparse direct solve of the same system)."""
+    from oracle import mgrit_oracle as O
+    kw = dict(x_start=0, x_end=1, y_start=0, y_end=1, nx=512, ny=512, a=1, rhs=C.heat2d_rhs, init_cond=C.heat2d_init)
+    app = P.Heat2D(t_start=0, t_stop=5, nt=4097, **kw)
+    orc = O.Heat2DOracle(t_start=0, t_stop=5, nt=4097, **kw)
+    for dt in (5.0 / 4096, 512 * 5.0 / 4096):
+        got = app.step(u_start=app.vector_t_start, t_start=0.5, t_stop=0.5 + dt).get_values()
+        ref = orc.phi(orc.u0, 0.5, 0.5 + dt)
+        assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    # the transforms are inverse to each other and orthogonal
+    fam = app.family()
+    v = app.vector_t_start
+    rows = fam.to_rows(v.device_values.reshape(1, 512, 512))
+    back = fam.from_rows(rows)[0].cpu().numpy()
+    assert np.max(np.abs(back - v.get_values())) <= 1e-13
+    assert abs(float(rows.norm()) - v.norm()) <= 1e-12 * v.norm()
+
+
+@pytest.mark.parametrize('make', [
+    lambda P: P.Heat1D(a=1, init_cond=lambda x: 2 * x, x_start=0, x_end=1, nx=12, t_start=0, t_stop=1, nt=11),
+    lambda P: P.Heat2D(a=1, x_start=0, x_end=1, y_start=3, y_end=4, nx=7, ny=9, init_cond=lambda x, y: x * y,
+                       t_start=0, t_stop=1, nt=11),
+    lambda P: P.Advection1D(c=1, x_start=0, x_end=1, nx=9, t_start=0, t_stop=1, nt=11),
+    lambda P: P.Brusselator(t_start=0, t_stop=1, nt=11),
+], ids=['heat1d', 'heat2d', 'advection1d', 'brusselator'])
+def test_vector_operations(P, make):
+    """The Vector contract (core/vector.py:38-151): out-of-place +, -, *, norm, clone family, set/get, pack/unpack."""
+    app = make(P)
+    v = app.vector_t_start
+    a = np.array(v.get_values(), dtype=float)
+    w = v.clone_rand()
+    b = np.array(w.get_values(), dtype=float)
+    assert a.shape == b.shape == tuple(app.vector_template.shape)
+    np.testing.assert_array_equal((v + w).get_values(), a + b)
+    np.testing.assert_array_equal((v - w).get_values(), a - b)
+    np.testing.assert_array_equal((v * 1.7).get_values(), a * 1.7)
+    np.testing.assert_array_equal((1.7 * v).get_values(), a * 1.7)
+    assert abs(w.norm() - np.linalg.norm(b)) <= 1e-14 * np.linalg.norm(b)
+    z = v.clone_zero()
+    assert not np.any(z.get_values())
+    c = v.clone()
+    c.set_values(a * 2)
+    np.testing.assert_array_equal(v.get_values(), a)                 # clone does not alias
+    u = v.clone_zero()
+    u.unpack(c.pack())
+    np.testing.assert_array_equal(u.get_values(), a * 2)
+    v2 = copy.deepcopy(v)
+    np.testing.assert_array_equal(v2.get_values(), a)
+
+
+def test_solver_state_is_user_visible(P):
+    """output_fcn / user code reads self.u[0][i], self.t[0], self.index_local_c[0] (docs/source/usage/advanced.rst)."""
+    prob = P.simple_setup_problem(P.Heat2D(x_start=0, x_end=1, y_start=0, y_end=1, nx=17, ny=21, a=1, rhs=C.heat2d_rhs,
+                                           t_start=0, t_stop=1, nt=17), level=2, coarsening=4)
+    seen = {}
+
+    def output(self):
+        seen['last'] = self.u[0][-1].get_values().copy()
+        seen['t'] = self.t[0][-1]
+        seen['c'] = list(self.index_local_c[0])
+
+    import logging
+    solver = P.Mgrit(problem=prob, output_fcn=output, tol=1e-9, logging_lvl=logging.WARNING)
+    solver.solve()
+    assert seen['last'].shape == (17, 21) and seen['t'] == 1.0 and seen['c'][:2] == [0, 4]
+    assert np.array_equal(seen['last'][0], np.zeros(21))              # Dirichlet boundary
+    # writing a vector back and reading it again round-trips through the level storage
+    v = solver.u[0][3]
+    solver.u[0][5] = v
+    assert np.max(np.abs(solver.u[0][5].get_values() - v.get_values())) <= 1e-13
