@@ -163,7 +163,7 @@ class Mgrit:
 
         # index tables (mgrit.py:206-222, 742-827) and level storage in HBM (mgrit.py:840-858)
         self.global_t = [np.copy(p.t) for p in problem]
-        part = partition.Partition(self.global_t, self.comm_time_size, self.comm_time_rank)
+        part = partition.Partition(self.global_t, self.comm_time_size, self.comm_time_rank, masks=masks)
         self._part = part
         self.m = part.m
         self.cpts = part.cpts
@@ -259,7 +259,8 @@ class Mgrit:
         m = self.m[0]
         row = 8.0 * lv.n
         sweeps = [
-            ('f_relax', lambda: self.f_relax(0), m, 1),
+            ('f_relax', lambda: self.f_relax(0), m, 0),                          # public sweep (stores every F-point)
+            ('f_relax(last point only)', lambda: self.f_relax(0, last_only=True), 2, 1),     # down-sweep variant
             ('c_relax', lambda: self.c_relax(0), 2 + (1 if self.weight_c != 1.0 else 0), 1),
             ('fas_residual', lambda: self.fas_residual(0), 5, 1),
             ('error_correction+f_relax', lambda: self.error_correction(0, f_relax=True), m + 2, 1),
@@ -287,11 +288,14 @@ class Mgrit:
         if lvl == self.lvl_max - 1:
             self.forward_solve(lvl=lvl)
             return
+        # Down-sweep: C-relaxation and the FAS restriction read only the last F-point of an interval, and the
+        # F-relaxation fused into error_correction() below rewrites every F-point, so the F-relaxations here keep
+        # only those last points (same values, the dead stores are skipped).
         if (lvl > 0 or (iteration == 0 and lvl == 0)) and first_f:
-            self.f_relax(lvl=lvl)
+            self.f_relax(lvl=lvl, last_only=True)
         for _ in range(self.cf_iter[lvl]):
             self.c_relax(lvl=lvl)
-            self.f_relax(lvl=lvl)
+            self.f_relax(lvl=lvl, last_only=True)
         self.fas_residual(lvl=lvl)
         self.iteration(lvl=lvl + 1, cycle_type=cycle_type, iteration=iteration, first_f=True)
         self.error_correction(lvl=lvl, f_relax=True)        # correction + the F-relaxation of mgrit.py:287, one launch

@@ -144,10 +144,10 @@ def reference_decomposition(global_t, size, rank):
 class Partition:
     """Aligned slab partition used by the engine (see module docstring)."""
 
-    def __init__(self, global_t, size, rank):
+    def __init__(self, global_t, size, rank, masks=None):
         self.size, self.rank = size, rank
         L = len(global_t)
-        masks = c_point_masks(global_t)
+        masks = c_point_masks(global_t) if masks is None else masks
         self.m = coarsening_factors(global_t, masks)
         t0 = global_t[0]
         n0 = len(t0)

@@ -235,6 +235,13 @@ __global__ void k_sumsq(int n, const double *__restrict__ x, double *__restrict_
 // ---- host-side step constants -------------------------------------------------------------------------
 static long double lpow(long double b, long e) { return e <= 0 ? 1.0L : powl(b, (long double)e); }
 
+// doubling steps of the cross-lane scan whose ratio B^(2^k) still matters (>= 1e-30)
+static int scan_steps(long double B) {
+    int n = 0;
+    while (n < 5 && lpow(B, 1L << n) >= 1e-30L) ++n;
+    return n;
+}
+
 }  // namespace mgb
 
 using namespace mgb;
@@ -286,7 +293,7 @@ int mgb_step_consts_width(int32_t app, int32_t team_threads, int32_t chunk) {
 int mgb_heat1d_step_consts(double r_, int32_t n, int32_t T, int32_t E, double *out) {
     if (!(r_ > 0.0) || n < 1 || T < 32 || E < 1 || out == nullptr) return fail(MGB_EINVAL, "bad argument%s");
     const int SUB = (E % 3 == 0) ? 3 : 1, SL = E / SUB, PT = 2 + 2 * SUB;
-    if (SL > 14) return fail(MGB_EINVAL, "chunk too long%s");
+    if (SL > 13) return fail(MGB_EINVAL, "chunk too long%s");
     const long double r = r_;
     // delta = 2 + 1/r; beta = smaller root of b^2 - delta b + 1;  delta^2 - 4 = (4 + 1/r)/r
     const long double delta = 2.0L + 1.0L / r;
@@ -302,6 +309,7 @@ int mgb_heat1d_step_consts(double r_, int32_t n, int32_t T, int32_t E, double *o
     for (int k = 0; k < 5; ++k) out[4 + k] = (double)lpow(B, 1L << k);
     out[9] = (double)lpow(B, 32);
     for (int j = 0; j < SL; ++j) out[10 + j] = (double)lpow(beta, j + 1);
+    out[23] = (double)scan_steps(B);
     for (int t = 0; t < T; ++t) {
         double *pt = out + kScalarConsts + t * PT;
         const int lane = t & 31;
@@ -321,7 +329,7 @@ int mgb_heat1d_step_consts(double r_, int32_t n, int32_t T, int32_t E, double *o
 int mgb_advection1d_step_consts(double nu_, int32_t n, int32_t T, int32_t E, double *out) {
     if (!(nu_ > 0.0) || n < 1 || T < 32 || E < 1 || out == nullptr) return fail(MGB_EINVAL, "bad argument%s");
     const int SUB = (E % 3 == 0) ? 3 : 1, SL = E / SUB, PT = 2 + 2 * SUB;
-    if (SL > 14) return fail(MGB_EINVAL, "chunk too long%s");
+    if (SL > 13) return fail(MGB_EINVAL, "chunk too long%s");
     const long double nu = nu_;
     const long double rho = nu / (1.0L + nu), sig = 1.0L / (1.0L + nu);
     const long double B = lpow(rho, E);
@@ -333,6 +341,7 @@ int mgb_advection1d_step_consts(double nu_, int32_t n, int32_t T, int32_t E, dou
     for (int k = 0; k < 5; ++k) out[4 + k] = (double)lpow(B, 1L << k);
     out[9] = (double)lpow(B, 32);
     for (int j = 0; j < SL; ++j) out[10 + j] = (double)lpow(rho, j + 1);
+    out[23] = (double)scan_steps(B);
     for (int t = 0; t < T; ++t) {
         double *pt = out + kScalarConsts + t * PT;
         pt[0] = (double)lpow(B, t & 31);

@@ -122,12 +122,16 @@ struct Team {
 
     // Exclusive forward scan with constant ratio B:  returns sum_{i < tid} B^(tid-1-i) a_i.
     // Bd = {B, B^2, B^4, B^8, B^16}; B32 = B^32; blane = B^lane.
-    __device__ __forceinline__ double scan_fwd(double a, const double (&Bd)[5], double B32, double blane) {
+    // Only the first `nsteps` doubling steps are done: the host sets nsteps so that the dropped powers B^(2^k) are
+    // below 1e-30 (a lane that far away cannot contribute to any digit of the result).
+    __device__ __forceinline__ double scan_fwd(double a, const double (&Bd)[5], double B32, double blane, int nsteps = 5) {
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const int d = 1 << k;
-            const double t = shfl_up_d(a, d);
-            if (lane >= d) a = fma(Bd[k], t, a);
+            if (k < nsteps) {
+                const int d = 1 << k;
+                const double t = shfl_up_d(a, d);
+                if (lane >= d) a = fma(Bd[k], t, a);
+            }
         }
         double excl = shfl_up_d(a, 1);
         if (lane == 0) excl = 0.0;
@@ -144,12 +148,14 @@ struct Team {
     }
 
     // Exclusive backward scan:  returns sum_{i > tid} B^(i-tid-1) a_i.   blane = B^(31-lane).
-    __device__ __forceinline__ double scan_bwd(double a, const double (&Bd)[5], double B32, double blane) {
+    __device__ __forceinline__ double scan_bwd(double a, const double (&Bd)[5], double B32, double blane, int nsteps = 5) {
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const int d = 1 << k;
-            const double t = shfl_down_d(a, d);
-            if (lane + d < 32) a = fma(Bd[k], t, a);
+            if (k < nsteps) {
+                const int d = 1 << k;
+                const double t = shfl_down_d(a, d);
+                if (lane + d < 32) a = fma(Bd[k], t, a);
+            }
         }
         double excl = shfl_down_d(a, 1);
         if (lane == 31) excl = 0.0;

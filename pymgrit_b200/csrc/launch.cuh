@@ -1,5 +1,7 @@
 // launch.cuh -- host-side launchers for the team kernels of sweeps.cuh, one table per (Phi, T, E).
 #pragma once
+#include <cstdlib>
+
 #include "sweeps.cuh"
 #include "table.h"
 
@@ -36,7 +38,12 @@ struct Launch {
     // flags & 1: store only the last point of every interval (the other F-points are dead in a down-sweep)
     static int f_relax(const LevelDev &L, int flags, cudaStream_t st) {
         if (L.ncpts < 1) return 0;
-        const int nin = 2 + rows_extra(L), nw = L.ncpts * nsys(L);
+        int nin = 2 + rows_extra(L);
+        if (flags & 1) {  // compute-bound variant: fewer staging slots -> more resident teams per SM
+            static const int knob = getenv("MGB_LAST_ONLY_NIN") ? atoi(getenv("MGB_LAST_ONLY_NIN")) : 0;
+            if (knob > 0) nin = knob + rows_extra(L);
+        }
+        const int nw = L.ncpts * nsys(L);
         int grid;
         if (int rc = grid_for(k_chain<Phi>, nw, nin, &grid)) return rc;
         k_chain<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, nw, flags & 1, nin);

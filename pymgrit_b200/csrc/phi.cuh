@@ -61,7 +61,7 @@ struct SubSplit {
 // ---------------------------------------------------------------------------------------------
 // Heat1D.  Step-constant row layout (doubles), written by mgb_heat1d_step_consts:
 //   [0] beta  [1] beta/r  [2] kappa = beta/(1+beta h0)  [3] beta^SL  [4..8] B^1,2,4,8,16 (B = beta^E)
-//   [9] B^32  [10..10+SL) beta^(jj+1)
+//   [9] B^32  [10..10+SL) beta^(jj+1)   [23] number of scan steps whose power B^(2^k) is >= 1e-30
 //   [24 + tid*PT ...): B^lane, B^(31-lane), PH[SUB], QH[SUB]      (PT = 2 + 2 SUB)
 // with PH[s] = beta^(tid E + s SL)/(1-beta^2), QH[s] = beta^(2n+1-tid E-(s+1) SL)/(1-beta^2) (0 where
 // the sub-chunk holds no valid element).
@@ -72,10 +72,11 @@ struct Heat1D {
     static constexpr int T = T_, E = E_;
     static constexpr int SUB = SubSplit<E_>::SUB, SL = SubSplit<E_>::SL;
     static constexpr int PT = 2 + 2 * SUB;
-    static_assert(SL <= 14, "power table does not fit the scalar block");
+    static_assert(SL <= 13, "power table does not fit the scalar block");
 
     struct C {
         double beta, cs, kappa, bsl, Bd[5], B32, pw[SL], blf, blb, PH[SUB], QH[SUB];
+        int nscan;
     };
 
     __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int tid) {
@@ -88,6 +89,7 @@ struct Heat1D {
         c.B32 = __ldg(row + 9);
 #pragma unroll
         for (int j = 0; j < SL; ++j) c.pw[j] = __ldg(row + 10 + j);
+        c.nscan = (int)__ldg(row + 23);
         const double *pt = row + kScalarConsts + tid * PT;
         c.blf = __ldg(pt + 0);
         c.blb = __ldg(pt + 1);
@@ -132,7 +134,7 @@ struct Heat1D {
         double a = e[0];
 #pragma unroll
         for (int s = 1; s < SUB; ++s) a = fma(c.bsl, a, e[s]);
-        double in = team.scan_fwd(a, c.Bd, c.B32, c.blf);
+        double in = team.scan_fwd(a, c.Bd, c.B32, c.blf, c.nscan);
         // add the inflow; everything beyond element n-1 must stay exactly 0 for the backward recurrence
         if (L.n % E == 0) {
             // no thread holds a partially valid chunk (e.g. n = 1023 = 31 x 33): threads beyond n have zero data, so
@@ -176,7 +178,7 @@ struct Heat1D {
 #pragma unroll
         for (int s = SUB - 2; s >= 0; --s) a2 = fma(c.bsl, a2, f[s]);
         double inb[SUB];
-        inb[SUB - 1] = team.scan_bwd(a2, c.Bd, c.B32, c.blb);
+        inb[SUB - 1] = team.scan_bwd(a2, c.Bd, c.B32, c.blb, c.nscan);
 #pragma unroll
         for (int s = SUB - 2; s >= 0; --s) inb[s] = fma(c.bsl, inb[s + 1], f[s + 1]);
         // Sherman-Morrison:  x = z - gamma h,  gamma = kappa * z_0
@@ -198,7 +200,7 @@ struct Heat1D {
 // ---------------------------------------------------------------------------------------------
 // Advection1D.  Step-constant row layout:
 //   [0] rho  [1] sigma  [2] 1/(1-rho^n)  [3] rho^SL  [4..8] B^1,2,4,8,16 (B = rho^E)  [9] B^32
-//   [10..10+SL) rho^(jj+1)
+//   [10..10+SL) rho^(jj+1)   [23] number of scan steps (as for Heat1D)
 //   [24 + tid*PT ...): B^lane, (unused), RH[SUB] = rho^(tid E + s SL), (unused)[SUB]
 // ---------------------------------------------------------------------------------------------
 template <int T_, int E_>
@@ -210,6 +212,7 @@ struct Advection1D {
 
     struct C {
         double rho, sig, dinv, rsl, Bd[5], B32, pw[SL], blf, RH[SUB];
+        int nscan;
     };
 
     __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int tid) {
@@ -222,6 +225,7 @@ struct Advection1D {
         c.B32 = __ldg(row + 9);
 #pragma unroll
         for (int j = 0; j < SL; ++j) c.pw[j] = __ldg(row + 10 + j);
+        c.nscan = (int)__ldg(row + 23);
         const double *pt = row + kScalarConsts + tid * PT;
         c.blf = __ldg(pt + 0);
 #pragma unroll
@@ -253,7 +257,7 @@ struct Advection1D {
         double a = e[0];
 #pragma unroll
         for (int s = 1; s < SUB; ++s) a = fma(c.rsl, a, e[s]);
-        double in = team.scan_fwd(a, c.Bd, c.B32, c.blf);
+        double in = team.scan_fwd(a, c.Bd, c.B32, c.blf, c.nscan);
         // solution with zero inflow at element 0; pick out its last element
         double ylast = 0.0;
         double ins[SUB];

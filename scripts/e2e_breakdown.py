@@ -1,0 +1,43 @@
+"""Where the end-to-end time of the headline workload goes (host setup vs device), run on the GPU box:
+
+    python scripts/e2e_breakdown.py [cfg5|cfg2]
+"""
+import cProfile
+import logging
+import os
+import pstats
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+import pymgrit_b200 as P
+
+wl = sys.argv[1] if len(sys.argv) > 1 else 'cfg5'
+nt, co = bench.WORKLOADS[wl]
+
+
+def run():
+    t = [time.perf_counter()]
+    prob = bench.hierarchy(P.Heat1D, nt, co)
+    t.append(time.perf_counter())
+    s = P.Mgrit(problem=prob, logging_lvl=logging.WARNING, **bench.SOLVER_KW)
+    t.append(time.perf_counter())
+    info = s.solve()
+    t.append(time.perf_counter())
+    last = s.u[0][-1].get_values()
+    torch.cuda.synchronize()
+    t.append(time.perf_counter())
+    return [1e3 * (b - a) for a, b in zip(t, t[1:])], s
+
+
+for k in range(4):
+    ms, s = run()
+    print('hierarchy %.1f ms | Mgrit() %.1f ms | solve() %.1f ms | readback %.1f ms | total %.1f ms' % (*ms, sum(ms)))
+    del s
+pr = cProfile.Profile()
+pr.enable()
+run()
+pr.disable()
+pstats.Stats(pr).sort_stats('cumulative').print_stats(35)

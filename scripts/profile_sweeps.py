@@ -1,6 +1,6 @@
 """Launch every level-0 sweep of the headline workload twice (warm-up pass, then the pass ncu captures).
 
-    ncu --set full --clock-control none --import-source on -s 5 -c 5 -o gpurun_out/prof python scripts/profile_sweeps.py
+    ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 6 -o gpurun_out/prof python scripts/profile_sweeps.py
 """
 import logging
 import os
@@ -18,6 +18,7 @@ problem = P.simple_setup_problem(P.Heat1D(nt=nt, **bench.HEAT_KW), level=levels,
 solver = P.Mgrit(problem=problem, nested_iteration=False, logging_lvl=logging.WARNING, tol=1e-10)
 for _ in range(2):
     solver.f_relax(0)
+    solver.f_relax(0, last_only=True)
     solver.c_relax(0)
     solver.fas_residual(0)
     solver.error_correction(0, f_relax=True)
