@@ -134,3 +134,22 @@ def test_phi_step_fixtures():
         got = h2.phi(h2.u0, 0.1, 0.1 + dt)
         ref = g[f'heat2d_65x49/out{k}']
         assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))
+
+
+def test_parallel_oracle_is_bitwise_serial():
+    """The time-parallel CPU baseline (oracle/mgrit_oracle_mp.py: forked workers over shared level arrays, one block of
+    intervals per worker like the reference's time ranks) reproduces the serial oracle exactly."""
+    from oracle import mgrit_oracle_mp as OM
+    from oracle_util import oracle_problem
+    for name in ('heat1d_small_f_cf2', 'heat1d_varying_w', 'heat1d_small_jump'):
+        case = C.CASES[name]
+        serial = O.MgritOracle(oracle_problem(case), **case['solver'])
+        ref = serial.solve()
+        par = OM.ParallelMgritOracle(oracle_problem(case), workers=3, **case['solver'])
+        try:
+            got = par.solve()
+            np.testing.assert_array_equal(got['conv'], ref['conv'])
+            np.testing.assert_array_equal(par.u[0], serial.u[0])
+            assert sum(par.nphi) == sum(serial.nphi)
+        finally:
+            par.close()
