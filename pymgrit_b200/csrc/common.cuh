@@ -14,6 +14,21 @@
 
 namespace mgb {
 
+// Optional cycle probes (scripts/micro/chain_cycles.cu defines MGB_CYCLES): where a team's time goes.
+#ifdef MGB_CYCLES
+__device__ long long g_cyc[24];
+#define MGB_T0 long long _t0 = clock64();
+#define MGB_T(k)                                  \
+    {                                             \
+        const long long _t1 = clock64();          \
+        if (threadIdx.x == 0) g_cyc[k] += _t1 - _t0; \
+        _t0 = _t1;                                \
+    }
+#else
+#define MGB_T0
+#define MGB_T(k)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
@@ -255,7 +270,9 @@ struct RowPipe {
     // Next input row -> registers (elements beyond n read as 0).
     template <class TeamT>
     __device__ __forceinline__ void pop(double (&x)[E], TeamT &team) {
+        MGB_T0
         mbar_wait(bar0 + 8u * cons_slot, cons_parity);
+        MGB_T(0)
         const double *s = in_slot(cons_slot) + tid * E;
         const int nv = n - tid * E;
 #pragma unroll
@@ -264,7 +281,9 @@ struct RowPipe {
             x[j] = (j < nv) ? v : 0.0;
         }
         team.sync();
+        MGB_T(1)
         if (tid == 0) issue(cons_slot);
+        MGB_T(2)
         ++cons;
         if (++cons_slot == nin) {
             cons_slot = 0;
@@ -275,17 +294,22 @@ struct RowPipe {
     // Registers -> output row in HBM.
     template <class TeamT>
     __device__ __forceinline__ void push(const double (&x)[E], double *dst, TeamT &team) {
+        MGB_T0
         if (tid == 0) bulk_wait_read<0>();
         team.sync();
+        MGB_T(3)
         double *s = out_slot() + tid * E;
 #pragma unroll
         for (int j = 0; j < E; ++j) s[j] = x[j];
+        MGB_T(4)
         fence_proxy_async();
         team.sync();
+        MGB_T(5)
         if (tid == 0) {
             bulk_s2g(dst, smem_u32(out_slot()), row_bytes);
             bulk_commit();
         }
+        MGB_T(6)
     }
 
     template <class TeamT>

@@ -65,18 +65,22 @@ __device__ __forceinline__ void step_consts(typename Phi::C &c, const LevelDev &
 template <class Phi, class Pipe, class TeamT>
 __device__ __forceinline__ void advance(double (&x)[Phi::E], typename Phi::C &c, const typename Phi::Item &it,
                                         const LevelDev &L, int i, Pipe &pipe, TeamT &team, bool add_g = true) {
+    MGB_T0
     step_consts<Phi>(c, L, i, team.tid);
     if (L.rhs_dense) {
         double b[Phi::E];
         pipe.pop(b, team);
         vadd(x, b);
     }
+    MGB_T(8)
     Phi::apply(x, c, it, L, i, team);
+    MGB_T(9)
     if (add_g && L.g) {
         double gg[Phi::E];
         pipe.pop(gg, team);
         vadd(x, gg);
     }
+    MGB_T(10)
 }
 
 // rows `advance` pops for step i, in order: returns false when stage runs past them
