@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 2
+#define MGB_ABI_VERSION 3
 
 /* application kinds (which Phi) */
 #define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
@@ -138,6 +138,14 @@ int mgb_c_relax(const mgb_level *lvl, double weight, void *stream);
  *                 - Phi_c(fine.u[c_{j-1}]). */
 int mgb_fas_residual(const mgb_level *fine, const mgb_level *coarse, void *stream);
 
+/* The down-sweep of a cycle in one pass, mgrit.py:277-281 + 488-549: exactly mgb_c_relax(fine, 1.0), then
+ * mgb_f_relax(fine, MGB_F_RELAX_LAST_ONLY), then mgb_fas_residual(fine, coarse) -- bit-identical values in fine.u at the
+ * C-points, coarse.u and coarse.g -- except that the last F-point of every interval is not stored (nothing reads it before
+ * the F-relaxation after the coarse-grid correction rewrites the interval).  Per interval 2 rows are read and 3 written
+ * instead of 5 + 4.  Requires weight 1 and at least one F-point between any two C-points (no adjacent C-points); the
+ * caller checks (pymgrit_b200/core/mgrit.py).  MGB_ENOSHAPE for the ODE applications (no team kernels). */
+int mgb_down_sweep(const mgb_level *fine, const mgb_level *coarse, void *stream);
+
 /* Coarse-grid correction, mgrit.py:715-726: fine.u[c_j] += coarse.u[j] - v[j], j >= 1.  flags:
  *   MGB_CORRECT_F_RELAX  also run the F-relaxation of mgrit.py:287 out of the same registers (one launch);
  *   MGB_CORRECT_GHOST    point 0 is the ghost copy of the previous time rank's last C-point (time rank > 0):
@@ -187,6 +195,27 @@ int mgb_heat2d_to_rows(int32_t nx, int32_t ny, const double *sx_dev, const doubl
 /* The inverse: nodes[b] from rows[b]. */
 int mgb_heat2d_from_rows(int32_t nx, int32_t ny, const double *sx_dev, const double *sy_dev, const double *rows_dev,
                          double *nodes_dev, int32_t count, double *work_dev, void *stream);
+
+/* ---- Heat1D: the coarsest-level solve in sine space (csrc/spectral.cu) ------------------------------------- */
+/* mgrit.py:459-486 runs npts-1 dependent Phi applications on one spatial system; every time rank waits for that chain
+ * (mgrit.py:467-484).  For HEAT1D the spatial operator is Toeplitz: with the rows transformed by the orthonormal sine
+ * matrix S (S = S^T = S^-1) the chain decouples into n independent scalar recurrences.  Usage for a level `lvl`:
+ *     work[0]  = u[0] S;  work[i] = g[i] S (i >= 1; 0 without g)        mgb_rows_gemm (one launch, a_row0 = u[0])
+ *     work[i]  = (work[i-1] + sum_q rhs_t[i][q] rxhat[q]) / (1 + dt_i lam) + work[i]      mgb_heat1d_spectral_recur
+ *     u[i]     = work[i] S                                              mgb_rows_gemm
+ * Between time ranks only work[npts-1] -> next rank's work[0] travels. */
+
+/* s_dev[j*ld + k] = sqrt(2/(n+1)) sin(pi (j+1)(k+1)/(n+1)), j, k < n. */
+int mgb_sine_matrix(int32_t n, double *s_dev, int32_t ld, void *stream);
+/* c (m x n, ldc) = a (m x k, lda) * b (k x n, ldb): plain FP64 product on the CUDA cores, row-major.  If a_row0_dev is
+ * not NULL, row 0 of a is read from there (the level's u[0] next to its g rows). */
+int mgb_rows_gemm(int32_t m, int32_t n, int32_t k, const double *a_dev, int32_t lda, const double *a_row0_dev,
+                  const double *b_dev, int32_t ldb, double *c_dev, int32_t ldc, void *stream);
+/* The n scalar recurrences, in place on work_dev [npts][pitch].  lam_dev [n] = eigenvalues of the spatial operator
+ * (a/dx^2) tridiag(-1, 2, -1); rxhat_dev [nrhs][pitch] = the spatial right-hand-side factors times S (rhs_t_dev of the
+ * level supplies the time factors).  Needs a separable right-hand side (rhs_dense_dev == NULL), nrhs <= 4. */
+int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const double *rxhat_dev, double *work_dev,
+                              void *stream);
 
 /* ---- Vector arithmetic (core/vector.py:38-110) ---------------------------------------------- */
 /* out = a*x + b*y on n doubles */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libmgrit_b200.so')
 
 APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D = 1, 2, 3, 4, 5
 TNORM_ONE, TNORM_TWO, TNORM_INF = 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 F_RELAX_LAST_ONLY = 1
 DAHLQUIST_METHODS = {'BE': 0, 'FE': 1, 'TR': 2, 'MR': 3}
 
@@ -48,6 +48,7 @@ SYMBOLS = {
     'mgb_f_relax': (C.c_int, [_LP, C.c_int32, C.c_void_p]),
     'mgb_c_relax': (C.c_int, [_LP, C.c_double, C.c_void_p]),
     'mgb_fas_residual': (C.c_int, [_LP, _LP, C.c_void_p]),
+    'mgb_down_sweep': (C.c_int, [_LP, _LP, C.c_void_p]),
     'mgb_error_correction': (C.c_int, [_LP, _LP, C.c_int32, C.c_void_p]),
     'mgb_forward_solve': (C.c_int, [_LP, C.c_void_p]),
     'mgb_residual_norms': (C.c_int, [_LP, C.c_void_p, C.c_void_p]),
@@ -60,6 +61,10 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p]),
     'mgb_heat2d_from_rows': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p]),
+    'mgb_sine_matrix': (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    'mgb_rows_gemm': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                C.c_void_p, C.c_int32, C.c_void_p]),
+    'mgb_heat1d_spectral_recur': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_vec_axpby': (C.c_int, [C.c_int32, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_vec_sumsq': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -27,10 +27,10 @@ class SerialComm:
     def exchange_ghost(self, solver, lvl):
         return None
 
-    def recv_chain(self, solver, lvl):
+    def recv_chain(self, solver, lvl, row=None):
         return None
 
-    def send_chain(self, solver, lvl):
+    def send_chain(self, solver, lvl, row=None):
         return None
 
     def reduce_norm(self, partial, t_norm):
@@ -81,15 +81,16 @@ class TorchDistComm:
             return
         self.shift_rows(lv.u[lv.npts - 1], lv.u[0])
 
-    def recv_chain(self, solver, lvl):
+    def recv_chain(self, solver, lvl, row=None):
+        """row: where the incoming row goes (default: the ghost row u[0] of the level)."""
         lv = solver._lv[lvl]
         if self.rank > 0 and lv.npts > 0:
-            self.dist.recv(lv.u[0], self._global(self.rank - 1), group=self.group)
+            self.dist.recv(lv.u[0] if row is None else row, self._global(self.rank - 1), group=self.group)
 
-    def send_chain(self, solver, lvl):
+    def send_chain(self, solver, lvl, row=None):
         lv = solver._lv[lvl]
         if self.rank + 1 < self.size and lv.npts > 0:
-            self.dist.send(lv.u[lv.npts - 1], self._global(self.rank + 1), group=self.group)
+            self.dist.send(lv.u[lv.npts - 1] if row is None else row, self._global(self.rank + 1), group=self.group)
 
     def reduce_norm(self, partial, t_norm):
         op = self.dist.ReduceOp.MAX if t_norm == 3 else self.dist.ReduceOp.SUM

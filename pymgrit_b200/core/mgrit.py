@@ -176,6 +176,26 @@ class Mgrit:
         for lvl in range(self.lvl_max):
             cp = part.sweep_cpts[lvl] if lvl < self.lvl_max - 1 else None
             self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0))
+        # levels whose down-sweep runs as one fused launch (mgb_down_sweep): unweighted C-relaxation, at least one
+        # F-point in every interval, team kernels, one time rank (the ghost C-point would need its own F-point)
+        import os
+        self._fused_down = []
+        for lvl in range(self.lvl_max - 1):
+            cp = self._lv[lvl].cpts
+            ok = (weight_c == 1.0 and self.comm_time_size == 1 and cp is not None and len(cp) > 1 and
+                  int(np.min(np.diff(cp))) >= 2 and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D,
+                                                                         _lib.APP_HEAT2D)
+                  and os.environ.get('MGB_FUSED_DOWN', '1') != '0')
+            self._fused_down.append(bool(ok))
+        self._fused_down.append(False)
+        # the sequential solve on the coarsest level in sine space where the application offers it (Heat1D)
+        self._spectral = {}
+        last = self._lv[-1]
+        maker = getattr(problem[-1], 'spectral_solver', None)
+        if maker is not None and self._all_ranks(last.npts >= getattr(problem[-1], 'SPECTRAL_MIN_POINTS', 1 << 30)):
+            sp = maker(last) if last.npts > 0 else None
+            if sp is not None:
+                self._spectral[self.lvl_max - 1] = sp
         self.u = [_LevelVectors(lv, 'u') for lv in self._lv]
         self.g = [None] + [_LevelVectors(lv, 'g') for lv in self._lv[1:]]
         self.v = [None] * self.lvl_max       # never materialised: identical to the fine level's C-point rows
@@ -218,6 +238,10 @@ class Mgrit:
                 if lv.npts > 0:
                     lv.set_vector(lv.u, 0, lv.app.vector_t_start)
 
+    def _all_ranks(self, flag: bool) -> bool:
+        """True if `flag` holds on every time rank (all ranks must take the same path through a chain exchange)."""
+        return all(self.comm_time.allgather(bool(flag)))
+
     def log_info(self, message: str) -> None:
         """Only the last time rank logs (mgrit.py:247-259)."""
         if self.comm_time_rank == self.comm_time_size - 1:
@@ -246,7 +270,8 @@ class Mgrit:
     @property
     def h2d_bytes(self):
         """Bytes copied host -> device while building the levels (tables, time grids, initial condition)."""
-        return sum(lv.h2d_bytes for lv in self._lv) + 8 * self._lv[0].n * self.lvl_max
+        return (sum(lv.h2d_bytes for lv in self._lv) + 8 * self._lv[0].n * self.lvl_max +
+                sum(sp.h2d_bytes for sp in self._spectral.values()))
 
     def time_level0_sweeps(self, repeats: int = 5):
         """CUDA-event timing of each level-0 sweep alone (bench.py roofline): list of dicts with the algorithmic
@@ -293,10 +318,16 @@ class Mgrit:
         # only those last points (same values, the dead stores are skipped).
         if (lvl > 0 or (iteration == 0 and lvl == 0)) and first_f:
             self.f_relax(lvl=lvl, last_only=True)
-        for _ in range(self.cf_iter[lvl]):
-            self.c_relax(lvl=lvl)
-            self.f_relax(lvl=lvl, last_only=True)
-        self.fas_residual(lvl=lvl)
+        fused = False
+        for k in range(self.cf_iter[lvl]):
+            if k == self.cf_iter[lvl] - 1 and self._fused_down[lvl]:
+                self.down_sweep(lvl=lvl)            # C-relaxation, F-relaxation and FAS restriction in one launch
+                fused = True
+            else:
+                self.c_relax(lvl=lvl)
+                self.f_relax(lvl=lvl, last_only=True)
+        if not fused:
+            self.fas_residual(lvl=lvl)
         self.iteration(lvl=lvl + 1, cycle_type=cycle_type, iteration=iteration, first_f=True)
         self.error_correction(lvl=lvl, f_relax=True)        # correction + the F-relaxation of mgrit.py:287, one launch
         if lvl != 0 and cycle_type == 'F':
@@ -320,6 +351,13 @@ class Mgrit:
             coarse.u[0].copy_(fine.u[0])             # the ghost / initial C-point is injected like any other
         _lib.check(_lib.lib().mgb_fas_residual(fine.ref, coarse.ref, self._stream()), 'fas_residual')
 
+    def down_sweep(self, lvl: int) -> None:
+        """c_relax + f_relax(last_only) + fas_residual of level lvl in one pass over the level (same values)."""
+        fine, coarse = self._lv[lvl], self._lv[lvl + 1]
+        if coarse.npts > 0 and fine.npts > 0:
+            coarse.u[0].copy_(fine.u[0])
+        _lib.check(_lib.lib().mgb_down_sweep(fine.ref, coarse.ref, self._stream()), 'down_sweep')
+
     def error_correction(self, lvl: int, f_relax: bool = False) -> None:
         """Coarse-grid correction of the C-points (mgrit.py:715-726), optionally fused with the next F-relaxation."""
         flags = (1 if f_relax else 0) | (2 if self.comm_time_rank > 0 else 0)      # MGB_CORRECT_F_RELAX | MGB_CORRECT_GHOST
@@ -328,10 +366,22 @@ class Mgrit:
         # no exchange: every rank corrects its ghost copy itself (MGB_CORRECT_GHOST)
 
     def forward_solve(self, lvl: int) -> None:
-        """Sequential time stepping on level lvl (mgrit.py:459-486)."""
-        self.comm_time.recv_chain(self, lvl)
-        _lib.check(_lib.lib().mgb_forward_solve(self._lv[lvl].ref, self._stream()), 'forward_solve')
-        self.comm_time.send_chain(self, lvl)
+        """Sequential time stepping on level lvl (mgrit.py:459-486).  Heat1D levels that are long enough are solved
+        in sine space (csrc/spectral.cu): two transforms and n independent scalar recurrences instead of a chain of
+        tridiagonal solves; between time ranks the last row travels in sine space."""
+        lv = self._lv[lvl]
+        sp = self._spectral.get(lvl) if lv.npts > 0 else None
+        if sp is None:
+            self.comm_time.recv_chain(self, lvl)
+            _lib.check(_lib.lib().mgb_forward_solve(lv.ref, self._stream()), 'forward_solve')
+            self.comm_time.send_chain(self, lvl)
+            return
+        sp.transform_in()
+        self.comm_time.recv_chain(self, lvl, row=sp.work[0])
+        sp.recur()
+        self.comm_time.send_chain(self, lvl, row=sp.work[lv.npts - 1])
+        sp.transform_out(first_row=0 if self.comm_time_rank > 0 else 1)
+        self.launches += 3
 
     def nested_iteration(self) -> None:
         """Coarsest solve, then interpolate upwards with a V-cycle per level (mgrit.py:551-566)."""

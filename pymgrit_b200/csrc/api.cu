@@ -377,6 +377,16 @@ int mgb_fas_residual(const mgb_level *fine, const mgb_level *coarse, void *strea
     return tab->fas_residual(L, G, st);
 }
 
+int mgb_down_sweep(const mgb_level *fine, const mgb_level *coarse, void *stream) {
+    MGB_PROLOGUE(fine)
+    const SweepTable *tab2 = nullptr;
+    LevelDev G;
+    if (int rc = check_level(coarse, &tab2, &G)) return rc;
+    if (int rc = check_pair(fine, coarse)) return rc;
+    if (tab->down == nullptr) return fail(MGB_ENOSHAPE, "no fused down-sweep for this application%s");
+    return tab->down(L, G, st);
+}
+
 int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t flags, void *stream) {
     MGB_PROLOGUE(fine)
     const SweepTable *tab2 = nullptr;

@@ -291,6 +291,36 @@ struct RowPipe {
         }
     }
 
+    // Next input row left in its shared-memory slot: the caller reads its own elements (s[tid*E + j], elements beyond n
+    // are whatever the row padding holds) and then calls pop_release().
+    __device__ __forceinline__ const double *pop_ptr() {
+        mbar_wait(bar0 + 8u * cons_slot, cons_parity);
+        return in_slot(cons_slot);
+    }
+    template <class TeamT>
+    __device__ __forceinline__ void pop_release(TeamT &team) {
+        team.sync();
+        if (tid == 0) issue(cons_slot);
+        ++cons;
+        if (++cons_slot == nin) {
+            cons_slot = 0;
+            cons_parity ^= 1u;
+        }
+    }
+
+    // A team-private scratch row behind the output slot (kernels that ask for it size the shared memory accordingly).
+    __device__ __forceinline__ double *stash_slot() const {
+        return reinterpret_cast<double *>(smem + kHeaderBytes + (size_t)(nin + 1) * SH::SLOT_BYTES);
+    }
+
+    // The row that the last push() left in the output slot, stored once more (another destination).
+    __device__ __forceinline__ void push_again(double *dst) {
+        if (tid == 0) {
+            bulk_s2g(dst, smem_u32(out_slot()), row_bytes);
+            bulk_commit();
+        }
+    }
+
     // Registers -> output row in HBM.
     template <class TeamT>
     __device__ __forceinline__ void push(const double (&x)[E], double *dst, TeamT &team) {

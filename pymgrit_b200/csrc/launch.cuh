@@ -38,11 +38,7 @@ struct Launch {
     // flags & 1: store only the last point of every interval (the other F-points are dead in a down-sweep)
     static int f_relax(const LevelDev &L, int flags, cudaStream_t st) {
         if (L.ncpts < 1) return 0;
-        int nin = 2 + rows_extra(L);
-        if (flags & 1) {  // compute-bound variant: fewer staging slots -> more resident teams per SM
-            static const int knob = getenv("MGB_LAST_ONLY_NIN") ? atoi(getenv("MGB_LAST_ONLY_NIN")) : 0;
-            if (knob > 0) nin = knob + rows_extra(L);
-        }
+        const int nin = 2 + rows_extra(L);
         const int nw = L.ncpts * nsys(L);
         int grid;
         if (int rc = grid_for(k_chain<Phi>, nw, nin, &grid)) return rc;
@@ -80,6 +76,16 @@ struct Launch {
         return cuda_fail(cudaGetLastError(), "fas_residual");
     }
 
+    // C-relaxation + F-relaxation + FAS restriction in one pass (k_down); one more slot: the stash
+    static int down(const LevelDev &L, const LevelDev &G, cudaStream_t st) {
+        if (L.ncpts < 2) return 0;
+        const int nin = 1 + rows_extra(L), nw = (L.ncpts - 1) * nsys(L);
+        int grid;
+        if (int rc = grid_for(k_down<Phi>, nw, nin + 1, &grid)) return rc;
+        k_down<Phi><<<grid, Phi::T, smem_bytes(nin + 1), st>>>(L, G, nw, nin);
+        return cuda_fail(cudaGetLastError(), "down_sweep");
+    }
+
     static int correct(const LevelDev &L, const LevelDev &G, int frelax, int kfirst, cudaStream_t st) {
         if (L.ncpts < 1) return 0;
         const int nin = 3 + rows_extra(L), nw = L.ncpts * nsys(L);
@@ -111,7 +117,7 @@ struct Launch {
 
     static const SweepTable *table() {
         static const SweepTable t = {Phi::T,       Phi::E,   &f_relax, &forward_solve, &c_relax,
-                                     &fas_residual, &correct, &residual, &step};
+                                     &fas_residual, &correct, &residual, &step,         &down};
         return &t;
     }
 };

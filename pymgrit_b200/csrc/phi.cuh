@@ -102,17 +102,42 @@ struct Heat1D {
 
     // x <- Phi(x) for the step that produces point i.  (the separable right-hand side is added here;
     // a dense right-hand-side row is added by the caller before.)
-    using Item = NoItem;
+    // The first spatial factor of the right-hand side stays in registers for all the steps of a work item: read from
+    // the table per step (33 loads through an L1 that the staging slots leave little of) it cost a quarter of the
+    // FP64-bound chains.
+    struct Item {
+        double rx0[E];
+    };
     template <class Pipe, class TeamT>
-    __device__ static __forceinline__ void begin_item(Item &, const LevelDev &, int, Pipe &, TeamT &) {}
+    __device__ static __forceinline__ void begin_item(Item &it, const LevelDev &L, int, Pipe &, TeamT &team) {
+        if (L.nrhs > 0) {
+            const double *__restrict__ rx = L.rhs_x + team.tid;
+#pragma unroll
+            for (int j = 0; j < E; ++j) it.rx0[j] = __ldg(rx + j * T);
+        }
+    }
+    // the item's data when the next Phi belongs to another level (FAS restriction: fine step, then coarse step)
+    template <class TeamT>
+    __device__ static __forceinline__ void retarget_item(Item &it, const LevelDev &from, const LevelDev &to, TeamT &team) {
+        if (to.nrhs > 0 && to.rhs_x != from.rhs_x) {
+            const double *__restrict__ rx = to.rhs_x + team.tid;
+#pragma unroll
+            for (int j = 0; j < E; ++j) it.rx0[j] = __ldg(rx + j * T);
+        }
+    }
 
     template <class TeamT>
-    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &, const LevelDev &L, int i,
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &it, const LevelDev &L, int i,
                                                  TeamT &team) {
         const int tid = team.tid;
         const int nv = L.n - tid * E;
         // b = u + dt * rhs(x, t_i)                                           heat_1d.py:214
-        for (int k = 0; k < L.nrhs; ++k) {
+        if (L.nrhs > 0) {
+            const double ct = __ldg(L.rhs_t + (size_t)i * L.nrhs);
+#pragma unroll
+            for (int j = 0; j < E; ++j) x[j] = fma(ct, it.rx0[j], x[j]);
+        }
+        for (int k = 1; k < L.nrhs; ++k) {
             const double ct = __ldg(L.rhs_t + (size_t)i * L.nrhs + k);
             const double *__restrict__ rx = L.rhs_x + (size_t)k * E * T + tid;
 #pragma unroll
@@ -235,6 +260,8 @@ struct Advection1D {
     using Item = NoItem;
     template <class Pipe, class TeamT>
     __device__ static __forceinline__ void begin_item(Item &, const LevelDev &, int, Pipe &, TeamT &) {}
+    template <class TeamT>
+    __device__ static __forceinline__ void retarget_item(Item &, const LevelDev &, const LevelDev &, TeamT &) {}
 
     template <class TeamT>
     __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &, const LevelDev &L, int i,
@@ -328,6 +355,9 @@ struct Heat2D {
             if (k < L.nrhs) pipe.pop(it.rx[k], team);
         it.boundary = sys >= L.ip[0];
     }
+    // all levels share the symbol and the right-hand-side factors (checked by the C ABI)
+    template <class TeamT>
+    __device__ static __forceinline__ void retarget_item(Item &, const LevelDev &, const LevelDev &, TeamT &) {}
 
     template <class TeamT>
     __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &it, const LevelDev &L, int i,

@@ -1,0 +1,247 @@
+// spectral.cu -- the sequential coarsest-level solve of Heat1D without its sequential Phi chain.
+//
+// mgrit.py:459-486 computes u_i = g_i + Phi_i(u_{i-1}), i = 1..N-1, one Phi (a tridiagonal solve, heat_1d.py:198-217)
+// after the other: N-1 dependent solves on ONE spatial system, which no amount of batching can spread over the device
+// and which every time rank has to wait for (the op-5 chain of mgrit.py:467-484).  Phi_i = (I + dt_i L)^-1 (. + dt_i b_i)
+// with the Toeplitz matrix L = (a/dx^2) tridiag(-1, 2, -1), whose eigenvectors are the columns of the orthonormal,
+// symmetric sine matrix S and whose eigenvalues lam_k = (a/dx^2) 4 sin^2(pi (k+1) / (2 (n+1))) are known in closed
+// form.  With w_i = S g_i (one product for all rows), the recurrence decouples into n scalar ones,
+//     uh_i[k] = (uh_{i-1}[k] + sum_q ct_q(i) rxh_q[k]) / (1 + dt_i lam_k) + w_i[k],
+// that run in parallel over k, and u_i = S uh_i is again one product for all rows.  The same linear system is solved
+// exactly (a direct method, like the reference's SuperLU call); only the order of the rounding errors differs (~1e-15
+// relative, tests/test_gpu_parity.py holds it to the 1e-10 of BASELINE.json).
+//
+// The two products are plain FP64 GEMMs on the CUDA cores (no tensor cores: nothing on the path is low precision).
+#include "../../include/mgrit_b200.h"
+#include "phi.cuh"
+#include "table.h"
+
+namespace mgb {
+
+int heat2d_fail(const char *msg);  // api.cu: records the message, returns MGB_EINVAL
+
+// S[j][k] = sqrt(2/(n+1)) sin(pi (j+1)(k+1)/(n+1)), argument reduced exactly in integers before sinpi
+__global__ void k_sine_matrix(int n, double *__restrict__ s, int ld) {
+    const long total = (long)n * n;
+    const double scale = sqrt(2.0 / (n + 1));
+    const long period = 2L * (n + 1);
+    for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+        const long j = q / n, k = q - j * n;
+        long r = ((j + 1) * (k + 1)) % period;  // angle = pi r / (n+1), r in [0, 2(n+1))
+        double sign = 1.0;
+        if (r > n + 1) {  // sin(pi + x) = -sin(x)
+            r -= n + 1;
+            sign = -1.0;
+        }
+        if (2 * r > n + 1) r = n + 1 - r;  // sin(pi - x) = sin(x): argument in [0, pi/2]
+        s[j * ld + k] = sign * scale * sinpi((double)r / (double)(n + 1));
+    }
+}
+
+// C (M x N, ldc) = A (M x K, lda) * B (K x N, ldb), FP64, row-major.  Row 0 of A is read from a_row0 when that is not
+// null (the level's u[0] next to its g rows).  TM x 64 tile per CTA, 256 threads, (TM/16) x 4 outputs per thread, K in
+// slabs of 16 through shared memory, register-prefetched: the next slab's global loads are in flight while the current
+// one is multiplied.  TM is chosen by the host so that the grid covers the SMs (64 for tall A, 32/16 for a few rows).
+constexpr int GN = 64, GK = 16;
+
+template <int TM>
+__global__ void __launch_bounds__(256) k_rows_gemm(int M, int N, int K, const double *__restrict__ A, int lda,
+                                                   const double *__restrict__ a_row0, const double *__restrict__ B, int ldb,
+                                                   double *__restrict__ Cm, int ldc) {
+    constexpr int RM = TM / 16;                 // output rows per thread
+    constexpr int LA = (TM * GK + 255) / 256;   // A elements staged per thread and slab
+    __shared__ double As[GK][TM + 4];
+    __shared__ double Bs[GK][GN];
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * GN;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // columns tx + 16 j, rows ty + 16 i
+    double acc[RM][4];
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    double ra[LA], rb[4];
+    auto load = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < LA; ++q) {
+            const int e = threadIdx.x + 256 * q;
+            const int mm = e >> 4, kk = e & 15;  // consecutive threads walk along k (contiguous in A)
+            const int m = m0 + mm, k = k0 + kk;
+            const double *row = (m == 0 && a_row0 != nullptr) ? a_row0 : A + (long)m * lda;
+            ra[q] = (mm < TM && m < M && k < K) ? __ldg(row + k) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = threadIdx.x + 256 * q;
+            const int kk = e >> 6, nn = e & 63;
+            const int k = k0 + kk, n = n0 + nn;
+            rb[q] = (k < K && n < N) ? __ldg(B + (long)k * ldb + n) : 0.0;
+        }
+    };
+    load(0);
+    for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+        for (int q = 0; q < LA; ++q) {
+            const int e = threadIdx.x + 256 * q;
+            if ((e >> 4) < TM) As[e & 15][e >> 4] = ra[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = threadIdx.x + 256 * q;
+            Bs[e >> 6][e & 63] = rb[q];
+        }
+        __syncthreads();
+        if (k0 + GK < K) load(k0 + GK);
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            double a[RM], b[4];
+#pragma unroll
+            for (int i = 0; i < RM; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+        const int m = m0 + ty + 16 * i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx + 16 * j;
+            if (n < N) Cm[(long)m * ldc + n] = acc[i][j];
+        }
+    }
+}
+
+// In-place scalar recurrences over the rows of W (sine space), one thread per mode k:
+//   W[i][k] = (W[i-1][k] + sum_q rhs_t[i][q] rxh[q][k]) / (1 + (t[i] - t[i-1]) lam[k]) + W[i][k],   i = 1 .. npts-1.
+// Rows are consumed in batches of UN: the next batch's loads are issued (and nothing waits for them) before this batch's
+// reciprocals, right-hand-side sums and dependent chain (one add, one FMA per step) run.
+constexpr int kSpectralMaxTerms = 4;
+constexpr int UN = 8;
+
+template <int NRHS>
+struct RecurBatch {
+    double w[UN], tv[UN + 1], ct[UN][NRHS > 0 ? NRHS : 1];
+    // raw loads of rows i0 .. i0+UN-1 (all in range): issued back to back, nothing consumes them here
+    __device__ __forceinline__ void load(const double *__restrict__ W, int pitch, int k, const double *__restrict__ t,
+                                         const double *__restrict__ rhs_t, int i0) {
+#pragma unroll
+        for (int j = 0; j < UN; ++j) w[j] = W[(long)(i0 + j) * pitch + k];
+#pragma unroll
+        for (int j = 0; j <= UN; ++j) tv[j] = __ldg(t + i0 - 1 + j);
+#pragma unroll
+        for (int j = 0; j < UN; ++j)
+#pragma unroll
+            for (int q = 0; q < NRHS; ++q) ct[j][q] = __ldg(rhs_t + (long)(i0 + j) * NRHS + q);
+    }
+};
+
+template <int NRHS>
+__global__ void __launch_bounds__(128) k_spectral_recur(double *__restrict__ W, int pitch, int n, int npts,
+                                                        const double *__restrict__ t, const double *__restrict__ lam,
+                                                        const double *__restrict__ rhs_t, const double *__restrict__ rxh) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double lk = lam[k];
+    double rx[NRHS > 0 ? NRHS : 1];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) rx[q] = rxh[(long)q * pitch + k];
+    double u = W[k];
+    const int nfull = (npts - 1) / UN;  // batches of UN steps; the remainder is stepped one by one below
+    RecurBatch<NRHS> cur, nxt;
+    if (nfull > 0) cur.load(W, pitch, k, t, rhs_t, 1);
+    for (int b = 0; b < nfull; ++b) {
+        const int i0 = 1 + b * UN;
+        if (b + 1 < nfull) nxt.load(W, pitch, k, t, rhs_t, i0 + UN);
+        // off the dependent chain: reciprocal denominators and right-hand-side sums of this batch
+        double inv[UN], s[UN];
+#pragma unroll
+        for (int j = 0; j < UN; ++j) {
+            inv[j] = __drcp_rn(fma(__dsub_rn(cur.tv[j + 1], cur.tv[j]), lk, 1.0));
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NRHS; ++q) acc = fma(cur.ct[j][q], rx[q], acc);
+            s[j] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < UN; ++j) {
+            u = fma(__dadd_rn(u, s[j]), inv[j], cur.w[j]);
+            W[(long)(i0 + j) * pitch + k] = u;
+        }
+        cur = nxt;
+    }
+    for (int i = 1 + nfull * UN; i < npts; ++i) {
+        const double inv = __drcp_rn(fma(__dsub_rn(__ldg(t + i), __ldg(t + i - 1)), lk, 1.0));
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) acc = fma(__ldg(rhs_t + (long)i * NRHS + q), rx[q], acc);
+        u = fma(__dadd_rn(u, acc), inv, W[(long)i * pitch + k]);
+        W[(long)i * pitch + k] = u;
+    }
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" {
+
+int mgb_sine_matrix(int32_t n, double *s_dev, int32_t ld, void *stream) {
+    if (n < 1 || ld < n || s_dev == nullptr) return heat2d_fail("sine_matrix: bad argument");
+    const DeviceInfo *di = device_info();
+    if (di == nullptr) return MGB_ECUDA;
+    k_sine_matrix<<<4 * di->sms, 256, 0, (cudaStream_t)stream>>>(n, s_dev, ld);
+    return cuda_fail(cudaGetLastError(), "sine_matrix");
+}
+
+int mgb_rows_gemm(int32_t m, int32_t n, int32_t k, const double *a_dev, int32_t lda, const double *a_row0_dev,
+                  const double *b_dev, int32_t ldb, double *c_dev, int32_t ldc, void *stream) {
+    if (m < 0 || n < 1 || k < 1 || a_dev == nullptr || b_dev == nullptr || c_dev == nullptr || lda < k || ldb < n || ldc < n)
+        return heat2d_fail("rows_gemm: bad argument");
+    const DeviceInfo *di = device_info();
+    if (di == nullptr) return MGB_ECUDA;
+    if (m == 0) return MGB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = (n + GN - 1) / GN;
+    // the tallest tile whose grid still covers the SMs
+    if ((long)((m + 63) / 64) * nb >= di->sms || m > 2048)
+        k_rows_gemm<64><<<dim3(nb, (m + 63) / 64), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc);
+    else if ((long)((m + 31) / 32) * nb >= di->sms || m > 256)
+        k_rows_gemm<32><<<dim3(nb, (m + 31) / 32), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc);
+    else
+        k_rows_gemm<16><<<dim3(nb, (m + 15) / 16), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc);
+    return cuda_fail(cudaGetLastError(), "rows_gemm");
+}
+
+int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const double *rxhat_dev, double *work_dev,
+                              void *stream) {
+    if (lvl == nullptr || lvl->app != MGB_APP_HEAT1D || lam_dev == nullptr || work_dev == nullptr || lvl->t_dev == nullptr)
+        return heat2d_fail("heat1d_spectral_recur: needs a HEAT1D level with its time grid, eigenvalues and work rows");
+    if (lvl->rhs_dense_dev != nullptr || lvl->nrhs > kSpectralMaxTerms || (lvl->nrhs > 0 && (rxhat_dev == nullptr || lvl->rhs_t_dev == nullptr)))
+        return heat2d_fail("heat1d_spectral_recur: right-hand side must be separable with at most 4 terms");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    if (lvl->npts < 2) return MGB_OK;
+    const dim3 grid((lvl->n + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MGB_RECUR(Q)                                                                                                       \
+    case Q:                                                                                                                \
+        k_spectral_recur<Q><<<grid, 128, 0, st>>>(work_dev, lvl->pitch, lvl->n, lvl->npts, lvl->t_dev, lam_dev, lvl->rhs_t_dev, \
+                                                  rxhat_dev);                                                              \
+        break;
+    switch (lvl->nrhs) {
+        MGB_RECUR(0)
+        MGB_RECUR(1)
+        MGB_RECUR(2)
+        MGB_RECUR(3)
+        MGB_RECUR(4)
+    }
+#undef MGB_RECUR
+    return cuda_fail(cudaGetLastError(), "heat1d_spectral_recur");
+}
+
+}  // extern "C"

@@ -156,6 +156,8 @@ struct GenChain {
     }
 };
 
+// (Measured: compiling the last-only variant for 12 instead of 8 warps per SM does not help -- the FP64 pipe is the
+// limiter, and the smaller L1 and the spills cost what the extra warps gain; profiles/r01c_last_only_occupancy.txt.)
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_chain(const LevelDev L, const int nw, const int last_only, const int nin) {
     using SH = typename Phi::SH;
@@ -376,10 +378,171 @@ __global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const
             for (int q = 0; q < E; ++q) x[q] = (x[q] - y[q]) + y[q];
         }
         pipe.pop(y, team);                                           // v[j-1]
+        Phi::retarget_item(it, L, G, team);
         Phi::load_consts(c, G.sconst + (G.ndt > 1 ? (size_t)__ldg(G.dtidx + j) * G.cw : 0), team.tid);
         advance<Phi>(y, c, it, G, j, pipe, team, false);             // Phi_c(v[j-1])
 #pragma unroll
         for (int q = 0; q < E; ++q) x[q] = x[q] - y[q];
+        pipe.push(x, G.g + (size_t)j * G.pitch + ip.soff, team);
+    }
+    pipe.finish(team);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Down-sweep of a cycle in one pass (mgrit.py:277-281 + 497-547 for cf_iter's last round, weight 1): C-relaxation,
+// the F-relaxation that follows it and the FAS restriction.  Work item j = 1 .. ncpts-1, a = cpts[j-1], c = cpts[j]:
+//     yc   = (g[c] +) Phi_f(u[c-1])                  C-relaxation of c (from the F-point as it is before this sweep)
+//     u[c] = yc,  G.u[j] = yc                        stored; injection
+//     x    = a == 0 ? u[0] : (g[a] +) Phi_f(u[a-1])  the C-relaxed left end, recomputed (its owner is item j-1)
+//     w    = Phi_c(x)                                coarse step from v[j-1] = new u[a]
+//     x    = Phi_f(F-relaxation chain from x to c-1) the new last F-point, never stored: nothing reads it before the
+//                                                    F-relaxation after the correction rewrites the interval
+//     G.g[j] = ((x - yc) + yc) - w                   (level 0)    or  (((g[c] - yc) + x) + yc) - w   (level > 0)
+// Same arithmetic, operation by operation, as k_c_relax + k_chain + k_fas_residual (bit-identical results), but per
+// interval it reads 2 rows (1 distinct) and writes 3 instead of 5 + 4, and the level is swept once instead of 3 times.
+// C-point rows are only written and F-point rows only read here, so items do not depend on each other.
+// Requires every interval to hold at least one F-point (no adjacent C-points) and weight 1; the host checks.
+// yc waits in the output slot and w in the stash slot, so that only one row (plus Phi's item data) lives in registers.
+// ------------------------------------------------------------------------------------------------
+struct GenDown {
+    LevelDev L, G;
+    int w, nw, stride, stage, sub, j, a, c, i, pro;
+    size_t soff;
+    __device__ GenDown(const LevelDev &L_, const LevelDev &G_, int first, int nw_, int stride_)
+        : L(L_), G(G_), w(first), nw(nw_), stride(stride_), stage(-2), sub(0), j(0), a(0), c(0), i(0), pro(0), soff(0) {}
+    __device__ bool next(const double *&p) {
+        for (;;) {
+            if (w >= nw) return false;
+            switch (stage) {
+                case -2: {
+                    const ItemPos ip = item_pos(L, w, 1);
+                    j = ip.k;
+                    soff = ip.soff;
+                    a = __ldg(L.cpts + j - 1);
+                    c = __ldg(L.cpts + j);
+                    pro = 0;
+                    stage = -1;
+                    break;
+                }
+                case -1:
+                    if (pro < n_prologue(L)) {
+                        p = prologue_row(L, pro++, soff);
+                        return true;
+                    }
+                    stage = 0;
+                    break;
+                case 0:  // u[c-1] for the C-relaxation of c
+                    p = L.u + (size_t)(c - 1) * L.pitch + soff;
+                    stage = 1;
+                    sub = 0;
+                    return true;
+                case 1:  // its dense rhs row and g[c]
+                    if (StepRows::next(L, c, sub, p, soff)) return true;
+                    stage = 2;
+                    break;
+                case 2:  // left end: u[0], or u[a-1] and the rows of step a
+                    stage = 3;
+                    sub = (a == 0) ? 2 : 0;
+                    p = L.u + (size_t)(a == 0 ? 0 : a - 1) * L.pitch + soff;
+                    return true;
+                case 3:
+                    if (StepRows::next(L, a, sub, p, soff)) return true;
+                    stage = 4;
+                    sub = 0;
+                    break;
+                case 4: {  // dense rhs row of the coarse step j
+                    const bool got = StepRows::next(G, j, sub, p, soff, false);
+                    stage = 5;
+                    i = a + 1;
+                    sub = 0;
+                    if (got) return true;
+                    break;
+                }
+                case 5:  // F-relaxation chain a+1 .. c-1
+                    if (i >= c) {
+                        stage = 6;
+                        sub = 0;
+                        break;
+                    }
+                    if (StepRows::next(L, i, sub, p, soff)) return true;
+                    ++i;
+                    sub = 0;
+                    break;
+                case 6:  // fine step into c: dense rhs row only
+                    stage = 7;
+                    if (StepRows::next(L, c, sub, p, soff, false)) return true;
+                    break;
+                case 7:  // g[c] for the FAS right-hand side
+                    stage = 8;
+                    if (L.g) {
+                        p = L.g + (size_t)c * L.pitch + soff;
+                        return true;
+                    }
+                    break;
+                default:
+                    w += stride;
+                    stage = -2;
+            }
+        }
+    }
+};
+
+template <class Phi>
+__global__ void __launch_bounds__(Phi::T) k_down(const LevelDev L, const LevelDev G, const int nw, const int nin) {
+    using SH = typename Phi::SH;
+    constexpr int E = Phi::E;
+    Team<Phi::T> team(g_smem);
+    RowPipe<SH, GenDown> pipe(g_smem, nin, L.tile, L.n, GenDown(L, G, blockIdx.x, nw, gridDim.x));
+    pipe.start(team);
+    typename Phi::C cf, cc;  // fine and coarse step constants (reloaded per step on non-uniform grids)
+    Phi::load_consts(cf, L.sconst, team.tid);
+    Phi::load_consts(cc, G.sconst, team.tid);
+    double *const stash = pipe.stash_slot() + team.tid * E;
+    const double *const outs = pipe.out_slot() + team.tid * E;
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(L, w, 1);
+        const int j = ip.k;
+        const int a = __ldg(L.cpts + j - 1), cp = __ldg(L.cpts + j);
+        typename Phi::Item it;
+        Phi::begin_item(it, L, ip.sys, pipe, team);
+        double x[E];
+        // C-relaxation of c; the output slot keeps yc until the last push of this item
+        pipe.pop(x, team);
+        advance<Phi>(x, cf, it, L, cp, pipe, team);
+        pipe.push(x, L.u + (size_t)cp * L.pitch + ip.soff, team);
+        pipe.push_again(G.u + (size_t)j * G.pitch + ip.soff);
+        // the C-relaxed left end
+        pipe.pop(x, team);
+        if (a != 0) advance<Phi>(x, cf, it, L, a, pipe, team);
+        // w = Phi_c(x) into the stash, x back
+#pragma unroll
+        for (int q = 0; q < E; ++q) stash[q] = x[q];
+        Phi::retarget_item(it, L, G, team);
+        advance<Phi>(x, cc, it, G, j, pipe, team, false);
+        Phi::retarget_item(it, G, L, team);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const double t = stash[q];
+            stash[q] = x[q];
+            x[q] = t;
+        }
+        // F-relaxation chain and the fine step into c
+        for (int i = a + 1; i < cp; ++i) advance<Phi>(x, cf, it, L, i, pipe, team);
+        advance<Phi>(x, cf, it, L, cp, pipe, team, false);
+        // FAS right-hand side
+        if (L.g) {
+            const double *gg = pipe.pop_ptr() + team.tid * E;
+            const int nv = L.n - team.tid * E;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const double r = (((gg[q] - outs[q]) + x[q]) + outs[q]) - stash[q];
+                x[q] = (q < nv) ? r : 0.0;  // the slot holds the raw row: keep the padding at zero
+            }
+            pipe.pop_release(team);
+        } else {
+#pragma unroll
+            for (int q = 0; q < E; ++q) x[q] = ((x[q] - outs[q]) + outs[q]) - stash[q];
+        }
         pipe.push(x, G.g + (size_t)j * G.pitch + ip.soff, team);
     }
     pipe.finish(team);

@@ -23,6 +23,7 @@ struct SweepTable {
     int (*correct)(const LevelDev &, const LevelDev &, int, int, cudaStream_t);
     int (*residual)(const LevelDev &, double *, cudaStream_t);
     int (*step)(const LevelDev &, int, const double *, double *, cudaStream_t);
+    int (*down)(const LevelDev &, const LevelDev &, cudaStream_t);  // nullptr: not available for this application
 };
 
 }  // namespace mgb

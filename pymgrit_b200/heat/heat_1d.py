@@ -59,3 +59,70 @@ class Heat1D(DeviceApplication):
         elif split.kind == 'dense':
             tab['rhs_dense'] = split.dense(t) * dt_full[:, None]
         return tab
+
+    # ---- coarsest-level solve in sine space (csrc/spectral.cu) ---------------------------------------------------
+    SPECTRAL_MIN_POINTS = 24     # below this the sequential Phi chain (mgb_forward_solve) is as fast
+
+    def spectral_solver(self, level):
+        """A SpectralSolve for `level` (the coarsest DeviceLevel of a hierarchy), or None when the chain of Phi
+        applications is used: short levels, or a right-hand side that is not separable."""
+        if level.npts < self.SPECTRAL_MIN_POINTS or self._rhs_split.kind == 'dense':
+            return None
+        return SpectralSolve(self, level)
+
+
+class SpectralSolve:
+    """u_i = g_i + Phi_i(u_{i-1}) over a whole level (mgrit.py:459-486) as two sine transforms and n scalar recurrences
+    (include/mgrit_b200.h, "the coarsest-level solve in sine space")."""
+
+    def __init__(self, app, level):
+        torch = dl._torch()
+        dev = level.u.device
+        n, pitch = app.nx, level.pitch
+        self.n, self.pitch, self.level = n, pitch, level
+        self.h2d_bytes = 0
+        self.smat = torch.empty((n, n), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().mgb_sine_matrix(n, self.smat.data_ptr(), n, _lib.current_stream_ptr()), 'sine_matrix')
+        k = np.arange(1, n + 1).astype(np.longdouble)
+        pi = np.longdouble('3.14159265358979323846264338327950288')
+        fac = np.longdouble(app.a) / np.longdouble(app.dx) ** 2                       # heat_1d.py:185
+        lam = np.asarray(fac * 4 * np.sin(k * pi / (2 * (n + 1))) ** 2, dtype=np.float64)
+        self.lam = torch.as_tensor(lam).to(dev)
+        self.h2d_bytes += lam.nbytes
+        self.work = torch.zeros((level.npts, pitch), dtype=torch.float64, device=dev)
+        self.rxhat = None
+        split = app._rhs_split
+        if split.kind == 'separable':
+            basis = np.zeros((split.basis.shape[0], pitch))
+            basis[:, :n] = split.basis
+            rows = torch.as_tensor(basis).to(dev)
+            self.h2d_bytes += basis.nbytes
+            self.rxhat = torch.zeros_like(rows)
+            self._gemm(rows, self.rxhat, len(basis))
+
+    def _gemm(self, src, dst, rows, row0=None):
+        """dst[:rows, :n] = src[:rows, :n] S (row 0 of src taken from row0 if given)."""
+        _lib.check(_lib.lib().mgb_rows_gemm(rows, self.n, self.n, src.data_ptr(), self.pitch,
+                                            None if row0 is None else row0.data_ptr(), self.smat.data_ptr(), self.n,
+                                            dst.data_ptr(), self.pitch, _lib.current_stream_ptr()), 'rows_gemm')
+
+    def transform_in(self):
+        """work[0] = u[0] S, work[i] = g[i] S: one product."""
+        lv = self.level
+        if lv.g is not None:
+            self._gemm(lv.g, self.work, lv.npts, row0=lv.u)
+        else:
+            self._gemm(lv.u, self.work, 1)
+            self.work[1:].zero_()
+
+    def recur(self):
+        lv = self.level
+        _lib.check(_lib.lib().mgb_heat1d_spectral_recur(lv.ref, self.lam.data_ptr(),
+                                                        None if self.rxhat is None else self.rxhat.data_ptr(),
+                                                        self.work.data_ptr(), _lib.current_stream_ptr()), 'spectral_recur')
+
+    def transform_out(self, first_row=1):
+        """u[i] = work[i] S for i >= first_row (row 0 is the initial condition on time rank 0, the ghost otherwise)."""
+        lv = self.level
+        if lv.npts > first_row:
+            self._gemm(self.work[first_row:], lv.u[first_row:], lv.npts - first_row)

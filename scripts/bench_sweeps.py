@@ -13,7 +13,10 @@ import pymgrit_b200 as P
 
 nt = int(os.environ.get('NT', 2 ** 20 + 1))
 m = int(os.environ.get('COARSENING', 16))
-problem = P.simple_setup_problem(P.Heat1D(nt=nt, **bench.HEAT_KW), level=3, coarsening=m)
+kw = dict(bench.HEAT_KW)
+if os.environ.get('RHS', '1') == '0':
+    kw.pop('rhs')
+problem = P.simple_setup_problem(P.Heat1D(nt=nt, **kw), level=3, coarsening=m)
 solver = P.Mgrit(problem=problem, nested_iteration=False, logging_lvl=logging.WARNING, tol=1e-10)
 for k in solver.time_level0_sweeps(repeats=10):
     print('%-28s %8.3f ms  %7.0f GB/s' % (k['name'], k['ms'], k['gbs']))

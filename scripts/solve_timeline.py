@@ -57,7 +57,7 @@ def wrap(name):
     setattr(M.Mgrit, name, inner)
 
 
-for nm in ('f_relax', 'c_relax', 'fas_residual', 'error_correction', 'forward_solve', 'convergence_criterion'):
+for nm in ('f_relax', 'c_relax', 'fas_residual', 'down_sweep', 'error_correction', 'forward_solve', 'convergence_criterion'):
     wrap(nm)
 _orig_nested = M.Mgrit.nested_iteration
 solver.restart()

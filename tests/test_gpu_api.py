@@ -161,3 +161,53 @@ def test_solver_state_is_user_visible(P):
     v = solver.u[0][3]
     solver.u[0][5] = v
     assert np.max(np.abs(solver.u[0][5].get_values() - v.get_values())) <= 1e-13
+
+
+@pytest.mark.parametrize('variant', ['uniform', 'nonuniform_t', 'zero_rhs', 'rank2_rhs'])
+def test_spectral_coarse_solve_matches_phi_chain(P, variant):
+    """The coarsest-level solve in sine space (csrc/spectral.cu) against the chain of tridiagonal Phi applications it
+    replaces (mgrit.py:459-486), on the same u[0] and FAS right-hand side g: 1e-12 relative."""
+    import logging
+    import torch
+    kw = dict(x_start=0, x_end=1, nx=1025, a=1, init_cond=C.heat_init, rhs=C.heat_rhs)
+    if variant == 'zero_rhs':
+        kw.pop('rhs')
+    if variant == 'rank2_rhs':
+        kw['rhs'] = C.heat_rhs_rank2
+    t = np.linspace(0, 2, 513)
+    if variant == 'nonuniform_t':
+        t = 2 * np.linspace(0, 1, 513) ** 1.3
+    fine = P.Heat1D(t_interval=t, **kw)
+    coarse = P.Heat1D(t_interval=t[::2], **kw)
+    solver = P.Mgrit(problem=[fine, coarse], nested_iteration=False, logging_lvl=logging.WARNING)
+    assert 1 in solver._spectral
+    lv = solver._lv[1]
+    gen = torch.Generator(device='cuda').manual_seed(7)
+    lv.g[:, :lv.n] = torch.randn((lv.npts, lv.n), generator=gen, device='cuda', dtype=torch.float64) * 1e-2
+    solver.forward_solve(1)
+    spectral = lv.u.clone()
+    sp = solver._spectral.pop(1)
+    lv.u[1:].zero_()
+    solver.forward_solve(1)
+    chain = lv.u.clone()
+    solver._spectral[1] = sp
+    assert float(chain[1:].abs().max()) > 1e-3
+    assert float((spectral - chain).abs().max()) <= 1e-12 * float(chain.abs().max())
+    assert float(spectral[:, lv.n:].abs().max()) == 0.0           # the row padding stays zero
+
+
+@pytest.mark.parametrize('name', ['heat1d_cfg2_nt1025', 'heat1d_nonuniform_t', 'heat1d_rhs_nonsep', 'heat1d_small_f_cf2',
+                                  'heat1d_rhs_rank2', 'heat1d_trailing_f', 'heat1d_nx4097', 'advection_cfg4_small',
+                                  'heat2d_bc', 'heat2d_cfg3_small'])
+def test_fused_down_sweep_is_bit_identical(P, name, monkeypatch):
+    """mgb_down_sweep (C-relaxation + F-relaxation + FAS restriction in one launch) against the three separate
+    launches: same residual history and the same solution, bit for bit."""
+    from b200_util import run_b200, solution_rows
+    monkeypatch.setenv('MGB_FUSED_DOWN', '1')
+    fused, info_f = run_b200(name)
+    assert any(fused._fused_down)
+    monkeypatch.setenv('MGB_FUSED_DOWN', '0')
+    plain, info_p = run_b200(name)
+    assert not any(plain._fused_down)
+    assert np.array_equal(info_f['conv'], info_p['conv']), (info_f['conv'], info_p['conv'])
+    assert np.array_equal(solution_rows(fused)[0], solution_rows(plain)[0])
