@@ -40,4 +40,4 @@ pr = cProfile.Profile()
 pr.enable()
 run()
 pr.disable()
-pstats.Stats(pr).sort_stats('cumulative').print_stats(35)
+pstats.Stats(pr).sort_stats('cumulative').print_stats(60)

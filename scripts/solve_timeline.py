@@ -17,6 +17,15 @@ import bench
 import pymgrit_b200 as P
 from pymgrit_b200.core import mgrit as M
 
+import torch.distributed as dist
+world = int(os.environ.get('WORLD_SIZE', '1'))
+rank = int(os.environ.get('RANK', '0'))
+if world > 1:                       # python -m torch.distributed.run --nproc-per-node N scripts/solve_timeline.py
+    torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+    dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+show = int(os.environ.get('SHOW_RANK', world - 1))
+if rank != show:
+    sys.stdout = open(os.devnull, 'w')
 wl = sys.argv[1] if len(sys.argv) > 1 else 'cfg5'
 nt, co = bench.WORKLOADS[wl]
 if len(sys.argv) > 2:
@@ -57,7 +66,8 @@ def wrap(name):
     setattr(M.Mgrit, name, inner)
 
 
-for nm in ('f_relax', 'c_relax', 'fas_residual', 'down_sweep', 'error_correction', 'forward_solve', 'convergence_criterion'):
+for nm in ('f_relax', 'c_relax', 'fas_residual', 'down_sweep', 'error_correction', 'forward_solve', 'convergence_criterion',
+           '_exchange_ghost'):
     wrap(nm)
 _orig_nested = M.Mgrit.nested_iteration
 solver.restart()
@@ -73,4 +83,6 @@ for k, (tag, lvl, s, e) in enumerate(records):
 total = sum(v[1] for v in tot.values())
 for key, (cnt, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f'{key}  x{cnt:3d}  {ms:8.3f} ms  {100 * ms / total:5.1f}%')
-print(f'sum of sweeps {total:.2f} ms (events add their own gaps)')
+print(f'sum of sweeps {total:.2f} ms (events add their own gaps; _exchange_ghost is nested inside c_relax)')
+if world > 1:
+    dist.destroy_process_group()
