@@ -60,6 +60,21 @@ def peaks():
     return 6650.0, 'fallback'
 
 
+def ncu_traffic(sweep, intervals):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `sweep` from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py traffic), scaled to this run's number of coarse
+    intervals (traffic is proportional to it); None if the sweep was not captured."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        cap = json.load(f)
+    ent = cap['sweeps'].get(sweep)
+    if ent is None:
+        return None
+    return (ent['dram_read_bytes'] + ent['dram_write_bytes']) * intervals / cap['intervals']
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -255,9 +270,10 @@ def gpu_arm(args):
     # ---- per-kernel roofline on level 0 (CUDA events around single launches on the solved state) ----
     kernels = solver.time_level0_sweeps(repeats=5)
     hbm, which = peaks()
-    dom = max(kernels, key=lambda k: k['share_ms'])
+    dom = max([k for k in kernels if k['bound'] == 'hbm'], key=lambda k: k['share_ms'])
     roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
-                'frac': dom['gbs'] / hbm, 'traffic': None, 'peak_source': which}
+                'frac': dom['gbs'] / hbm, 'traffic': ncu_traffic(dom['name'], dom['intervals']), 'peak_source': which,
+                'algorithmic_bytes': dom['algorithmic_bytes'], 'ms': dom['ms']}
 
     if rank == 0:
         cpu = None

@@ -2,9 +2,13 @@
 C ABI (include/mgrit_b200.h).  PyTorch owns the buffers; nothing here computes."""
 import ctypes as C
 
+import weakref
+
 import numpy as np
 
 from pymgrit_b200 import _lib
+
+_SHARED_TABLES = {}        # (device, table key) -> weak reference to a device tensor several levels point to
 
 
 def _torch():
@@ -65,7 +69,20 @@ class DeviceLevel:
         sconst = up(tab.get('sconst'), np.float64)
         dtidx = up(tab.get('dtidx'), np.int32)
         # tables an application family shares between its levels are handed over as device tensors
-        rhs_x = tab['rhs_x_dev'] if tab.get('rhs_x_dev') is not None else up(tab.get('rhs_x'), np.float64)
+        if tab.get('rhs_x_dev') is not None:
+            rhs_x = tab['rhs_x_dev']
+        elif tab.get('rhs_x_key') is not None:
+            key = (dev.index,) + tuple(tab['rhs_x_key'])
+            hit = _SHARED_TABLES.get(key)
+            if hit is None or hit[0]() is None or hit[0]().shape != tab['rhs_x'].shape:
+                ten = up(tab['rhs_x'], np.float64)
+                _SHARED_TABLES[key] = (weakref.ref(ten),)
+                rhs_x = ten
+            else:
+                rhs_x = hit[0]()
+                self._keep.append(rhs_x)
+        else:
+            rhs_x = up(tab.get('rhs_x'), np.float64)
         rhs_t = up(tab.get('rhs_t'), np.float64)
         sig = tab.get('sig_dev')
         self._keep += [t_ for t_ in (rhs_x, sig) if t_ is not None]

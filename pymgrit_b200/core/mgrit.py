@@ -274,8 +274,12 @@ class Mgrit:
                 sum(sp.h2d_bytes for sp in self._spectral.values()))
 
     def time_level0_sweeps(self, repeats: int = 5):
-        """CUDA-event timing of each level-0 sweep alone (bench.py roofline): list of dicts with the algorithmic
-        bytes (rows each interval must read or write exactly once), ms and GB/s."""
+        """CUDA-event timing of each level-0 sweep alone (bench.py roofline).  Per sweep: the algorithmic bytes (every
+        row an interval must read or write, counted once), ms, GB/s, how often it runs per
+        iteration of this solver, and what bounds it: 'hbm', or 'fp64' for the chains that read one row and write one
+        per interval but apply m Phi in between (then `fp64_frac` = Phi applications x 251 FP64 warp instructions per
+        33 elements per Phi / the measured issue rate of the FP64 pipe, 1 warp instruction per 2.07 cycles and
+        scheduler)."""
         torch = _lib_torch()
         lv = self._lv[0]
         if self.lvl_max < 2 or lv.cpts is None:
@@ -283,16 +287,28 @@ class Mgrit:
         k0 = len(lv.cpts) - 1
         m = self.m[0]
         row = 8.0 * lv.n
+        fused = self._fused_down[0]
+        cf = self.cf_iter[0]
         sweeps = [
-            ('f_relax', lambda: self.f_relax(0), m, 0),                          # public sweep (stores every F-point)
-            ('f_relax(last point only)', lambda: self.f_relax(0, last_only=True), 2, 1),     # down-sweep variant
-            ('c_relax', lambda: self.c_relax(0), 2 + (1 if self.weight_c != 1.0 else 0), 1),
-            ('fas_residual', lambda: self.fas_residual(0), 5, 1),
-            ('error_correction+f_relax', lambda: self.error_correction(0, f_relax=True), m + 2, 1),
-            ('residual_norms', lambda: self.compute_residual(), 2, 1),
+            # name, launch, rows per interval, Phi per interval, launches per iteration, bound
+            ('f_relax', lambda: self.f_relax(0), m, m - 1, 0, 'hbm'),               # public sweep: stores every F-point
+            ('f_relax(last point only)', lambda: self.f_relax(0, last_only=True), 2, m - 1,
+             0 if fused and cf == 1 else cf - (1 if fused else 0), 'fp64'),
+            ('c_relax', lambda: self.c_relax(0), 2 + (1 if self.weight_c != 1.0 else 0), 1,
+             cf - (1 if fused else 0), 'hbm'),
+            ('fas_residual', lambda: self.fas_residual(0), 4, 2, 0 if fused else 1, 'hbm'),
+            ('error_correction+f_relax', lambda: self.error_correction(0, f_relax=True), m + 2, m - 1, 1, 'hbm'),
+            ('residual_norms', lambda: self.compute_residual(), 2, 1, 1, 'hbm'),
         ]
+        if fused:
+            sweeps.insert(4, ('down_sweep(c_relax+f_relax+fas_residual)', lambda: self.down_sweep(0), 4, m + 3, 1, 'fp64'))
+        props = torch.cuda.get_device_properties(lv.u.device)
+        sms = props.multi_processor_count
+        clock_hz = float(getattr(props, 'clock_rate', 1965000)) * 1e3          # maximum SM clock (kHz -> Hz)
+        fp64_peak = sms * 4 * clock_hz / 2.07            # FP64 warp instructions per second (scripts/micro/fp64_latency.cu)
+        team_elems = self._lv[0].team_threads * self._lv[0].chunk
         out = []
-        for name, fn, rows, per_iter in sweeps:
+        for name, fn, rows, nphi, per_iter, bound in sweeps:
             fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -303,8 +319,12 @@ class Mgrit:
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / repeats
             nbytes = rows * k0 * row
-            out.append({'name': name, 'rows_per_interval': rows, 'intervals': k0, 'algorithmic_bytes': nbytes, 'ms': ms,
-                        'gbs': nbytes / (ms * 1e-3) / 1e9, 'share_ms': ms * per_iter})
+            # 251 FP64 warp instructions per Phi of a 32 x 33 team (ncu source view); scaled by the team size
+            fp64_instr = nphi * k0 * 251.0 * team_elems / (32 * 33)
+            out.append({'name': name, 'bound': bound, 'rows_per_interval': rows, 'phi_per_interval': nphi, 'intervals': k0,
+                        'algorithmic_bytes': nbytes, 'ms': ms, 'gbs': nbytes / (ms * 1e-3) / 1e9,
+                        'fp64_frac': fp64_instr / (ms * 1e-3) / fp64_peak, 'launches_per_iteration': per_iter,
+                        'share_ms': ms * per_iter})
         return out
 
     # ------------------------------------------------------------------------------------------

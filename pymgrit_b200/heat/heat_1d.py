@@ -15,6 +15,28 @@ from pymgrit_b200.core import device_level as dl
 from pymgrit_b200.core.rhs_tables import RhsSplit
 
 
+_SPLITS = {}          # (id(rhs), grid) -> RhsSplit, a handful of entries
+
+
+def _shared_split(rhs, x, t):
+    key = (id(rhs), len(x), float(x[0]), float(x[-1]))
+    split = _SPLITS.get(key)
+    if split is not None and split.sampler.rhs is rhs:
+        if split.kind == 'separable' and split.reproduces(t):
+            return split
+        if split.kind == 'zero':
+            tt = np.asarray(t, dtype=float)
+            pick = tt[np.unique(np.round(np.linspace(0, len(tt) - 1, min(len(tt), 5))).astype(int))]
+            if not np.any(split._rows(pick)):
+                return split
+    split = RhsSplit(rhs, x).analyse(t)
+    if len(_SPLITS) > 16:
+        _SPLITS.clear()
+    if split.kind != 'dense':
+        _SPLITS[key] = split
+    return split
+
+
 class VectorHeat1D(DeviceVector):
     """Vector of the nx-2 interior unknowns (heat_1d.py:14-128), stored in HBM."""
 
@@ -39,9 +61,10 @@ class Heat1D(DeviceApplication):
         self.init_cond = init_cond
         self.vector_t_start = VectorHeat1D(self.nx)
         self.vector_t_start.set_values(np.asarray(self.init_cond(self.x), dtype=float))
-        # device representation of rhs(x, t), analysed once here so that the deep copies made by
-        # simple_setup_problem share it
-        self._rhs_split = RhsSplit(self.rhs, self.x).analyse(self.t)
+        # device representation of rhs(x, t): analysed once per (callable, grid) so that the levels of a hierarchy --
+        # deep copies made by simple_setup_problem or separately constructed applications -- share one split, hence
+        # one table of spatial factors on the device
+        self._rhs_split = _shared_split(self.rhs, self.x, self.t)
 
     def level_tables(self, t, team_threads, chunk):
         fac = self.a / self.dx ** 2                                   # heat_1d.py:185
@@ -55,6 +78,7 @@ class Heat1D(DeviceApplication):
         if split.kind == 'separable':
             tab['nrhs'] = split.basis.shape[0]
             tab['rhs_x'] = dl.rhs_x_layout(split.basis, self.nx, team_threads, chunk)
+            tab['rhs_x_key'] = (id(split), team_threads, chunk)      # levels with the same split share the device table
             tab['rhs_t'] = split.coefficients(t) * dt_full[:, None]  # b * dt, heat_1d.py:214
         elif split.kind == 'dense':
             tab['rhs_dense'] = split.dense(t) * dt_full[:, None]

@@ -2,6 +2,7 @@
 
     python scripts/ncu_summary.py launches gpurun_out/r01_launches.csv      # per-kernel totals of a launch list
     python scripts/ncu_summary.py full gpurun_out/r01_sweeps.ncu-rep        # key metrics of a --set full capture
+    python scripts/ncu_summary.py traffic gpurun_out/r01_sweeps.ncu-rep name1,name2,... <intervals> profiles/ncu_traffic.json
 """
 import collections
 import csv
@@ -68,5 +69,27 @@ def full(path):
             pass
 
 
+def traffic(path, names, intervals, out_path):
+    """profiles/ncu_traffic.json for bench.py: DRAM bytes (read + write) per captured launch, keyed by the sweep names
+    given in launch order (scripts/profile_sweeps.py), with the number of coarse intervals the capture ran on."""
+    import json
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    h, units = rows[0], rows[1]
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    ir, iw = h.index('dram__bytes_read.sum'), h.index('dram__bytes_write.sum')
+    res = {'source': path, 'intervals': int(intervals), 'sweeps': {}}
+    for name, r in zip(names.split(','), rows[2:]):
+        rd = float(r[ir].replace(',', '')) * scale[units[ir]]
+        wr = float(r[iw].replace(',', '')) * scale[units[iw]]
+        res['sweeps'][name] = {'kernel': short(r[h.index('Kernel Name')]), 'dram_read_bytes': rd, 'dram_write_bytes': wr}
+    with open(out_path, 'w') as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == 'traffic':
+        traffic(*sys.argv[2:6])
+    else:
+        {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2])

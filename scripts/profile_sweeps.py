@@ -1,6 +1,6 @@
 """Launch every level-0 sweep of the headline workload twice (warm-up pass, then the pass ncu captures).
 
-    ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 6 -o gpurun_out/prof python scripts/profile_sweeps.py
+    ncu --set full --clock-control none --import-source on -k "regex:k_chain|k_c_relax|k_fas_residual|k_down|k_correct|k_residual" -s 7 -c 7 -o gpurun_out/prof python scripts/profile_sweeps.py
 """
 import logging
 import os
@@ -21,6 +21,7 @@ for _ in range(2):
     solver.f_relax(0, last_only=True)
     solver.c_relax(0)
     solver.fas_residual(0)
+    solver.down_sweep(0)
     solver.error_correction(0, f_relax=True)
     solver.compute_residual()
     torch.cuda.synchronize()
