@@ -131,6 +131,10 @@ int mgb_f_relax(const mgb_level *lvl, int32_t flags, void *stream);
 /* C-relaxation, mgrit.py:335-370: for every C-point c != 0,
  * u[c] = w * ((g[c] +) Phi(u[c-1])) + (1 - w) * u[c]. */
 int mgb_c_relax(const mgb_level *lvl, double weight, void *stream);
+/* The same for the last C-point of the level only.  A time rank calls it ahead of mgb_down_sweep so that its last row
+ * -- the next rank's ghost C-point, reference message kind 0 (mgrit.py:305-310) -- can travel before the fused pass
+ * (which recomputes the same value). */
+int mgb_c_relax_last(const mgb_level *lvl, double weight, void *stream);
 
 /* FAS restriction, mgrit.py:488-549 with GridTransferCopy (grid_transfer_copy.py:25-47): for every
  * C-point j, coarse.u[j] = fine.u[c_j]; for j >= 1
@@ -215,7 +219,14 @@ int mgb_rows_gemm(int32_t m, int32_t n, int32_t k, const double *a_dev, int32_t 
  * (a/dx^2) tridiag(-1, 2, -1); rxhat_dev [nrhs][pitch] = the spatial right-hand-side factors times S (rhs_t_dev of the
  * level supplies the time factors).  Needs a separable right-hand side (rhs_dense_dev == NULL), nrhs <= 4. */
 int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const double *rxhat_dev, double *work_dev,
-                              void *stream);
+                              double *ends_dev, int32_t zero_start, void *stream);
+/* Time-parallel form (replaces the rank-to-rank chain of mgrit.py:467-484).  Every rank runs mgb_heat1d_spectral_recur
+ * with ends_dev [2][pitch] != NULL -- rank 0 from its true first row, the others with zero_start = 1 -- which returns the
+ * last value and the product of the step factors per mode; the pairs are all-gathered ([nranks][2][pitch]) and rank r > 0
+ * calls mgb_heat1d_spectral_fixup: work[0] = true value at the slab start, work[i] += (product of the first i factors)
+ * times it.  One collective of 16 KB per rank instead of nranks - 1 dependent sends. */
+int mgb_heat1d_spectral_fixup(const mgb_level *lvl, const double *lam_dev, double *work_dev, const double *all_ends_dev,
+                              int32_t rank, void *stream);
 
 /* ---- Vector arithmetic (core/vector.py:38-110) ---------------------------------------------- */
 /* out = a*x + b*y on n doubles */

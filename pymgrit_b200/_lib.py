@@ -47,6 +47,7 @@ SYMBOLS = {
     'mgb_advection1d_step_consts': (C.c_int, [C.c_double, C.c_int32, C.c_int32, C.c_int32, c_double_p]),
     'mgb_f_relax': (C.c_int, [_LP, C.c_int32, C.c_void_p]),
     'mgb_c_relax': (C.c_int, [_LP, C.c_double, C.c_void_p]),
+    'mgb_c_relax_last': (C.c_int, [_LP, C.c_double, C.c_void_p]),
     'mgb_fas_residual': (C.c_int, [_LP, _LP, C.c_void_p]),
     'mgb_down_sweep': (C.c_int, [_LP, _LP, C.c_void_p]),
     'mgb_error_correction': (C.c_int, [_LP, _LP, C.c_int32, C.c_void_p]),
@@ -64,7 +65,8 @@ SYMBOLS = {
     'mgb_sine_matrix': (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_rows_gemm': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.c_void_p]),
-    'mgb_heat1d_spectral_recur': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mgb_heat1d_spectral_recur': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    'mgb_heat1d_spectral_fixup': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_vec_axpby': (C.c_int, [C.c_int32, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_vec_sumsq': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -92,6 +92,10 @@ class TorchDistComm:
         if self.rank + 1 < self.size and lv.npts > 0:
             self.dist.send(lv.u[lv.npts - 1] if row is None else row, self._global(self.rank + 1), group=self.group)
 
+    def all_gather_rows(self, out, mine):
+        """out[r] = rank r's `mine` (device tensors; the sine-space coarsest solve, heat/heat_1d.py)."""
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+
     def reduce_norm(self, partial, t_norm):
         op = self.dist.ReduceOp.MAX if t_norm == 3 else self.dist.ReduceOp.SUM
         self.dist.all_reduce(partial, op=op, group=self.group)

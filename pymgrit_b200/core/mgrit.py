@@ -177,16 +177,15 @@ class Mgrit:
             cp = part.sweep_cpts[lvl] if lvl < self.lvl_max - 1 else None
             self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0))
         # levels whose down-sweep runs as one fused launch (mgb_down_sweep): unweighted C-relaxation, at least one
-        # F-point in every interval, team kernels, one time rank (the ghost C-point would need its own F-point)
+        # F-point in every interval (on every time rank), team kernels
         import os
         self._fused_down = []
         for lvl in range(self.lvl_max - 1):
             cp = self._lv[lvl].cpts
-            ok = (weight_c == 1.0 and self.comm_time_size == 1 and cp is not None and len(cp) > 1 and
-                  int(np.min(np.diff(cp))) >= 2 and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D,
-                                                                         _lib.APP_HEAT2D)
+            ok = (weight_c == 1.0 and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D)
+                  and (cp is None or len(cp) < 2 or int(np.min(np.diff(cp))) >= 2)
                   and os.environ.get('MGB_FUSED_DOWN', '1') != '0')
-            self._fused_down.append(bool(ok))
+            self._fused_down.append(self._all_ranks(ok))
         self._fused_down.append(False)
         # the sequential solve on the coarsest level in sine space where the application offers it (Heat1D)
         self._spectral = {}
@@ -374,6 +373,12 @@ class Mgrit:
     def down_sweep(self, lvl: int) -> None:
         """c_relax + f_relax(last_only) + fas_residual of level lvl in one pass over the level (same values)."""
         fine, coarse = self._lv[lvl], self._lv[lvl + 1]
+        if self.comm_time_size > 1:
+            # the next rank's ghost is my last C-point after its C-relaxation: relax that one point first, send it, and
+            # let the fused pass recompute it
+            if self.comm_time_rank + 1 < self.comm_time_size and fine.npts > 1:
+                _lib.check(_lib.lib().mgb_c_relax_last(fine.ref, 1.0, self._stream()), 'c_relax_last')
+            self._exchange_ghost(lvl)
         if coarse.npts > 0 and fine.npts > 0:
             coarse.u[0].copy_(fine.u[0])
         _lib.check(_lib.lib().mgb_down_sweep(fine.ref, coarse.ref, self._stream()), 'down_sweep')
@@ -388,7 +393,8 @@ class Mgrit:
     def forward_solve(self, lvl: int) -> None:
         """Sequential time stepping on level lvl (mgrit.py:459-486).  Heat1D levels that are long enough are solved
         in sine space (csrc/spectral.cu): two transforms and n independent scalar recurrences instead of a chain of
-        tridiagonal solves; between time ranks the last row travels in sine space."""
+        tridiagonal solves; the time ranks exchange one all-gather of two rows each instead of the rank-to-rank
+        chain (mgrit.py:467-484)."""
         lv = self._lv[lvl]
         sp = self._spectral.get(lvl) if lv.npts > 0 else None
         if sp is None:
@@ -397,9 +403,11 @@ class Mgrit:
             self.comm_time.send_chain(self, lvl)
             return
         sp.transform_in()
-        self.comm_time.recv_chain(self, lvl, row=sp.work[0])
-        sp.recur()
-        self.comm_time.send_chain(self, lvl, row=sp.work[lv.npts - 1])
+        if self.comm_time_size > 1:
+            sp.recur_time_parallel(self.comm_time)
+            self.launches += 1 if self.comm_time_rank > 0 else 0
+        else:
+            sp.recur()
         sp.transform_out(first_row=0 if self.comm_time_rank > 0 else 1)
         self.launches += 3
 

@@ -365,7 +365,13 @@ int mgb_f_relax(const mgb_level *lvl, int32_t flags, void *stream) {
 int mgb_c_relax(const mgb_level *lvl, double weight, void *stream) {
     MGB_PROLOGUE(lvl)
     if (L.cpts == nullptr) return fail(MGB_EINVAL, "c_relax needs the C-point table%s");
-    return tab->c_relax(L, weight, st);
+    return tab->c_relax(L, weight, 0, st);
+}
+
+int mgb_c_relax_last(const mgb_level *lvl, double weight, void *stream) {
+    MGB_PROLOGUE(lvl)
+    if (L.cpts == nullptr) return fail(MGB_EINVAL, "c_relax needs the C-point table%s");
+    return tab->c_relax(L, weight, 1, st);
 }
 
 int mgb_fas_residual(const mgb_level *fine, const mgb_level *coarse, void *stream) {

@@ -58,12 +58,14 @@ struct Launch {
         return cuda_fail(cudaGetLastError(), "forward_solve");
     }
 
-    static int c_relax(const LevelDev &L, double w, cudaStream_t st) {
+    // last_only: relax the last C-point of the level only
+    static int c_relax(const LevelDev &L, double w, int last_only, cudaStream_t st) {
         if (L.ncpts < 2) return 0;
-        const int nin = 3, nw = (L.ncpts - 1) * nsys(L);
+        const int kbase = last_only ? L.ncpts - 1 : 1;
+        const int nin = 3, nw = (L.ncpts - kbase) * nsys(L);
         int grid;
         if (int rc = grid_for(k_c_relax<Phi>, nw, nin, &grid)) return rc;
-        k_c_relax<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, w, nw, nin);
+        k_c_relax<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, w, nw, nin, kbase);
         return cuda_fail(cudaGetLastError(), "c_relax");
     }
 

@@ -141,17 +141,23 @@ struct RecurBatch {
     }
 };
 
+// ends != nullptr (time rank > 0 of a time-parallel solve): the recurrence starts from 0 instead of W[0] and the kernel
+// also returns, in ends[0][k] and ends[1][k], its last value and the product of all its step factors 1 / (1 + dt_i lam_k):
+// with them every rank can work out the true value at its slab start without waiting for its predecessors' recurrences
+// (k_spectral_fixup).  On rank 0 ends[1] is not needed; ends[0] is the true last value.
 template <int NRHS>
 __global__ void __launch_bounds__(128) k_spectral_recur(double *__restrict__ W, int pitch, int n, int npts,
                                                         const double *__restrict__ t, const double *__restrict__ lam,
-                                                        const double *__restrict__ rhs_t, const double *__restrict__ rxh) {
+                                                        const double *__restrict__ rhs_t, const double *__restrict__ rxh,
+                                                        double *__restrict__ ends, int zero_start) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const double lk = lam[k];
     double rx[NRHS > 0 ? NRHS : 1];
 #pragma unroll
     for (int q = 0; q < NRHS; ++q) rx[q] = rxh[(long)q * pitch + k];
-    double u = W[k];
+    double u = zero_start ? 0.0 : W[k];
+    double prod = 1.0;
     const int nfull = (npts - 1) / UN;  // batches of UN steps; the remainder is stepped one by one below
     RecurBatch<NRHS> cur, nxt;
     if (nfull > 0) cur.load(W, pitch, k, t, rhs_t, 1);
@@ -173,6 +179,10 @@ __global__ void __launch_bounds__(128) k_spectral_recur(double *__restrict__ W, 
             u = fma(__dadd_rn(u, s[j]), inv[j], cur.w[j]);
             W[(long)(i0 + j) * pitch + k] = u;
         }
+        if (ends != nullptr) {
+#pragma unroll
+            for (int j = 0; j < UN; ++j) prod *= inv[j];
+        }
         cur = nxt;
     }
     for (int i = 1 + nfull * UN; i < npts; ++i) {
@@ -182,6 +192,43 @@ __global__ void __launch_bounds__(128) k_spectral_recur(double *__restrict__ W, 
         for (int q = 0; q < NRHS; ++q) acc = fma(__ldg(rhs_t + (long)i * NRHS + q), rx[q], acc);
         u = fma(__dadd_rn(u, acc), inv, W[(long)i * pitch + k]);
         W[(long)i * pitch + k] = u;
+        prod *= inv;
+    }
+    if (ends != nullptr) {
+        ends[k] = u;
+        ends[pitch + k] = prod;
+    }
+}
+
+// Time rank `rank` > 0: all[r] = the (last value, factor product) pairs of every rank r (all-gathered, [nranks][2][pitch]).
+// The true value at my slab start is s = end_{rank-1}, with end_0 = all[0][0] and end_r = all[r][1] end_{r-1} + all[r][0];
+// then W[0] = s and W[i] += (prod_{j <= i} 1 / (1 + dt_j lam)) s.
+__global__ void __launch_bounds__(128) k_spectral_fixup(double *__restrict__ W, int pitch, int n, int npts,
+                                                        const double *__restrict__ t, const double *__restrict__ lam,
+                                                        const double *__restrict__ all, int rank) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double lk = lam[k];
+    double s = all[k];
+    for (int r = 1; r < rank; ++r) s = fma(all[(long)(2 * r + 1) * pitch + k], s, all[(long)(2 * r) * pitch + k]);
+    W[k] = s;
+    double p = s;  // p = s * running product of the step factors
+    int i = 1;
+    for (; i + UN <= npts; i += UN) {
+        double w[UN], tv[UN + 1];
+#pragma unroll
+        for (int j = 0; j < UN; ++j) w[j] = W[(long)(i + j) * pitch + k];
+#pragma unroll
+        for (int j = 0; j <= UN; ++j) tv[j] = __ldg(t + i - 1 + j);
+#pragma unroll
+        for (int j = 0; j < UN; ++j) {
+            p *= __drcp_rn(fma(__dsub_rn(tv[j + 1], tv[j]), lk, 1.0));
+            W[(long)(i + j) * pitch + k] = w[j] + p;
+        }
+    }
+    for (; i < npts; ++i) {
+        p *= __drcp_rn(fma(__dsub_rn(__ldg(t + i), __ldg(t + i - 1)), lk, 1.0));
+        W[(long)i * pitch + k] += p;
     }
 }
 
@@ -219,19 +266,19 @@ int mgb_rows_gemm(int32_t m, int32_t n, int32_t k, const double *a_dev, int32_t 
 }
 
 int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const double *rxhat_dev, double *work_dev,
-                              void *stream) {
+                              double *ends_dev, int32_t zero_start, void *stream) {
     if (lvl == nullptr || lvl->app != MGB_APP_HEAT1D || lam_dev == nullptr || work_dev == nullptr || lvl->t_dev == nullptr)
         return heat2d_fail("heat1d_spectral_recur: needs a HEAT1D level with its time grid, eigenvalues and work rows");
     if (lvl->rhs_dense_dev != nullptr || lvl->nrhs > kSpectralMaxTerms || (lvl->nrhs > 0 && (rxhat_dev == nullptr || lvl->rhs_t_dev == nullptr)))
         return heat2d_fail("heat1d_spectral_recur: right-hand side must be separable with at most 4 terms");
     if (device_info() == nullptr) return MGB_ECUDA;
-    if (lvl->npts < 2) return MGB_OK;
+    if (lvl->npts < 2 && ends_dev == nullptr) return MGB_OK;
     const dim3 grid((lvl->n + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
 #define MGB_RECUR(Q)                                                                                                       \
     case Q:                                                                                                                \
         k_spectral_recur<Q><<<grid, 128, 0, st>>>(work_dev, lvl->pitch, lvl->n, lvl->npts, lvl->t_dev, lam_dev, lvl->rhs_t_dev, \
-                                                  rxhat_dev);                                                              \
+                                                  rxhat_dev, ends_dev, zero_start);                                        \
         break;
     switch (lvl->nrhs) {
         MGB_RECUR(0)
@@ -242,6 +289,17 @@ int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const
     }
 #undef MGB_RECUR
     return cuda_fail(cudaGetLastError(), "heat1d_spectral_recur");
+}
+
+int mgb_heat1d_spectral_fixup(const mgb_level *lvl, const double *lam_dev, double *work_dev, const double *all_ends_dev,
+                              int32_t rank, void *stream) {
+    if (lvl == nullptr || lvl->app != MGB_APP_HEAT1D || lam_dev == nullptr || work_dev == nullptr || lvl->t_dev == nullptr ||
+        all_ends_dev == nullptr || rank < 1)
+        return heat2d_fail("heat1d_spectral_fixup: bad argument");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    k_spectral_fixup<<<(lvl->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(work_dev, lvl->pitch, lvl->n, lvl->npts, lvl->t_dev,
+                                                                            lam_dev, all_ends_dev, rank);
+    return cuda_fail(cudaGetLastError(), "heat1d_spectral_fixup");
 }
 
 }  // extern "C"

@@ -202,14 +202,15 @@ struct GenCRelax {
     int w, nw, stride, stage, kk, pro;
     size_t soff;
     bool weighted;
-    __device__ GenCRelax(const LevelDev &L_, int first, int nw_, int stride_, bool weighted_)
-        : L(L_), w(first), nw(nw_), stride(stride_), stage(-2), kk(0), pro(0), soff(0), weighted(weighted_) {}
+    int kbase;
+    __device__ GenCRelax(const LevelDev &L_, int first, int nw_, int stride_, bool weighted_, int kbase_)
+        : L(L_), w(first), nw(nw_), stride(stride_), stage(-2), kk(0), pro(0), soff(0), weighted(weighted_), kbase(kbase_) {}
     __device__ bool next(const double *&p) {
         for (;;) {
             if (w >= nw) return false;
             if (stage == -2) {
-                const ItemPos ip = item_pos(L, w, 1);
-                if (!c_run_leader(L, ip.k)) {
+                const ItemPos ip = item_pos(L, w, kbase);
+                if (!c_run_leader(L, ip.k) && ip.k != kbase) {
                     w += stride;
                     continue;
                 }
@@ -247,18 +248,22 @@ struct GenCRelax {
     }
 };
 
+// kbase: first C-point relaxed (1 for the whole level; ncpts-1 to relax only the last C-point, which a time rank does
+// ahead of the fused down-sweep so that the next rank's ghost can travel first).  A run that starts before kbase is cut
+// there: the caller guarantees that point cpts[kbase]-1 is current.
 template <class Phi>
-__global__ void __launch_bounds__(Phi::T) k_c_relax(const LevelDev L, const double wgt, const int nw, const int nin) {
+__global__ void __launch_bounds__(Phi::T) k_c_relax(const LevelDev L, const double wgt, const int nw, const int nin,
+                                                    const int kbase) {
     using SH = typename Phi::SH;
     const bool weighted = (wgt != 1.0);
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenCRelax> pipe(g_smem, nin, L.tile, L.n, GenCRelax(L, blockIdx.x, nw, gridDim.x, weighted));
+    RowPipe<SH, GenCRelax> pipe(g_smem, nin, L.tile, L.n, GenCRelax(L, blockIdx.x, nw, gridDim.x, weighted, kbase));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
     for (int w = blockIdx.x; w < nw; w += gridDim.x) {
-        const ItemPos ip = item_pos(L, w, 1);
-        if (!c_run_leader(L, ip.k)) continue;
+        const ItemPos ip = item_pos(L, w, kbase);
+        if (!c_run_leader(L, ip.k) && ip.k != kbase) continue;
         typename Phi::Item it;
         Phi::begin_item(it, L, ip.sys, pipe, team);
         double x[Phi::E];

@@ -18,7 +18,7 @@ struct SweepTable {
     int chunk;
     int (*f_relax)(const LevelDev &, int flags, cudaStream_t);
     int (*forward_solve)(const LevelDev &, cudaStream_t);
-    int (*c_relax)(const LevelDev &, double, cudaStream_t);
+    int (*c_relax)(const LevelDev &, double, int last_only, cudaStream_t);
     int (*fas_residual)(const LevelDev &, const LevelDev &, cudaStream_t);
     int (*correct)(const LevelDev &, const LevelDev &, int, int, cudaStream_t);
     int (*residual)(const LevelDev &, double *, cudaStream_t);

@@ -223,7 +223,8 @@ struct TinyLaunch {
         kt_chain<P><<<1, 32, 0, st>>>(L, 1);
         return cuda_fail(cudaGetLastError(), "forward_solve");
     }
-    static int c_relax(const LevelDev &L, double w, cudaStream_t st) {
+    static int c_relax(const LevelDev &L, double w, int last_only, cudaStream_t st) {
+        if (last_only) return 2;  // MGB_ENOSHAPE: only used ahead of the fused down-sweep, which the ODE kernels do not have
         if (device_info() == nullptr) return MGB_ECUDA;
         kt_c_relax<P><<<grid(L.ncpts), 128, 0, st>>>(L, w);
         return cuda_fail(cudaGetLastError(), "c_relax");

@@ -139,11 +139,26 @@ class SpectralSolve:
             self._gemm(lv.u, self.work, 1)
             self.work[1:].zero_()
 
-    def recur(self):
+    def recur(self, ends=None, zero_start=False):
         lv = self.level
         _lib.check(_lib.lib().mgb_heat1d_spectral_recur(lv.ref, self.lam.data_ptr(),
                                                         None if self.rxhat is None else self.rxhat.data_ptr(),
-                                                        self.work.data_ptr(), _lib.current_stream_ptr()), 'spectral_recur')
+                                                        self.work.data_ptr(), None if ends is None else ends.data_ptr(),
+                                                        1 if zero_start else 0, _lib.current_stream_ptr()), 'spectral_recur')
+
+    def recur_time_parallel(self, comm):
+        """The recurrences over all time ranks without a rank-to-rank chain: local recurrences (from zero on ranks > 0),
+        one all-gather of (last value, factor product) per rank, local fix-up."""
+        torch = dl._torch()
+        if getattr(self, '_ends', None) is None:
+            self._ends = torch.zeros((2, self.pitch), dtype=torch.float64, device=self.work.device)
+            self._all_ends = torch.zeros((comm.size, 2, self.pitch), dtype=torch.float64, device=self.work.device)
+        self.recur(ends=self._ends, zero_start=comm.rank > 0)
+        comm.all_gather_rows(self._all_ends, self._ends)
+        if comm.rank > 0:
+            _lib.check(_lib.lib().mgb_heat1d_spectral_fixup(self.level.ref, self.lam.data_ptr(), self.work.data_ptr(),
+                                                            self._all_ends.data_ptr(), comm.rank,
+                                                            _lib.current_stream_ptr()), 'spectral_fixup')
 
     def transform_out(self, first_row=1):
         """u[i] = work[i] S for i >= first_row (row 0 is the initial condition on time rank 0, the ghost otherwise)."""
