@@ -453,6 +453,8 @@ class Mgrit:
 
     # ------------------------------------------------------------------------------------------
     def ouput_run_information(self) -> None:
+        if self._log_lvl > logging.INFO:        # nothing would be printed: skip the O(nt) max-dt scan
+            return
         msg = ['Run parameter overview',
                '  ' + '{0: <25}'.format(f'time interval') + ' : ' + '[' + str(self.problem[0].t[0]) + ', ' + str(
                    self.problem[0].t[-1]) + ']',

@@ -38,7 +38,11 @@ def c_point_masks(global_t):
             continue
         tc = global_t[l + 1]
         mask = np.zeros(len(t), dtype=bool)
-        if np.all(t[1:] > t[:-1]):                       # sorted grid: binary search instead of np.isin's sort
+        stride = (len(t) - 1) // (len(tc) - 1) if len(tc) > 1 and (len(t) - 1) % (len(tc) - 1) == 0 else 0
+        increasing = bool(np.all(t[1:] > t[:-1]))
+        if increasing and stride > 0 and np.array_equal(t[::stride], tc):
+            mask[::stride] = True                        # the usual case t_coarse = t[::m]: no search needed
+        elif increasing:                       # sorted grid: binary search instead of np.isin's sort
             idx = np.minimum(np.searchsorted(t, tc), len(t) - 1)
             mask[idx[t[idx] == tc]] = True
         else:
@@ -141,6 +145,64 @@ def reference_decomposition(global_t, size, rank):
     return out
 
 
+class _LazyArrays:
+    """A list of per-level index arrays that are built on first access (they are O(nt) and the sweeps never read them;
+    user code and tests do: mgrit.index_local[lvl])."""
+
+    def __init__(self):
+        self._make, self._val = [], []
+
+    def append(self, make):
+        self._make.append(make)
+        self._val.append(None)
+
+    def __len__(self):
+        return len(self._make)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if self._val[i] is None:
+            self._val[i] = self._make[i]()
+        return self._val[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _slab_tables(global_t, masks, lvl, rank, window):
+    """What Partition needs of _level_tables, with slices instead of index arrays: a rank's points of a level are a
+    contiguous range [a, b], so the ghost, the local time grid and the C-points come from views (at nt = 2^20 the index
+    arithmetic of _level_tables costs 10 ms of host time per construction)."""
+    t = global_t[lvl]
+    is_c = masks[lvl]
+    t0 = global_t[0]
+    first0, last0 = window
+    if first0 > last0:
+        a, b = 0, -1
+    elif lvl == 0:
+        a, b = first0, last0
+    else:
+        a = int(np.searchsorted(t, t0[first0], side='left'))
+        b = int(np.searchsorted(t, t0[last0], side='right')) - 1
+    n_own = max(b - a + 1, 0)
+    ghost = rank != 0 and n_own > 0
+    off = 1 if ghost else 0
+    own = lambda: np.arange(a, b + 1)
+    sub = is_c[a:b + 1]
+    local_c = np.flatnonzero(sub)                    # positions inside the owned range
+    t_local = t[a - off:b + 1] if n_own else t[0:0]
+
+    def f_list():
+        fpts = a + np.flatnonzero(~sub)
+        if 0 < n_own <= _SET_ORDER_LIMIT:            # the reference's set-iteration order, see _level_tables
+            fpts = np.array(list(set(own()) - set(a + local_c)), dtype=np.int64)
+        return (_f_groups_reversed(fpts) - a + off) if len(fpts) else np.array([], dtype=float)
+
+    pos = {'index_local': lambda: np.arange(off, n_own + off), 'index_local_c': local_c + off, 'index_local_f': f_list}
+    return own, t_local, a + local_c, pos
+
+
 class Partition:
     """Aligned slab partition used by the engine (see module docstring)."""
 
@@ -168,13 +230,13 @@ class Partition:
         last = int(bounds[rank])
         self.window = (first, last)
         self.int_start, self.int_stop = t0[first], t0[last]
-        self.t_local, self.cpts, self.index_local, self.index_local_c, self._f_lists = [], [], [], [], []
+        self.t_local, self.cpts, self.index_local, self.index_local_c, self._f_lists = [], [], _LazyArrays(), [], []
         self.masks = masks
-        self.sweep_cpts, self.send_to, self.get_from, self.owned = [], [], [], []
+        self.sweep_cpts, self.send_to, self.get_from, self.owned = [], [], [], _LazyArrays()
         for lvl in range(L):
-            own, with_ghost, cpts, pos, _ = _level_tables(global_t, masks, lvl, size, rank, (first, last), lazy_f=True)
+            own, t_local, cpts, pos = _slab_tables(global_t, masks, lvl, rank, (first, last))
             self.owned.append(own)
-            self.t_local.append(global_t[lvl][with_ghost])
+            self.t_local.append(t_local)
             self.cpts.append(cpts)
             self.index_local.append(pos['index_local'])
             self.index_local_c.append(pos['index_local_c'])

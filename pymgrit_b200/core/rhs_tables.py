@@ -147,8 +147,8 @@ class RhsSplit:
             return self.sampler.subset(self.sel, t)
         import concurrent.futures as cf
         import os
-        nthr = max(1, min(8, (os.cpu_count() or 1)))
-        chunks = np.array_split(t, 4 * nthr)
+        nthr = max(1, min(16, (os.cpu_count() or 1)))
+        chunks = np.array_split(t, 2 * nthr)
         with cf.ThreadPoolExecutor(max_workers=nthr) as ex:
             parts = list(ex.map(lambda c: np.asarray(self.sampler.subset(self.sel, c), dtype=float), chunks))
         if any(p.shape != (len(c), len(self.sel)) for p, c in zip(parts, chunks)):
