@@ -228,6 +228,21 @@ int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const
 int mgb_heat1d_spectral_fixup(const mgb_level *lvl, const double *lam_dev, double *work_dev, const double *all_ends_dev,
                               int32_t rank, void *stream);
 
+/* ---- Ghost rows between time ranks over peer memory (csrc/peer.cu) ----------------------------------------- */
+/* Replaces the reference's kind-0/4 messages (mgrit.py:305-310, 510-517, 693-713: pickled vector, isend/recv) by direct
+ * stores into the successor's mailbox over NVLink.  The caller owns a symmetric allocation per rank (same layout on
+ * every rank, peer-mapped): per level two row slots, two flags and one acknowledgement word (uint64, zero-initialised).
+ * The k-th exchange of a level uses seq = k >= 1 and slot / flag k & 1 on both sides.
+ *   sender:   mgb_peer_put_row(my last row, successor's slot, count, successor's flag, MY ack word, seq)
+ *             waits (on the device) until the successor has acknowledged seq - 2, stores the row, publishes seq;
+ *   receiver: mgb_peer_wait_row(my slot, my ghost row, count, my flag, PREDECESSOR's ack word, seq)
+ *             waits (on the device) for seq, copies the row, acknowledges.
+ * Both are ordinary asynchronous launches on `stream`; neither touches the host. */
+int mgb_peer_put_row(const double *src_dev, double *peer_slot_dev, int32_t count, void *peer_flag_dev, const void *my_ack_dev,
+                     uint64_t seq, void *stream);
+int mgb_peer_wait_row(const double *my_slot_dev, double *dst_dev, int32_t count, const void *my_flag_dev, void *peer_ack_dev,
+                      uint64_t seq, void *stream);
+
 /* ---- Vector arithmetic (core/vector.py:38-110) ---------------------------------------------- */
 /* out = a*x + b*y on n doubles */
 int mgb_vec_axpby(int32_t n, double a, const double *x_dev, double b, const double *y_dev, double *out_dev,

@@ -33,8 +33,47 @@ class SerialComm:
     def send_chain(self, solver, lvl, row=None):
         return None
 
+    def setup_peer_exchange(self, solver):
+        return None
+
     def reduce_norm(self, partial, t_norm):
         return partial
+
+
+class PeerMailbox:
+    """Symmetric memory every time rank's neighbours can address directly (torch.distributed._symmetric_memory: the
+    same allocation on every rank, peer-mapped over NVLink).  Layout in 8-byte words, identical on all ranks:
+        rows  [levels][2][pitch]   the ghost row of a level in flight (two slots, sequence parity)
+        flags [levels][2]          sequence number of the row in the slot, written by the predecessor
+        acks  [levels]             last sequence number my successor has consumed, written by the successor
+    include/mgrit_b200.h (mgb_peer_put_row / mgb_peer_wait_row) has the protocol."""
+
+    def __init__(self, dist, group, levels, pitch, device):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        self.levels, self.pitch = levels, pitch
+        words = levels * 2 * pitch + levels * 2 + levels
+        words += words & 1
+        self.buf = symm_mem.empty((words,), dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group=dist.group.WORLD if group is None else group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.rank = dist.get_rank(group)
+        self.seq = [0] * levels
+        torch.cuda.synchronize()
+        dist.barrier(group=group)            # every rank's mailbox is zeroed before anybody stores into one
+
+    def row(self, rank, lvl, slot):
+        return self.ptrs[rank] + 8 * ((lvl * 2 + slot) * self.pitch)
+
+    def flag(self, rank, lvl, slot):
+        return self.ptrs[rank] + 8 * (self.levels * 2 * self.pitch + lvl * 2 + slot)
+
+    def ack(self, rank, lvl):
+        return self.ptrs[rank] + 8 * (self.levels * 2 * self.pitch + self.levels * 2 + lvl)
+
+
+_MAILBOXES = {}
 
 
 class TorchDistComm:
@@ -75,11 +114,52 @@ class TorchDistComm:
             for req in self.dist.batch_isend_irecv(ops):
                 req.wait()
 
+    def setup_peer_exchange(self, solver):
+        """Use direct peer-memory stores for the ghost rows if every rank can: CUDA tensors over NCCL, symmetric memory
+        available, every rank holds points on every level.  Decided collectively; otherwise NCCL send/recv stays."""
+        import os
+        self.mailbox = None
+        ok = os.environ.get('MGB_PEER_EXCHANGE', '1') != '0' and self.dist.get_backend(self.group) == 'nccl'
+        ok = ok and all(lv.npts > 1 and lv.u.is_cuda for lv in solver._lv)
+        if ok:
+            try:
+                import torch.distributed._symmetric_memory  # noqa: F401
+            except Exception:
+                ok = False
+        if not all(self.allgather(bool(ok))):
+            return
+        levels, pitch = len(solver._lv), max(lv.pitch for lv in solver._lv)
+        key = (id(self.group), levels, pitch, solver._lv[0].u.device.index)
+        box = _MAILBOXES.get(key)
+        if box is None:
+            try:
+                box = PeerMailbox(self.dist, self.group, levels, pitch, solver._lv[0].u.device)
+            except Exception:
+                box = False
+            _MAILBOXES[key] = box
+        if all(self.allgather(bool(box))):
+            self.mailbox = box
+
     def exchange_ghost(self, solver, lvl):
         lv = solver._lv[lvl]
         if lv.npts == 0:
             return
-        self.shift_rows(lv.u[lv.npts - 1], lv.u[0])
+        box = getattr(self, 'mailbox', None)
+        if not box:
+            self.shift_rows(lv.u[lv.npts - 1], lv.u[0])
+            return
+        from pymgrit_b200 import _lib
+        box.seq[lvl] += 1
+        seq, slot = box.seq[lvl], box.seq[lvl] & 1
+        stream = _lib.current_stream_ptr()
+        if self.rank + 1 < self.size:
+            _lib.check(_lib.lib().mgb_peer_put_row(lv.u[lv.npts - 1].data_ptr(), box.row(self.rank + 1, lvl, slot), lv.pitch,
+                                                   box.flag(self.rank + 1, lvl, slot), box.ack(self.rank, lvl), seq, stream),
+                       'peer_put_row')
+        if self.rank > 0:
+            _lib.check(_lib.lib().mgb_peer_wait_row(box.row(self.rank, lvl, slot), lv.u[0].data_ptr(), lv.pitch,
+                                                    box.flag(self.rank, lvl, slot), box.ack(self.rank - 1, lvl), seq, stream),
+                       'peer_wait_row')
 
     def recv_chain(self, solver, lvl, row=None):
         """row: where the incoming row goes (default: the ghost row u[0] of the level)."""

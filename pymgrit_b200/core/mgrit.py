@@ -195,6 +195,7 @@ class Mgrit:
             sp = maker(last) if last.npts > 0 else None
             if sp is not None:
                 self._spectral[self.lvl_max - 1] = sp
+        self.comm_time.setup_peer_exchange(self)         # ghost rows over peer memory where the ranks can (core/comm.py)
         self.u = [_LevelVectors(lv, 'u') for lv in self._lv]
         self.g = [None] + [_LevelVectors(lv, 'g') for lv in self._lv[1:]]
         self.v = [None] * self.lvl_max       # never materialised: identical to the fine level's C-point rows
