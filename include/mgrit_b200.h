@@ -243,6 +243,17 @@ int mgb_peer_put_row(const double *src_dev, double *peer_slot_dev, int32_t count
 int mgb_peer_wait_row(const double *my_slot_dev, double *dst_dev, int32_t count, const void *my_flag_dev, void *peer_ack_dev,
                       uint64_t seq, void *stream);
 
+/* One-to-many form, used by the sine-space coarsest solve instead of an all-gather: rank r stores its (last value,
+ * factor product) rows into the gather buffer of every rank above it.  The pointer arrays are HOST arrays of npeers
+ * (<= 16) device addresses: for put, the destination slot and flag in each peer's buffer and the acknowledgement word
+ * that peer writes in mine; for wait, the flags the sources write in my buffer and the acknowledgement words in theirs.
+ * The wait acknowledges seq - 1: the rows of the previous round, which everything queued before it has finished reading
+ * (the rows of this round are read in place by the next kernel, mgb_heat1d_spectral_fixup). */
+int mgb_peer_put_rows(const double *src_dev, int32_t count, int32_t npeers, const uint64_t *peer_slot_ptrs,
+                      const uint64_t *peer_flag_ptrs, const uint64_t *my_ack_ptrs, uint64_t seq, void *stream);
+int mgb_peer_wait_flags(int32_t npeers, const uint64_t *my_flag_ptrs, const uint64_t *peer_ack_ptrs, uint64_t seq,
+                        void *stream);
+
 /* ---- Vector arithmetic (core/vector.py:38-110) ---------------------------------------------- */
 /* out = a*x + b*y on n doubles */
 int mgb_vec_axpby(int32_t n, double a, const double *x_dev, double b, const double *y_dev, double *out_dev,

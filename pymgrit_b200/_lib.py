@@ -69,6 +69,9 @@ SYMBOLS = {
     'mgb_heat1d_spectral_fixup': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_peer_put_row': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     'mgb_peer_wait_row': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    'mgb_peer_put_rows': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_uint64), C.c_uint64, C.c_void_p]),
+    'mgb_peer_wait_flags': (C.c_int, [C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64, C.c_void_p]),
     'mgb_vec_axpby': (C.c_int, [C.c_int32, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_vec_sumsq': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

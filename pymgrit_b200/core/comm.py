@@ -52,8 +52,16 @@ class PeerMailbox:
         import torch
         import torch.distributed._symmetric_memory as symm_mem
         self.levels, self.pitch = levels, pitch
+        self.size = dist.get_world_size(group)
         words = levels * 2 * pitch + levels * 2 + levels
         words += words & 1
+        # gather region (the sine-space coarsest solve): gath [2][size][2][pitch], gflag [2][size], gack [size]
+        self.gather = pitch <= 16384
+        self.gbase = words
+        if self.gather:
+            words += 2 * self.size * 2 * pitch + 2 * self.size + self.size
+            words += words & 1
+        self.gseq = 0
         self.buf = symm_mem.empty((words,), dtype=torch.int64, device=device)
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, group=dist.group.WORLD if group is None else group)
@@ -71,6 +79,35 @@ class PeerMailbox:
 
     def ack(self, rank, lvl):
         return self.ptrs[rank] + 8 * (self.levels * 2 * self.pitch + self.levels * 2 + lvl)
+
+    # gather region of `rank`: rows written by `src`, the flag `src` sets, the acknowledgement `consumer` writes
+    def gath(self, rank, slot, src):
+        return self.ptrs[rank] + 8 * (self.gbase + ((slot * self.size + src) * 2) * self.pitch)
+
+    def gflag(self, rank, slot, src):
+        return self.ptrs[rank] + 8 * (self.gbase + 2 * self.size * 2 * self.pitch + slot * self.size + src)
+
+    def gack(self, rank, consumer):
+        return self.ptrs[rank] + 8 * (self.gbase + 2 * self.size * 2 * self.pitch + 2 * self.size + consumer)
+
+    def share_rows(self, mine):
+        """Every rank above me gets my `mine` ([2][pitch] doubles) in its gather buffer; returns the address of my
+        gather buffer [size][2][pitch] once the rows of all ranks below me have arrived (device-side waits only)."""
+        import ctypes as C
+        from pymgrit_b200 import _lib
+        self.gseq += 1
+        seq, slot, me = self.gseq, self.gseq & 1, self.rank
+        arr = lambda vals: (C.c_uint64 * max(len(vals), 1))(*vals)
+        up = list(range(me + 1, self.size))
+        down = list(range(me))
+        stream = _lib.current_stream_ptr()
+        _lib.check(_lib.lib().mgb_peer_put_rows(mine.data_ptr(), 2 * self.pitch, len(up),
+                                                arr([self.gath(r, slot, me) for r in up]),
+                                                arr([self.gflag(r, slot, me) for r in up]),
+                                                arr([self.gack(me, r) for r in up]), seq, stream), 'peer_put_rows')
+        _lib.check(_lib.lib().mgb_peer_wait_flags(len(down), arr([self.gflag(me, slot, r) for r in down]),
+                                                  arr([self.gack(r, me) for r in down]), seq, stream), 'peer_wait_flags')
+        return self.gath(me, slot, 0)
 
 
 _MAILBOXES = {}

@@ -65,6 +65,51 @@ __global__ void __launch_bounds__(256) k_wait_row(const double *__restrict__ slo
     if (threadIdx.x == 0) st_release_sys(ack, seq);
 }
 
+// The same for one-to-many: CTA b stores src into peer b's slot and publishes seq in peer b's flag (after peer b has
+// acknowledged seq - 2); the matching wait is CTA b spinning on the flag source b wrote and acknowledging seq - 1, i.e.
+// the data of the PREVIOUS round, which every kernel queued before this one has finished reading.
+constexpr int kMaxPeers = 16;
+struct PeerList {
+    unsigned long long a[kMaxPeers];  // put: peer slot address   | wait: my flag address
+    unsigned long long b[kMaxPeers];  // put: peer flag address   | wait: peer ack address
+    unsigned long long c[kMaxPeers];  // put: my ack address      | wait: unused
+    int n;
+};
+
+__global__ void __launch_bounds__(256) k_put_rows(const double *__restrict__ src, int count, const PeerList pl,
+                                                  unsigned long long seq) {
+    const int p = blockIdx.x;
+    if (threadIdx.x == 0 && seq > 2)
+        while (ld_acquire_sys(reinterpret_cast<const unsigned long long *>(pl.c[p])) + 2 < seq) {
+        }
+    __syncthreads();
+    copy_row(src, reinterpret_cast<double *>(pl.a[p]), count);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned long long *>(pl.b[p]), seq);
+}
+
+__global__ void __launch_bounds__(32) k_wait_flags(const PeerList pl, unsigned long long seq) {
+    const int p = blockIdx.x;
+    if (threadIdx.x == 0) {
+        while (ld_acquire_sys(reinterpret_cast<const unsigned long long *>(pl.a[p])) < seq) {
+        }
+        st_release_sys(reinterpret_cast<unsigned long long *>(pl.b[p]), seq - 1);
+    }
+}
+
+static int fill(PeerList &pl, int n, const uint64_t *a, const uint64_t *b, const uint64_t *c) {
+    if (n < 0 || n > kMaxPeers || (n > 0 && (a == nullptr || b == nullptr))) return 1;
+    pl.n = n;
+    for (int k = 0; k < n; ++k) {
+        pl.a[k] = a[k];
+        pl.b[k] = b[k];
+        pl.c[k] = c ? c[k] : 0;
+        if (pl.a[k] == 0 || pl.b[k] == 0) return 1;
+    }
+    return 0;
+}
+
 }  // namespace mgb
 
 using namespace mgb;
@@ -91,6 +136,27 @@ int mgb_peer_wait_row(const double *my_slot_dev, double *dst_dev, int32_t count,
     k_wait_row<<<1, 256, 0, (cudaStream_t)stream>>>(my_slot_dev, dst_dev, count, (const unsigned long long *)my_flag_dev,
                                                     (unsigned long long *)peer_ack_dev, seq);
     return cuda_fail(cudaGetLastError(), "peer_wait_row");
+}
+
+int mgb_peer_put_rows(const double *src_dev, int32_t count, int32_t npeers, const uint64_t *peer_slot_ptrs,
+                      const uint64_t *peer_flag_ptrs, const uint64_t *my_ack_ptrs, uint64_t seq, void *stream) {
+    PeerList pl;
+    if (src_dev == nullptr || count < 1 || seq < 1 || my_ack_ptrs == nullptr || fill(pl, npeers, peer_slot_ptrs, peer_flag_ptrs, my_ack_ptrs))
+        return heat2d_fail("peer_put_rows: bad argument");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    if (npeers == 0) return MGB_OK;
+    k_put_rows<<<npeers, 256, 0, (cudaStream_t)stream>>>(src_dev, count, pl, seq);
+    return cuda_fail(cudaGetLastError(), "peer_put_rows");
+}
+
+int mgb_peer_wait_flags(int32_t npeers, const uint64_t *my_flag_ptrs, const uint64_t *peer_ack_ptrs, uint64_t seq,
+                        void *stream) {
+    PeerList pl;
+    if (seq < 1 || fill(pl, npeers, my_flag_ptrs, peer_ack_ptrs, nullptr)) return heat2d_fail("peer_wait_flags: bad argument");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    if (npeers == 0) return MGB_OK;
+    k_wait_flags<<<npeers, 32, 0, (cudaStream_t)stream>>>(pl, seq);
+    return cuda_fail(cudaGetLastError(), "peer_wait_flags");
 }
 
 }  // extern "C"

@@ -154,11 +154,15 @@ class SpectralSolve:
             self._ends = torch.zeros((2, self.pitch), dtype=torch.float64, device=self.work.device)
             self._all_ends = torch.zeros((comm.size, 2, self.pitch), dtype=torch.float64, device=self.work.device)
         self.recur(ends=self._ends, zero_start=comm.rank > 0)
-        comm.all_gather_rows(self._all_ends, self._ends)
+        box = getattr(comm, 'mailbox', None)
+        if box and box.gather and box.pitch == self.pitch:
+            all_ends = box.share_rows(self._ends)            # peer-memory stores instead of a collective
+        else:
+            comm.all_gather_rows(self._all_ends, self._ends)
+            all_ends = self._all_ends.data_ptr()
         if comm.rank > 0:
             _lib.check(_lib.lib().mgb_heat1d_spectral_fixup(self.level.ref, self.lam.data_ptr(), self.work.data_ptr(),
-                                                            self._all_ends.data_ptr(), comm.rank,
-                                                            _lib.current_stream_ptr()), 'spectral_fixup')
+                                                            all_ends, comm.rank, _lib.current_stream_ptr()), 'spectral_fixup')
 
     def transform_out(self, first_row=1):
         """u[i] = work[i] S for i >= first_row (row 0 is the initial condition on time rank 0, the ghost otherwise)."""
