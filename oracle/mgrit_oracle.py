@@ -126,12 +126,15 @@ class Heat1DOracle(OracleProblem):
 
 
 class Heat2DOracle(OracleProblem):
-    """heat/heat_2d.py:139-366, backward-Euler branch only (theta = 1), Dirichlet values as given."""
+    """heat/heat_2d.py:139-366: theta method (BE, CN, FE), Dirichlet values as given."""
 
     def __init__(self, x_start, x_end, y_start, y_end, nx, ny, a,
-                 rhs=lambda x, y, t: 0 * x * y, init_cond=lambda x, y: x * y * 0,
+                 rhs=lambda x, y, t: 0 * x * y, init_cond=lambda x, y: x * y * 0, method='BE',
                  bc_left=0, bc_right=0, bc_bottom=0, bc_top=0, **kw):
         super().__init__(**kw)
+        if method not in ('BE', 'FE', 'CN'):                     # heat_2d.py:192-200
+            raise Exception("Unknown method. Choose BE (Backward Euler), FE (Forward Euler) or CN (Crank-Nicolson")
+        self.theta = {'BE': 1, 'FE': 0, 'CN': 0.5}[method]
         self.x = np.linspace(x_start, x_end, nx)
         self.y = np.linspace(y_start, y_end, ny)
         self.x_2d = self.x[:, np.newaxis]
@@ -174,10 +177,22 @@ class Heat2DOracle(OracleProblem):
 
     def phi(self, u, t_start, t_stop):
         dt = t_stop - t_start
+        xi, yi = self.x_2d[1:-1], self.y_2d[:, 1:-1]
+        if self.theta == 0:                              # FE, heat_2d.py:341-358 (boundary values are ADDED, as there)
+            new = np.zeros((self.nx, self.ny))
+            self._apply_bc(new)
+            new += ((self.I - dt * self.L) * u.flatten()).reshape(self.nx, self.ny)
+            new[1:-1, 1:-1] += dt * self.rhs(x=xi, y=yi, t=t_start)
+            return new
         b = np.zeros((self.nx, self.ny))
-        b[1:-1, 1:-1] = u[1:-1, 1:-1] + dt * self.rhs(x=self.x_2d[1:-1], y=self.y_2d[:, 1:-1], t=t_stop)
-        self._apply_bc(b)                                # heat_2d.py:300-320
-        new = spsolve(dt * self.L + self.I, b.flatten())  # heat_2d.py:363 with theta = 1
+        if self.theta == 1:                              # BE, heat_2d.py:300-303
+            b[1:-1, 1:-1] = u[1:-1, 1:-1] + dt * self.rhs(x=xi, y=yi, t=t_stop)
+        else:                                            # CN, heat_2d.py:305-313
+            b += ((self.I - self.theta * dt * self.L) * u.flatten()).reshape(self.nx, self.ny)
+            b[1:-1, 1:-1] += self.theta * dt * self.rhs(x=xi, y=yi, t=t_stop) + \
+                (1 - self.theta) * dt * self.rhs(x=xi, y=yi, t=t_start)
+        self._apply_bc(b)                                # heat_2d.py:315-319
+        new = spsolve(dt * self.theta * self.L + self.I, b.flatten())  # heat_2d.py:363
         return new.reshape(self.nx, self.ny)
 
 

@@ -326,7 +326,10 @@ struct Advection1D {
 // coupling of the interior to the boundary data), ct_k(i) = dt_i T_k(t_i).  Rows are cut into tiles of T*E elements;
 // a tile is one "system" (no coupling between elements), tiles >= ip[0] hold boundary nodes and `sig` holds bc there.
 // Transforms happen only where values enter or leave the solver (csrc/heat2d.cu).
-//   step-constant row: [0] dt
+// The theta method of heat_2d.py:322-366 (FE theta = 0, CN 1/2, BE 1) only changes the two factors:
+//     Phi(x)_e = ((1 - (1-theta) dt_i sig_e) x_e + sum_k ct_k(i) rx_k,e) / (1 + theta dt_i sig_e),
+// with ct_k(i) = dt_i (theta T_k(t_i) + (1-theta) T_k(t_{i-1})) made on the host.
+//   step-constant row: [0] theta dt   [1] (1 - theta) dt
 // ---------------------------------------------------------------------------------------------
 constexpr int kHeat2DMaxTerms = 3;
 
@@ -337,7 +340,8 @@ struct Heat2D {
     static constexpr int QMAX = kHeat2DMaxTerms;
 
     struct C {
-        double dt;
+        double dt;   // theta * dt: the implicit part, (1 + dt sig) y = ...
+        double ex;   // (1 - theta) * dt: the explicit part, ... = (1 - ex sig) x + rhs   (0 for backward Euler)
     };
     struct Item {
         double sig[E];
@@ -345,7 +349,10 @@ struct Heat2D {
         bool boundary;
     };
 
-    __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int) { c.dt = __ldg(row); }
+    __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int) {
+        c.dt = __ldg(row);
+        c.ex = __ldg(row + 1);
+    }
 
     template <class Pipe, class TeamT>
     __device__ static __forceinline__ void begin_item(Item &it, const LevelDev &L, int sys, Pipe &pipe, TeamT &team) {
@@ -367,6 +374,10 @@ struct Heat2D {
             for (int j = 0; j < E; ++j) x[j] = it.sig[j];
             return;
         }
+        if (c.ex != 0.0) {  // Crank-Nicolson / forward Euler: (I - (1 - theta) dt L) u first (heat_2d.py:306, 352)
+#pragma unroll
+            for (int j = 0; j < E; ++j) x[j] = x[j] * fma(-c.ex, it.sig[j], 1.0);
+        }
 #pragma unroll
         for (int k = 0; k < QMAX; ++k) {
             if (k < L.nrhs) {
@@ -375,8 +386,10 @@ struct Heat2D {
                 for (int j = 0; j < E; ++j) x[j] = fma(ct, it.rx[k][j], x[j]);
             }
         }
+        if (c.dt != 0.0) {
 #pragma unroll
-        for (int j = 0; j < E; ++j) x[j] = __ddiv_rn(x[j], fma(c.dt, it.sig[j], 1.0));
+            for (int j = 0; j < E; ++j) x[j] = __ddiv_rn(x[j], fma(c.dt, it.sig[j], 1.0));
+        }
     }
 };
 

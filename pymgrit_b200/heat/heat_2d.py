@@ -133,11 +133,18 @@ class _Family:
         return out.view(rows.shape[0], self.nx, self.ny)
 
 
+def in_time_dense(vals, dts, theta):
+    """Rows dt_i (theta b(t_i) + (1 - theta) b(t_{i-1})) of a block of consecutive time points (first row: no predecessor
+    inside the block, only used when the block starts at point 0, whose step does not exist)."""
+    prev = np.concatenate([vals[:1], vals[:-1]])
+    return (theta * vals + (1 - theta) * prev) * dts[:, None]
+
+
 _FAMILIES = OrderedDict()
 
 
 class Heat2D(DeviceApplication):
-    """Same constructor as the reference (heat_2d.py:147-248); only method='BE' has device kernels."""
+    """Same constructor as the reference (heat_2d.py:147-248): theta method (BE, CN, FE) in sine space."""
     kind = _lib.APP_HEAT2D
 
     def __init__(self, x_start: float, x_end: float, y_start: float, y_end: float, nx: int, ny: int, a: float,
@@ -155,12 +162,15 @@ class Heat2D(DeviceApplication):
         self.dy = self.y[1] - self.y[0]
         self.a = a
         self.rhs = rhs
-        if method == 'BE':
+        if method == 'BE':                                    # heat_2d.py:192-200
             self.theta = 1
-        elif method in ('FE', 'CN'):
-            raise Exception("pymgrit_b200.Heat2D has device kernels for method 'BE' only (no CPU fallback)")
+        elif method == 'FE':
+            self.theta = 0
+        elif method == 'CN':
+            self.theta = 1 / 2
         else:
             raise Exception("Unknown method. Choose BE (Backward Euler), FE (Forward Euler) or CN (Crank-Nicolson")
+        self.method = method
 
         def as_fn(v, name):                                  # heat_2d.py:205-231
             if isinstance(v, (float, int)):
@@ -178,6 +188,10 @@ class Heat2D(DeviceApplication):
         init = np.array(np.broadcast_to(self.init_cond(self.x_2d, self.y_2d), (nx, ny)), dtype=float)   # heat_2d.py:243
         self._apply_bc(init)
         self.vector_t_start.set_values(init)
+        if self.theta == 0 and np.any(self.boundary_values()):
+            # the reference's forward-Euler branch ADDS the Dirichlet values to the boundary nodes in every step
+            # (heat_2d.py:346-353), so they grow with the step count: not reproduced on the device
+            raise Exception("pymgrit_b200.Heat2D: method 'FE' is available for homogeneous Dirichlet data only")
         self._family_key = (nx, ny, float(x_start), float(x_end), float(y_start), float(y_end), float(a), id(rhs),
                             self.boundary_values().tobytes())
         self.ndof = self.family().pitch
@@ -221,15 +235,22 @@ class Heat2D(DeviceApplication):
         st = fam.dev()
         t = np.asarray(t, dtype=float)
         dts, dtidx = dl.dt_classes(t)
+        th = self.theta
         sconst = np.zeros((len(dts), 8))
-        sconst[:, 0] = dts
+        sconst[:, 0] = th * dts                                # implicit part, heat_2d.py:363
+        sconst[:, 1] = (1 - th) * dts                          # explicit part, heat_2d.py:306, 352
         dt_full = np.zeros(len(t))
         dt_full[1:] = np.diff(t)
         tab = dict(ndt=len(dts), dtidx=dtidx, sconst=sconst, cw=8, nsys=fam.nsys, sig_dev=st['sig'],
                    ip=[fam.first_boundary, 0, 0, 0])
+
+        def in_time(vals):
+            """dt_i (theta b(t_i) + (1 - theta) b(t_{i-1})) from b at every point of t (heat_2d.py:302, 309-313, 356)."""
+            prev = np.concatenate([vals[:1], vals[:-1]])
+            return (th * vals + (1 - th) * prev) * dt_full.reshape((-1,) + (1,) * (vals.ndim - 1))
         cols = []
         if fam.split.kind == 'separable':
-            cols.append(fam.split.coefficients(t) * dt_full[:, None])      # dt * b, heat_2d.py:302
+            cols.append(in_time(fam.split.coefficients(t)))
         if fam.coupling is not None:
             cols.append(dt_full[:, None])
         if cols:
@@ -239,8 +260,9 @@ class Heat2D(DeviceApplication):
             dense = torch.empty((len(t), fam.pitch), dtype=torch.float64, device=st['sig'].device)
             for a in range(0, len(t), 16):                                  # transform in batches
                 nodes = np.zeros((len(t[a:a + 16]), self.nx, self.ny))
-                nodes[:, 1:-1, 1:-1] = (fam.split.dense(t[a:a + 16]) *
-                                        dt_full[a:a + 16, None]).reshape(-1, self.nx - 2, self.ny - 2)
+                lo = max(a - 1, 0)                                           # one point back for the explicit part
+                vals = in_time_dense(fam.split.dense(t[lo:a + 16]), dt_full[lo:a + 16], th)[a - lo:]
+                nodes[:, 1:-1, 1:-1] = vals.reshape(-1, self.nx - 2, self.ny - 2)
                 rows = fam.to_rows(torch.as_tensor(nodes).to(dense.device))
                 rows[:, fam.boff:] = 0.0
                 dense[a:a + 16] = rows

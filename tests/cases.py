@@ -169,6 +169,18 @@ CASES = {
                                                 rhs=heat2d_rhs_xy, init_cond=heat2d_init, bc_left=2.0, bc_right=1.0,
                                                 bc_bottom=0.5, bc_top=1.5),
                       t=(0, 1, 65), grids=_simple(2, 4), solver=dict(tol=1e-8)),
+    # heat_2d.py:341-366: Crank-Nicolson (theta = 1/2) with non-zero Dirichlet data, and forward Euler (theta = 0)
+    'heat2d_cn': dict(app='heat2d', app_kw=dict(x_start=0, x_end=1, y_start=0, y_end=1, nx=17, ny=13, a=1,
+                                                rhs=heat2d_rhs, init_cond=heat2d_init, method='CN', bc_left=1.0,
+                                                bc_top=0.5),
+                      t=(0, 1, 33), grids=_simple(2, 4), solver=dict(tol=1e-9)),
+    'heat2d_cn_3lvl': dict(app='heat2d', app_kw=dict(x_start=0, x_end=0.75, y_start=0, y_end=1.5, nx=15, ny=25, a=0.5,
+                                                     rhs=heat2d_rhs, init_cond=heat2d_init, method='CN',
+                                                     bc_bottom=lambda y: 0.25 * y),
+                           t=(0, 1, 65), grids=_simple(3, 4), solver=dict(tol=1e-9, cycle_type='F')),
+    'heat2d_fe': dict(app='heat2d', app_kw=dict(x_start=0, x_end=1, y_start=0, y_end=1, nx=9, ny=9, a=1,
+                                                rhs=heat2d_rhs, init_cond=heat2d_init, method='FE'),
+                      t=(0, 0.05, 33), grids=_simple(2, 2), solver=dict(tol=1e-9)),
 }
 
 

@@ -96,11 +96,12 @@ def test_no_cpu_fallback(lib):
         P.Mgrit(problem=[P.Dahlquist(t_start=0, t_stop=5, nt=11)]).solve()
 
 
-@pytest.mark.parametrize('name', ['heat2d_bc', 'heat2d_example', 'heat2d_cfg3_small'])
+@pytest.mark.parametrize('name', ['heat2d_bc', 'heat2d_example', 'heat2d_cfg3_small', 'heat2d_cn', 'heat2d_cn_3lvl',
+                                  'heat2d_fe'])
 def test_heat2d_sine_space_tables_reproduce_the_oracle(lib, name):
     """Host-side check of the Heat2D design (pymgrit_b200/heat/heat_2d.py, csrc/phi.cuh): the row layout, symbol row,
     right-hand-side factors and boundary coupling the host builds, pushed through a numpy restatement of the kernel's
-    arithmetic, give the oracle's backward-Euler step (sparse direct solve) to rounding."""
+    arithmetic, give the oracle's theta-method step (sparse direct solve; BE, CN and FE cases) to rounding."""
     import cases as CS
     import pymgrit_b200 as P
     from oracle import mgrit_oracle as O
@@ -137,14 +138,16 @@ def test_heat2d_sine_space_tables_reproduce_the_oracle(lib, name):
     rx = [to_rows(f) for f in fields]
     dt = np.zeros(len(t))
     dt[1:] = np.diff(t)
-    cols = ([fam.split.coefficients(t) * dt[:, None]] if fam.split.kind == 'separable' else []) + \
+    th = app.theta
+    coef = fam.split.coefficients(t) if fam.split.kind == 'separable' else None
+    cols = ([(th * coef + (1 - th) * np.concatenate([coef[:1], coef[:-1]])) * dt[:, None]] if coef is not None else []) + \
            ([dt[:, None]] if fam.coupling is not None else [])
     rt = np.concatenate(cols, axis=1)
     assert rt.shape[1] == len(rx) <= 3
     row, u = to_rows(orc.u0), orc.u0
     for i in range(1, 5):
-        x = row + sum(rt[i, k] * rx[k] for k in range(len(rx)))
-        x = x / (1 + dt[i] * fam.sig)
+        x = row * (1 - (1 - th) * dt[i] * fam.sig) + sum(rt[i, k] * rx[k] for k in range(len(rx)))
+        x = x / (1 + th * dt[i] * fam.sig)
         x[fam.boff:] = fam.sig[fam.boff:]              # boundary tiles: the Dirichlet values
         x[fam.nint:fam.boff] = 0.0
         row, u = x, orc.phi(u, t[i - 1], t[i])

@@ -43,7 +43,8 @@ def test_heat2d_constructor_errors(P):           # tests/heat/test_heat_2d.py:20
     with pytest.raises(Exception):
         P.Heat2D(bc_left='0', **kw)
     with pytest.raises(Exception):
-        P.Heat2D(method='CN', **kw)              # no device kernels for CN / FE: fails loudly, no fallback
+        P.Heat2D(method='FE', bc_top=1.0, **kw)  # FE with non-zero Dirichlet data is not reproduced: fails loudly
+    assert P.Heat2D(method='CN', **kw).theta == 0.5
 
 
 def test_advection_step_known_answer(P):         # tests/advection/test_advection_1d.py:33-45
@@ -211,3 +212,22 @@ def test_fused_down_sweep_is_bit_identical(P, name, monkeypatch):
     assert not any(plain._fused_down)
     assert np.array_equal(info_f['conv'], info_p['conv']), (info_f['conv'], info_p['conv'])
     assert np.array_equal(solution_rows(fused)[0], solution_rows(plain)[0])
+
+
+@pytest.mark.parametrize('method', ['CN', 'FE', 'BE'])
+def test_heat2d_theta_method_step_against_oracle(P, method):
+    """Heat2D.step for the three branches of heat_2d.py:322-366 against the oracle's sparse solve of the same system."""
+    from oracle import mgrit_oracle as O
+    kw = dict(x_start=0, x_end=1, y_start=0, y_end=2, nx=33, ny=21, a=0.7, rhs=C.heat2d_rhs, init_cond=C.heat2d_init,
+              method=method)
+    if method != 'FE':
+        kw.update(bc_left=1.0, bc_bottom=lambda y: 0.5 * y)
+    app = P.Heat2D(t_start=0, t_stop=1, nt=11, **kw)
+    orc = O.Heat2DOracle(t_start=0, t_stop=1, nt=11, **kw)
+    dt = 1e-4 if method == 'FE' else 0.1
+    got = app.step(u_start=app.vector_t_start, t_start=0.2, t_stop=0.2 + dt).get_values()
+    ref = orc.phi(orc.u0, 0.2, 0.2 + dt)
+    assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    if method == 'FE':
+        with pytest.raises(Exception):
+            P.Heat2D(t_start=0, t_stop=1, nt=11, bc_left=1.0, **kw)
