@@ -297,8 +297,10 @@ class MgritOracle:
             raise Exception("Cycle-type " + str(cycle_type) + " is not implemented. Choose 'V' or 'F'")
         if t_norm not in (1, 2, 3):
             raise Exception('Unknown norm.')
-        if conv_crit not in (0, 1):
-            raise Exception('oracle covers the global criteria 0 and 1 only')
+        if conv_crit not in (0, 1, 2, 3):
+            raise Exception('Unknown convergence criterion')
+        # one time rank: the local criteria 2 / 3 (mgrit.py:434-454) stop on the same per-point norms as 0 / 1
+        conv_crit = conv_crit % 2
         t0 = time.time()
         self.problem = list(problem)
         self.L = len(self.problem)

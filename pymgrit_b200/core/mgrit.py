@@ -7,7 +7,8 @@ reference loops over time points and calls Application.step once per point (mgri
 coarse interval of the level; the state of a level is one [points x dofs] array in HBM.
 
 Supported on the device path: applications derived from DeviceApplication, the identity GridTransferCopy, the global
-convergence criteria (conv_crit 0 and 1).  Anything else raises: there is no per-point Python fallback.
+convergence criteria (conv_crit 0 and 1; the local ones, 2 and 3, on one time rank).  Anything else raises: there is no
+per-point Python fallback.
 """
 import logging
 import sys
@@ -115,8 +116,9 @@ class Mgrit:
         for tr in transfer:
             if type(tr) is not GridTransferCopy:
                 raise Exception('only the identity GridTransferCopy is fused into the device sweeps')
-        if conv_crit in (2, 3):
-            raise Exception('local convergence criteria (conv_crit 2, 3) are not available on the device path')
+        # conv_crit 2 / 3 (local criteria, mgrit.py:434-454) let a time rank stop once its own points and all earlier
+        # ranks have converged.  On one rank that is the global test on the same per-point norms; the rank-by-rank
+        # shutdown protocol (message kind 6, sender_finished) is not built.
         if len({(p.kind, p.ndof) for p in problem}) != 1:
             raise Exception('all levels must use the same application kind and spatial size')
 
@@ -130,9 +132,15 @@ class Mgrit:
         self.comm_space_rank = -99
         self.comm_space_size = 1
 
+        if conv_crit in (2, 3) and self.comm_time_size > 1:
+            raise Exception('local convergence criteria (conv_crit 2, 3) are available on one time rank only; '
+                            'use conv_crit 0 or 1 with several ranks')
         self.comm_time.barrier()
         runtime_setup_start = time.time()
         self.log_info(f"Start setup")
+        if conv_crit in (2, 3):
+            self.log_info(f"A local criterion is used. The following output describes only the convergence of "
+                          f"process {self.comm_time_size - 1}.")
 
         self.launches = 0
         self.problem = problem
@@ -156,7 +164,8 @@ class Mgrit:
         self.t_norm = 1 if t_norm == 1 else None if t_norm == 2 else np.inf
         self._t_norm_id = t_norm
         self.conv_crit = conv_crit
-        self.global_conv_crit = True
+        self.global_conv_crit = conv_crit in (0, 1)
+        self._jump_crit = conv_crit in (1, 3)
         self.save_values_last_iter = None
         self.output_lvl = output_lvl
         self.output_fcn = output_fcn if output_fcn is not None and callable(output_fcn) else None
@@ -211,7 +220,7 @@ class Mgrit:
         if nested_iteration:
             self.nested_iteration()
 
-        if self.conv_crit == 1:
+        if self._jump_crit:
             self.save_values_last_iter = self._lv[0].u.clone()
 
         if self.iter_max == 0:
@@ -264,7 +273,7 @@ class Mgrit:
         self._init_levels()
         if self.nes_it:
             self.nested_iteration()
-        if self.conv_crit == 1:
+        if self._jump_crit:
             self.save_values_last_iter = self._lv[0].u.clone()
 
     @property
@@ -442,7 +451,7 @@ class Mgrit:
         lv0 = self._lv[0]
         ncp = 0 if lv0.cpts is None else len(lv0.cpts)
         if ncp > 0:
-            sq = self.compute_residual() if self.conv_crit == 0 else self.compute_jump()
+            sq = self.compute_jump() if self._jump_crit else self.compute_residual()
             _lib.check(_lib.lib().mgb_temporal_norm(sq.data_ptr(), ncp, self._t_norm_id, self._norm_out.data_ptr(),
                                                     self._stream()), 'temporal_norm')
         else:
@@ -474,6 +483,12 @@ class Mgrit:
                '  ' + '{0: <25}'.format(f'convergence criterion') + ' : ' + str(self.conv_crit)]
         self.log_info(message='\n'.join(msg))
 
+    def _conv_text(self, iteration: int) -> str:
+        """Residual column of the iteration log line (mgrit.py:611-624)."""
+        if self.global_conv_crit:
+            return '{0: <32}'.format(f" | conv: {self.conv[iteration + 1]}")
+        return '{0: <32}'.format(f" | conv on process {self.comm_time_size - 1}: {self.conv[iteration + 1]}")
+
     def solve(self) -> dict:
         """Iterate until the stopping criterion is met (mgrit.py:590-646)."""
         torch = _lib_torch()
@@ -490,12 +505,12 @@ class Mgrit:
 
             if iteration == 0:
                 self.log_info('{0: <7}'.format(f"iter {iteration + 1}") +
-                              '{0: <32}'.format(f" | conv: {self.conv[iteration + 1]}") +
+                              self._conv_text(iteration) +
                               '{0: <37}'.format(f" | conv factor: -") +
                               '{0: <35}'.format(f" | runtime: {time_it_stop - time_it_start} s"))
             else:
                 self.log_info('{0: <7}'.format(f"iter {iteration + 1}") +
-                              '{0: <32}'.format(f" | conv: {self.conv[iteration + 1]}") +
+                              self._conv_text(iteration) +
                               '{0: <37}'.format(f" | conv factor: {self.conv[iteration + 1] / self.conv[iteration]}") +
                               '{0: <35}'.format(f" | runtime: {time_it_stop - time_it_start} s"))
 

@@ -169,6 +169,11 @@ CASES = {
                                                 rhs=heat2d_rhs_xy, init_cond=heat2d_init, bc_left=2.0, bc_right=1.0,
                                                 bc_bottom=0.5, bc_top=1.5),
                       t=(0, 1, 65), grids=_simple(2, 4), solver=dict(tol=1e-8)),
+    # local convergence criteria (mgrit.py:434-454) on one time rank
+    'heat1d_small_local_res': dict(app='heat1d', app_kw=dict(nx=17, **HEAT), t=(0, 2, 65), grids=_simple(3, 2),
+                                   solver=dict(tol=1e-9, conv_crit=2)),
+    'heat1d_small_local_jump': dict(app='heat1d', app_kw=dict(nx=17, **HEAT), t=(0, 2, 65), grids=_simple(3, 2),
+                                    solver=dict(tol=1e-9, conv_crit=3, t_norm=3)),
     # heat_2d.py:341-366: Crank-Nicolson (theta = 1/2) with non-zero Dirichlet data, and forward Euler (theta = 0)
     'heat2d_cn': dict(app='heat2d', app_kw=dict(x_start=0, x_end=1, y_start=0, y_end=1, nx=17, ny=13, a=1,
                                                 rhs=heat2d_rhs, init_cond=heat2d_init, method='CN', bc_left=1.0,
