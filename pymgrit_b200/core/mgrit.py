@@ -140,7 +140,7 @@ class Mgrit:
         self.log_info(f"Start setup")
         if conv_crit in (2, 3):
             self.log_info(f"A local criterion is used. The following output describes only the convergence of "
-                          f"process {self.comm_time_size - 1}.")
+                          f"the time points of one process")
 
         self.launches = 0
         self.problem = problem
