@@ -125,6 +125,65 @@ class Heat1DOracle(OracleProblem):
         return out
 
 
+class Heat1D2PtsOracle(OracleProblem):
+    """heat/heat_1d_2pts_bdf1.py:16-117 (method='BDF1') and heat/heat_1d_2pts_bdf2.py:17-138 (method='BDF2'): the state
+    of a time point is the PAIR of values at t and t + dtau (heat/vector_heat_1d_2pts.py:12-140), held here as one
+    (2, n) array, so the vector norm (2-norm of both halves appended, vector_heat_1d_2pts.py:68-74) is the Frobenius
+    norm of that array."""
+
+    def __init__(self, x_start, x_end, nx, dtau, a, init_cond=lambda x: x * 0, rhs=lambda x, t: x * 0,
+                 method='BDF2', **kw):
+        super().__init__(**kw)
+        if method not in ('BDF1', 'BDF2'):
+            raise Exception('Unknown method')
+        x = np.linspace(x_start, x_end, nx)
+        self.x = x[1:-1]
+        self.n = nx - 2
+        self.dx = self.x[1] - self.x[0]
+        self.a = a
+        self.dtau = dtau
+        fac = a / self.dx ** 2
+        self.L = sp.diags([np.ones(self.n) * 2 * fac, np.ones(self.n - 1) * -fac, np.ones(self.n - 1) * -fac],
+                          [0, -1, 1], shape=(self.n, self.n), format='csr')
+        self.I = sp.identity(self.n, dtype='float', format='csr')
+        self.rhs = rhs
+        self.method = method
+        tmp1 = np.asarray(init_cond(self.x), dtype=float)
+        if method == 'BDF1':                             # one BDF1 step, heat_1d_2pts_bdf1.py:64-66
+            tmp2 = spsolve(dtau * self.L + self.I, tmp1 + self.rhs(self.x, self.t[0] + dtau) * dtau)
+        else:                                            # trapezoidal rule, heat_1d_2pts_bdf2.py:65-68
+            tmp2 = spsolve((dtau / 2) * self.L + self.I,
+                           (self.I - (dtau / 2) * self.L) * tmp1 +
+                           (dtau / 2) * (self.rhs(self.x, self.t[0]) + self.rhs(self.x, self.t[0] + dtau)))
+        self.u0 = np.stack([tmp1, tmp2])
+
+    def phi(self, u, t_start, t_stop):
+        first, second, dtau = u[0], u[1], self.dtau
+        if self.method == 'BDF1':                        # heat_1d_2pts_bdf1.py:108-113
+            tmp1 = spsolve((t_stop - t_start - dtau) * self.L + self.I,
+                           second + self.rhs(self.x, t_stop) * (t_stop - t_start - dtau))
+            tmp2 = spsolve(dtau * self.L + self.I, tmp1 + self.rhs(self.x, t_stop + dtau) * dtau)
+            return np.stack([tmp1, tmp2])
+        # BDF2 on the variably spaced grid, heat_1d_2pts_bdf2.py:110-133
+        tau_i = t_stop - t_start - dtau
+        tau_im1 = dtau
+        r_i = tau_i / tau_im1
+        coeffm2 = (r_i ** 2) / (tau_i * (1 + r_i))
+        coeffm1 = (1 + r_i) / tau_i
+        coeff = (1 + 2 * r_i) / (tau_i * (1 + r_i))
+        rhs = self.rhs(self.x, t_stop) - coeffm2 * first + coeffm1 * second
+        tmp1 = spsolve(self.L + coeff * self.I, rhs)
+        tau_im1 = tau_i
+        tau_i = dtau
+        r_i = tau_i / tau_im1
+        coeffm2 = (r_i ** 2) / (tau_i * (1 + r_i))
+        coeffm1 = (1 + r_i) / tau_i
+        coeff = (1 + 2 * r_i) / (tau_i * (1 + r_i))
+        rhs = self.rhs(self.x, t_stop + dtau) - coeffm2 * second + coeffm1 * tmp1
+        tmp2 = spsolve(self.L + coeff * self.I, rhs)
+        return np.stack([tmp1, tmp2])
+
+
 class Heat2DOracle(OracleProblem):
     """heat/heat_2d.py:139-366: theta method (BE, CN, FE), Dirichlet values as given."""
 

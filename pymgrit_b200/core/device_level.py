@@ -18,6 +18,21 @@ def _torch():
     return torch
 
 
+class _PinnedArray(np.ndarray):
+    """ndarray view of a page-locked torch tensor (kept alive by the view)."""
+    _owner = None
+
+
+def pinned_array(shape):
+    """Uninitialised float64 host array in page-locked memory (torch's caching host allocator: no cudaHostAlloc after
+    the first use of a size), so that DeviceLevel uploads it with one asynchronous copy and no staging pass."""
+    torch = _torch()
+    ten = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
+    arr = ten.numpy().view(_PinnedArray)
+    arr._owner = ten
+    return arr
+
+
 def team_shape(kind, n):
     t, e = C.c_int32(0), C.c_int32(0)
     _lib.check(_lib.lib().mgb_team_shape(kind, n, C.byref(t), C.byref(e)), 'team_shape')
@@ -55,6 +70,13 @@ class DeviceLevel:
         def up(a, dtype):
             if a is None:
                 return None
+            owner = getattr(a, '_owner', None)
+            if owner is not None and a.dtype == dtype:        # page-locked already: asynchronous copy, no staging
+                ten = owner.to(dev, non_blocking=True)
+                self._keep.append(owner)                       # alive until the copy has run
+                self.h2d_bytes += a.nbytes
+                self._keep.append(ten)
+                return ten
             host = np.ascontiguousarray(a, dtype=dtype)
             ten = torch.as_tensor(host).to(dev)
             self.h2d_bytes += host.nbytes

@@ -16,6 +16,18 @@ import numpy as np
 
 MAX_TERMS = 4
 _SAMPLES = 12
+_POOL = None
+
+
+def _pool():
+    """Worker threads for the table evaluation on long time grids, started once per process."""
+    global _POOL
+    if _POOL is None:
+        import concurrent.futures as cf
+        import os
+        nthr = max(1, min(16, (os.cpu_count() or 1)))
+        _POOL = (cf.ThreadPoolExecutor(max_workers=nthr, thread_name_prefix='mgb-rhs'), nthr)
+    return _POOL
 
 
 def _pivoted_rows(R, rtol, max_rows):
@@ -124,36 +136,49 @@ class RhsSplit:
         self.kind = 'separable' if err <= 1e-13 * max(scale, np.max(np.abs(check)) if check.size else 0.0) else 'dense'
         return self
 
-    def coefficients(self, t):
-        """T_k(t_i) for every t_i: shape (len(t), q)."""
+    def coefficients(self, t, scale=None, out=None):
+        """T_k(t_i) for every t_i (times scale[i] if given): shape (len(t), q), written to `out` if given (the caller
+        may hand in page-locked memory so that the upload needs no staging copy)."""
         t = np.asarray(t, dtype=float)
-        vals = None
-        try:                                   # one broadcast call when the callable allows it
-            cand = self._subset(t)
-            if cand.shape == (len(t), len(self.sel)):
-                probe = np.unique(np.array([0, len(t) // 2, len(t) - 1]))
-                ok = all(np.array_equal(cand[i], self.sampler.full(float(t[i]))[self.sel]) for i in probe)
-                vals = cand if ok else None
+        inv = np.linalg.inv(self.basis[:, self.sel])             # q x q system, q <= MAX_TERMS
+        if out is None:
+            out = np.empty((len(t), len(self.sel)))
+        try:                                   # one broadcast call per chunk when the callable allows it
+            self._broadcast_coefficients(t, inv, scale, out)
         except Exception:
-            vals = None
-        if vals is None:
             vals = np.stack([self.sampler.full(float(tt))[self.sel] for tt in t])
-        return vals @ np.linalg.inv(self.basis[:, self.sel])      # q x q system, q <= MAX_TERMS
+            np.matmul(vals, inv, out=out)
+            if scale is not None:
+                out *= np.asarray(scale, dtype=float)[:, None]
+        return out
 
-    def _subset(self, t):
-        """sampler.subset over all of t; long grids are cut into chunks evaluated on a few threads (NumPy ufuncs
-        release the GIL), which matters at nt = 2^20 where this is the largest host cost of the setup."""
-        if len(t) < (1 << 16):
-            return self.sampler.subset(self.sel, t)
-        import concurrent.futures as cf
-        import os
-        nthr = max(1, min(16, (os.cpu_count() or 1)))
-        chunks = np.array_split(t, 2 * nthr)
-        with cf.ThreadPoolExecutor(max_workers=nthr) as ex:
-            parts = list(ex.map(lambda c: np.asarray(self.sampler.subset(self.sel, c), dtype=float), chunks))
-        if any(p.shape != (len(c), len(self.sel)) for p, c in zip(parts, chunks)):
-            raise ValueError('right-hand side does not broadcast')
-        return np.concatenate(parts)
+    def _broadcast_coefficients(self, t, inv, scale, out):
+        """sampler.subset over all of t -> coefficients, or None if the callable does not broadcast over (t, x).
+        Long grids are cut into chunks worked on by a persistent pool of threads (NumPy ufuncs release the GIL); each
+        chunk is evaluated, solved for the coefficients and scaled in place, which matters at nt = 2^20 where this is
+        the largest host cost of the setup."""
+        nt, q = len(t), len(self.sel)
+        probe = np.unique(np.array([0, nt // 2, nt - 1]))
+        want = np.stack([self.sampler.full(float(t[i]))[self.sel] for i in probe])
+
+        def work(a, b):
+            vals = np.asarray(self.sampler.subset(self.sel, t[a:b]), dtype=float)
+            if vals.shape != (b - a, q):
+                vals = np.broadcast_to(vals, (b - a, q))          # e.g. a right-hand side that does not depend on t
+            for k, i in enumerate(probe):                         # the broadcast call must equal the plain one
+                if a <= i < b and not np.array_equal(vals[i - a], want[k]):
+                    raise ValueError('right-hand side does not broadcast')
+            np.matmul(vals, inv, out=out[a:b])
+            if scale is not None:
+                out[a:b] *= scale[a:b, None]
+
+        if nt < (1 << 15):
+            work(0, nt)
+            return out
+        pool, nthr = _pool()
+        edges = np.linspace(0, nt, 2 * nthr + 1).astype(int)
+        list(pool.map(lambda ab: work(*ab), zip(edges[:-1], edges[1:])))
+        return out
 
     def dense(self, t):
         return self._rows(np.asarray(t, dtype=float))

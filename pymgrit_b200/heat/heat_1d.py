@@ -79,7 +79,9 @@ class Heat1D(DeviceApplication):
             tab['nrhs'] = split.basis.shape[0]
             tab['rhs_x'] = dl.rhs_x_layout(split.basis, self.nx, team_threads, chunk)
             tab['rhs_x_key'] = (id(split), team_threads, chunk)      # levels with the same split share the device table
-            tab['rhs_t'] = split.coefficients(t) * dt_full[:, None]  # b * dt, heat_1d.py:214
+            # b * dt (heat_1d.py:214), evaluated straight into page-locked memory on long grids
+            out = dl.pinned_array((len(t), tab['nrhs'])) if len(t) >= (1 << 15) else None
+            tab['rhs_t'] = split.coefficients(t, scale=dt_full, out=out)
         elif split.kind == 'dense':
             tab['rhs_dense'] = split.dense(t) * dt_full[:, None]
         return tab

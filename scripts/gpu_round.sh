@@ -18,4 +18,5 @@ COARSENING=16 LEVELS=3 timeout 600 ncu --set full --clock-control none --import-
     -o gpurun_out/${tag}_sweeps -f python scripts/profile_sweeps.py > gpurun_out/${tag}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 python scripts/solve_timeline.py cfg5 > gpurun_out/${tag}_timeline.txt 2>&1
+timeout 300 python scripts/e2e_breakdown.py cfg5 > gpurun_out/${tag}_e2e_breakdown.txt 2>&1
 ls -la gpurun_out

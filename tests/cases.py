@@ -169,6 +169,24 @@ CASES = {
                                                 rhs=heat2d_rhs_xy, init_cond=heat2d_init, bc_left=2.0, bc_right=1.0,
                                                 bc_bottom=0.5, bc_top=1.5),
                       t=(0, 1, 65), grids=_simple(2, 4), solver=dict(tol=1e-8)),
+    # two-point (pair) states, heat/heat_1d_2pts_bdf{1,2}.py: examples/example_heat_1d_bdf2.py (BDF2 on the fine grid,
+    # BDF1 on the coarse grids; nt = 512 steps -> 257 pairs, dtau = t_stop / nt), and smaller variants
+    'heat1d_bdf2_example': dict(app='heat1d2pts',
+                                app_kw=[dict(nx=1001, dtau=2 / 512, method='BDF2', **HEAT),
+                                        dict(nx=1001, dtau=2 / 512, method='BDF1', **HEAT),
+                                        dict(nx=1001, dtau=2 / 512, method='BDF1', **HEAT)],
+                                t=(0, 2, 257), grids=_simple(3, 2), solver=dict()),
+    'heat1d_bdf1_small': dict(app='heat1d2pts', app_kw=dict(nx=17, dtau=2 / 128, method='BDF1', **HEAT),
+                              t=(0, 2, 65), grids=_simple(3, 2), solver=dict(tol=1e-9)),
+    'heat1d_bdf2_small_f': dict(app='heat1d2pts', app_kw=dict(nx=34, dtau=1 / 256, method='BDF2', **HEAT),
+                                t=(0, 1, 129), grids=_simple(3, 4), solver=dict(tol=1e-9, cycle_type='F')),
+    'heat1d_bdf2_nonuniform': dict(app='heat1d2pts',
+                                   app_kw=[dict(nx=65, dtau=0.004, method='BDF2', x_start=0, x_end=1, a=0.5,
+                                                init_cond=heat_init, rhs=heat_rhs_rank2),
+                                           dict(nx=65, dtau=0.004, method='BDF1', x_start=0, x_end=1, a=0.5,
+                                                init_cond=heat_init, rhs=heat_rhs_rank2)],
+                                   t_interval=0.01 + np.linspace(0, 1, 49) ** 1.3 * 1.5, grids=_simple(2, 3),
+                                   solver=dict(tol=1e-9, weight_c=0.9, nested_iteration=False)),
     # local convergence criteria (mgrit.py:434-454) on one time rank
     'heat1d_small_local_res': dict(app='heat1d', app_kw=dict(nx=17, **HEAT), t=(0, 2, 65), grids=_simple(3, 2),
                                    solver=dict(tol=1e-9, conv_crit=2)),

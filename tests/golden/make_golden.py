@@ -27,6 +27,8 @@ warnings.filterwarnings('ignore')
 from pymgrit.core.mgrit import Mgrit                      # noqa: E402
 from pymgrit.heat.heat_1d import Heat1D                   # noqa: E402
 from pymgrit.heat.heat_2d import Heat2D                   # noqa: E402
+from pymgrit.heat.heat_1d_2pts_bdf1 import Heat1DBDF1     # noqa: E402
+from pymgrit.heat.heat_1d_2pts_bdf2 import Heat1DBDF2     # noqa: E402
 from pymgrit.advection.advection_1d import Advection1D    # noqa: E402
 from pymgrit.dahlquist.dahlquist import Dahlquist         # noqa: E402
 from pymgrit.brusselator.brusselator import Brusselator   # noqa: E402
@@ -36,13 +38,23 @@ APPS = {'heat1d': Heat1D, 'heat2d': Heat2D, 'advection1d': Advection1D, 'dahlqui
         'brusselator': Brusselator}
 
 
+def heat1d2pts(method, **kw):
+    return {'BDF1': Heat1DBDF1, 'BDF2': Heat1DBDF2}[method](**kw)
+
+
+APPS['heat1d2pts'] = heat1d2pts
+
+
 def build_reference_problem(case):
     grids = C.case_time_grids(case)
     return [APPS[case['app']](t_interval=t, **C.level_app_kw(case, l)) for l, t in enumerate(grids)]
 
 
 def values_of(vec):
-    return np.array(vec.get_values(), dtype=float)
+    vals = vec.get_values()
+    if isinstance(vals, tuple):        # VectorHeat1D2Pts: (first, second, dtau)
+        return np.stack([np.asarray(vals[0], dtype=float), np.asarray(vals[1], dtype=float)])
+    return np.array(vals, dtype=float)
 
 
 def run_case(name):
@@ -128,6 +140,14 @@ def phi_steps():
     for k, dt in enumerate([5.0 / 4096, 40.0 / 4096, 2.5]):
         out[f'heat2d_65x49/dt{k}'] = np.array([dt])
         out[f'heat2d_65x49/out{k}'] = values_of(h2.step(u_start=v, t_start=0.1, t_stop=0.1 + dt))
+    for method, cls in (('BDF1', Heat1DBDF1), ('BDF2', Heat1DBDF2)):
+        hb = cls(x_start=0, x_end=1, nx=1001, a=1, dtau=2 / 512, init_cond=C.heat_init, rhs=C.heat_rhs, t_start=0,
+                 t_stop=2, nt=257)
+        v = hb.vector_t_start
+        out[f'heat1d2pts_{method}/in'] = values_of(v)
+        for k, dt in enumerate([2.0 / 256, 8.0 / 256, 0.5]):
+            out[f'heat1d2pts_{method}/dt{k}'] = np.array([dt])
+            out[f'heat1d2pts_{method}/out{k}'] = values_of(hb.step(u_start=v, t_start=0.25, t_stop=0.25 + dt))
     np.savez_compressed(os.path.join(HERE, 'phi_steps.npz'), **out)
     print('phi steps:', len(out), 'arrays')
 
