@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 3
+#define MGB_ABI_VERSION 4
 
 /* application kinds (which Phi) */
 #define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
@@ -43,6 +43,9 @@ extern "C" {
 #define MGB_APP_BRUSSELATOR 4 /* brusselator/brusselator.py:105-132  classical RK4 on 2 components           */
 #define MGB_APP_HEAT2D 5      /* heat/heat_2d.py:322-366 (BE branch) 5-point Laplacian, Dirichlet data;     */
                               /* rows are kept in sine space (see mgb_heat2d_to_rows)                         */
+#define MGB_APP_HEAT1D_2PTS 6 /* heat/heat_1d_2pts_bdf1.py:90-117, heat_1d_2pts_bdf2.py:92-138: a time point is    */
+                              /* the pair (u(t), u(t + dtau)), Phi = two Toeplitz tridiagonal solves; BDF1 or     */
+                              /* BDF2 is a property of the level's step constants (see "two-point rows" below)    */
 
 /* error codes */
 #define MGB_OK 0
@@ -116,6 +119,17 @@ int mgb_step_consts_width(int32_t app, int32_t team_threads, int32_t chunk);
  *   advection1d: nu = dt * c / dx     (advection_1d.py:108, 140) */
 int mgb_heat1d_step_consts(double r, int32_t n, int32_t team_threads, int32_t chunk, double *out);
 int mgb_advection1d_step_consts(double nu, int32_t n, int32_t team_threads, int32_t chunk, double *out);
+
+/* Two-point rows (MGB_APP_HEAT1D_2PTS).  n = unknowns of ONE of the two time points, chunk = 2 h + 1 with h the elements
+ * of each time point a thread owns, pitch = team_threads * chunk and a row is laid out per thread:
+ *     row[tid * chunk + j] = first[tid * h + j],  row[tid * chunk + h + j] = second[tid * h + j]  (j < h),  one 0.
+ * Phi(first, second) = (tmp1, tmp2),  tmp1 = S(r1) (a1 first + b1 second + rhs1),  tmp2 = S(r2) (a2 second + b2 tmp1 + rhs2),
+ * S(r) = (I + r tridiag(-1, 2, -1))^-1.  One step-constant row (width mgb_step_consts_width) is
+ *     [mgb_heat1d_step_consts(r1, n, team_threads, h)] [mgb_heat1d_step_consts(r2, ...)] [a1 b1 a2 b2 skip1 0 0 0]
+ * (skip1 != 0: r1 = 0, the first solve is the identity and its constants are ignored), rhs_x_dev is
+ * [nrhs][h][team_threads] and rhs_t_dev is [npts][2 nrhs]: the time factors of rhs1, then those of rhs2.
+ * mgb_heat1d_2pts_half_width returns the width of one of the two Heat1D blocks. */
+int mgb_heat1d_2pts_half_width(int32_t team_threads, int32_t chunk);
 
 /* ---- sweeps (one launch covers every coarse interval of the level) -------------------------- */
 

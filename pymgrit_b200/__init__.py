@@ -13,6 +13,9 @@ from pymgrit_b200.core.simple_setup_problem import simple_setup_problem
 from pymgrit_b200.core.mgrit import Mgrit
 from pymgrit_b200.heat.heat_1d import Heat1D, VectorHeat1D
 from pymgrit_b200.heat.heat_2d import Heat2D, VectorHeat2D
+from pymgrit_b200.heat.vector_heat_1d_2pts import VectorHeat1D2Pts
+from pymgrit_b200.heat.heat_1d_2pts_bdf1 import Heat1DBDF1
+from pymgrit_b200.heat.heat_1d_2pts_bdf2 import Heat1DBDF2
 from pymgrit_b200.advection.advection_1d import Advection1D, VectorAdvection1D
 from pymgrit_b200.dahlquist.dahlquist import Dahlquist, VectorDahlquist
 from pymgrit_b200.brusselator.brusselator import Brusselator, VectorBrusselator

@@ -10,9 +10,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libmgrit_b200.so')
 
-APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D = 1, 2, 3, 4, 5
+APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D, APP_HEAT1D_2PTS = 1, 2, 3, 4, 5, 6
 TNORM_ONE, TNORM_TWO, TNORM_INF = 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 F_RELAX_LAST_ONLY = 1
 DAHLQUIST_METHODS = {'BE': 0, 'FE': 1, 'TR': 2, 'MR': 3}
 
@@ -45,6 +45,7 @@ SYMBOLS = {
     'mgb_step_consts_width': (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     'mgb_heat1d_step_consts': (C.c_int, [C.c_double, C.c_int32, C.c_int32, C.c_int32, c_double_p]),
     'mgb_advection1d_step_consts': (C.c_int, [C.c_double, C.c_int32, C.c_int32, C.c_int32, c_double_p]),
+    'mgb_heat1d_2pts_half_width': (C.c_int, [C.c_int32, C.c_int32]),
     'mgb_f_relax': (C.c_int, [_LP, C.c_int32, C.c_void_p]),
     'mgb_c_relax': (C.c_int, [_LP, C.c_double, C.c_void_p]),
     'mgb_c_relax_last': (C.c_int, [_LP, C.c_double, C.c_void_p]),

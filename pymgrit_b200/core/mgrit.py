@@ -191,7 +191,8 @@ class Mgrit:
         self._fused_down = []
         for lvl in range(self.lvl_max - 1):
             cp = self._lv[lvl].cpts
-            ok = (weight_c == 1.0 and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D)
+            ok = (weight_c == 1.0 and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D,
+                                                           _lib.APP_HEAT1D_2PTS)
                   and (cp is None or len(cp) < 2 or int(np.min(np.diff(cp))) >= 2)
                   and os.environ.get('MGB_FUSED_DOWN', '1') != '0')
             self._fused_down.append(self._all_ranks(ok))

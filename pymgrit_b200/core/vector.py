@@ -102,8 +102,12 @@ class DeviceVector(Vector):
         return self.values
 
     @property
-    def size(self):
+    def _numel(self):
         return int(np.prod(self.shape)) if self.shape else 1
+
+    @property
+    def size(self):
+        return self._numel
 
     # -- arithmetic (C ABI) ------------------------------------------------------------------------
     def _axpby(self, a, other, b):
@@ -112,7 +116,7 @@ class DeviceVector(Vector):
         x = self.device_values.contiguous()
         y = other.device_values.contiguous() if other is not None else None
         out = torch.empty_like(x)
-        _lib.check(_lib.lib().mgb_vec_axpby(self.size, a, x.data_ptr(), b, y.data_ptr() if y is not None else None,
+        _lib.check(_lib.lib().mgb_vec_axpby(self._numel, a, x.data_ptr(), b, y.data_ptr() if y is not None else None,
                                             out.data_ptr(), _lib.current_stream_ptr()), 'vec_axpby')
         return self._new(out)
 
@@ -130,7 +134,7 @@ class DeviceVector(Vector):
         torch = _torch()
         x = self.device_values.contiguous()
         out = torch.empty(1, dtype=torch.float64, device=x.device)
-        _lib.check(_lib.lib().mgb_vec_sumsq(self.size, x.data_ptr(), out.data_ptr(), _lib.current_stream_ptr()),
+        _lib.check(_lib.lib().mgb_vec_sumsq(self._numel, x.data_ptr(), out.data_ptr(), _lib.current_stream_ptr()),
                    'vec_sumsq')
         return float(np.sqrt(out.item()))
 

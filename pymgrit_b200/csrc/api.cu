@@ -51,6 +51,7 @@ const DeviceInfo *device_info() {
 #define MGB_APP_Heat1D MGB_APP_HEAT1D
 #define MGB_APP_Advection1D MGB_APP_ADVECTION1D
 #define MGB_APP_Heat2D MGB_APP_HEAT2D
+#define MGB_APP_Heat1D2Pts MGB_APP_HEAT1D_2PTS
 #define MGB_SHAPE(APP, T, E) const SweepTable *mgb_table_##APP##_##T##_##E();
 #include "shapes.inc"
 #undef MGB_SHAPE
@@ -87,6 +88,18 @@ static int check_level(const mgb_level *l, const SweepTable **tab, LevelDev *out
             return fail(MGB_EINVAL, "missing heat2d symbol or step-constant table%s");
         if (l->nrhs < 0 || l->nrhs > kHeat2DMaxTerms || (l->nrhs > 0 && (l->rhs_x_dev == nullptr || l->rhs_t_dev == nullptr)))
             return fail(MGB_EINVAL, "heat2d takes at most 3 separable right-hand-side terms%s (got %ld)", "", l->nrhs);
+    } else if (l->app == MGB_APP_HEAT1D_2PTS) {
+        const long h = (l->chunk - 1) / 2;
+        if (l->chunk < 3 || l->chunk % 2 == 0 || (long)l->team_threads * h < l->n ||
+            (long)l->team_threads * l->chunk != l->pitch)
+            return fail(MGB_EINVAL, "two-point rows%s: pitch %ld must be team_threads * chunk and cover n = %ld", "",
+                        l->pitch, l->n);
+        if (l->sconst_dev == nullptr || l->ndt < 1 || (l->ndt > 1 && l->dtidx_dev == nullptr))
+            return fail(MGB_EINVAL, "missing step-constant table%s");
+        if (l->nrhs > 0 && (l->rhs_x_dev == nullptr || l->rhs_t_dev == nullptr))
+            return fail(MGB_EINVAL, "missing right-hand-side tables%s");
+        if (l->rhs_dense_dev != nullptr)
+            return fail(MGB_EINVAL, "two-point heat levels take a separable right-hand side only%s");
     } else if (!tiny) {
         if (l->pitch % 2) return fail(MGB_EINVAL, "pitch must be even%s (got %ld)", "", l->pitch);
         if ((long)l->team_threads * l->chunk < l->pitch)
@@ -119,7 +132,7 @@ static int check_level(const mgb_level *l, const SweepTable **tab, LevelDev *out
     for (int k = 0; k < 4; ++k) out->ip[k] = l->ip[k];
     out->nsys = multi ? l->nsys : 1;
     out->tile = multi ? l->team_threads * l->chunk : l->pitch;
-    out->nrow = l->n;
+    out->nrow = (l->app == MGB_APP_HEAT1D_2PTS) ? l->pitch : l->n;  // doubles of a row the row-wise helpers touch
     out->sig = multi ? l->sig_dev : nullptr;
     if (multi) out->n = out->tile;
     if (tiny && l->t_dev == nullptr) return fail(MGB_EINVAL, "ODE applications need the time grid t_dev%s");
@@ -271,7 +284,9 @@ int mgb_team_shape(int32_t app, int32_t n, int32_t *team_threads, int32_t *chunk
     const int pitch = n + (n & 1);
     long best = -1;
     for (const ShapeEntry &s : g_shapes) {
-        if (s.app != app || (long)s.T * s.E < pitch) continue;
+        // two-point rows: a thread owns (E - 1) / 2 elements of each of the two time points
+        const long cover = (app == MGB_APP_HEAT1D_2PTS) ? (long)s.T * ((s.E - 1) / 2) : (long)s.T * s.E;
+        if (s.app != app || cover < (app == MGB_APP_HEAT1D_2PTS ? n : pitch)) continue;
         // fewest threads first, then the smallest chunk
         const long key = (long)s.T * 1000 + s.E;
         if (best < 0 || key < best) {
@@ -286,7 +301,14 @@ int mgb_team_shape(int32_t app, int32_t n, int32_t *team_threads, int32_t *chunk
 
 int mgb_step_consts_width(int32_t app, int32_t team_threads, int32_t chunk) {
     if (app == MGB_APP_HEAT2D) return 8;  // [0] dt
+    if (app == MGB_APP_HEAT1D_2PTS) return 2 * mgb_heat1d_2pts_half_width(team_threads, chunk) + 8;
     const int sub = (chunk % 3 == 0) ? 3 : 1;
+    return kScalarConsts + team_threads * (2 + 2 * sub);
+}
+
+int mgb_heat1d_2pts_half_width(int32_t team_threads, int32_t chunk) {
+    const int h = (chunk - 1) / 2;
+    const int sub = (h % 3 == 0) ? 3 : 1;
     return kScalarConsts + team_threads * (2 + 2 * sub);
 }
 

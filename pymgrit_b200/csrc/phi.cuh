@@ -78,6 +78,8 @@ struct Heat1D {
         double beta, cs, kappa, bsl, Bd[5], B32, pw[SL], blf, blb, PH[SUB], QH[SUB];
         int nscan;
     };
+    // doubles of a row slice that carry values (the rest of the tile is padding the pipe reads as 0)
+    __device__ static __forceinline__ int row_n(const LevelDev &L) { return L.n; }
 
     __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int tid) {
         c.beta = __ldg(row + 0);
@@ -130,7 +132,6 @@ struct Heat1D {
     __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &it, const LevelDev &L, int i,
                                                  TeamT &team) {
         const int tid = team.tid;
-        const int nv = L.n - tid * E;
         // b = u + dt * rhs(x, t_i)                                           heat_1d.py:214
         if (L.nrhs > 0) {
             const double ct = __ldg(L.rhs_t + (size_t)i * L.nrhs);
@@ -143,6 +144,15 @@ struct Heat1D {
 #pragma unroll
             for (int j = 0; j < E; ++j) x[j] = fma(ct, __ldg(rx + j * T), x[j]);
         }
+        solve(x, c, L.n, team);
+    }
+
+    // x <- (I + r tridiag(-1, 2, -1))^-1 x for the r the constants c were made for; n = unknowns of the system.
+    // Elements beyond n must be 0 on entry.
+    template <class TeamT>
+    __device__ static __forceinline__ void solve(double (&x)[E], const C &c, const int n, TeamT &team) {
+        const int tid = team.tid;
+        const int nv = n - tid * E;
         // f = b * beta / r, forward recurrence y = beta (f + y_prev) inside each sub-chunk
         double e[SUB];
 #pragma unroll
@@ -161,7 +171,7 @@ struct Heat1D {
         for (int s = 1; s < SUB; ++s) a = fma(c.bsl, a, e[s]);
         double in = team.scan_fwd(a, c.Bd, c.B32, c.blf, c.nscan);
         // add the inflow; everything beyond element n-1 must stay exactly 0 for the backward recurrence
-        if (L.n % E == 0) {
+        if (n % E == 0) {
             // no thread holds a partially valid chunk (e.g. n = 1023 = 31 x 33): threads beyond n have zero data, so
             // cutting their inflow keeps them at 0 without a select per element
             in = (nv > 0) ? in : 0.0;
@@ -223,6 +233,109 @@ struct Heat1D {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Heat1D2Pts: the two-point (pair) states of heat/heat_1d_2pts_bdf1.py:90-117 and heat/heat_1d_2pts_bdf2.py:92-138.
+// A time point holds the values at t_i ("first") and t_i + dtau ("second"); one Phi is two tridiagonal solves
+//     s1   = a1 first + b1 second + sum_k ct1_k(i) X_k        tmp1 = (I + r1 tridiag(-1,2,-1))^-1 s1
+//     s2   = a2 second + b2 tmp1  + sum_k ct2_k(i) X_k        tmp2 = (I + r2 tridiag(-1,2,-1))^-1 s2
+//     Phi(first, second) = (tmp1, tmp2)
+// BDF1: a1 = a2 = 0, b1 = b2 = 1, r1 = (dt - dtau) a/dx^2, r2 = dtau a/dx^2, ct1 = (dt - dtau) T_k(t_i),
+//       ct2 = dtau T_k(t_i + dtau).
+// BDF2: the reference solves (L + coeff I) y = rhs - coeffm2 u_{-2} + coeffm1 u_{-1}; divided by coeff this is the same
+//       form with r = (a/dx^2)/coeff, a = -coeffm2/coeff, b = coeffm1/coeff, ct = T_k / coeff (host: heat_1d_2pts.py).
+// The method is a property of the level's constants, so a BDF2 fine level over BDF1 coarse levels
+// (examples/example_heat_1d_bdf2.py) runs through the same kernels.
+// Row layout (private to the engine, values enter and leave through Heat1D2Pts.values_to_rows / rows_to_values): thread
+// tid owns row[tid E, tid E + E) = first[tid EH, +EH) | second[tid EH, +EH) | one zero, E = 2 EH + 1 (odd stride).
+// Step-constant row: [Heat1D constants for r1 (width W)] [Heat1D constants for r2 (W)] [a1 b1 a2 b2 skip1 0 0 0],
+// W = kScalarConsts + T (2 + 2 SUB(EH)); skip1 != 0: r1 = 0, the first solve is the identity (dt = dtau).
+// Right-hand-side time table: [npts][2 nrhs] = ct1_0.. ct1_{q-1} ct2_0 .. ct2_{q-1}.
+// ---------------------------------------------------------------------------------------------
+template <int T_, int E_>
+struct Heat1D2Pts {
+    using SH = Shape<T_, E_>;
+    static constexpr int T = T_, E = E_;
+    static constexpr int EH = (E_ - 1) / 2;
+    using H = Heat1D<T_, EH>;
+    static constexpr int W = kScalarConsts + T_ * H::PT;
+
+    struct C {
+        typename H::C s1, s2;
+        double a1, b1, a2, b2;
+        bool skip1;
+    };
+    __device__ static __forceinline__ int row_n(const LevelDev &L) { return L.tile; }
+
+    __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int tid) {
+        H::load_consts(c.s1, row, tid);
+        H::load_consts(c.s2, row + W, tid);
+        c.a1 = __ldg(row + 2 * W + 0);
+        c.b1 = __ldg(row + 2 * W + 1);
+        c.a2 = __ldg(row + 2 * W + 2);
+        c.b2 = __ldg(row + 2 * W + 3);
+        c.skip1 = __ldg(row + 2 * W + 4) != 0.0;
+    }
+
+    struct Item {
+        double rx0[EH];
+    };
+    __device__ static __forceinline__ void load_rx0(Item &it, const LevelDev &L, int tid) {
+        const double *__restrict__ rx = L.rhs_x + tid;
+#pragma unroll
+        for (int j = 0; j < EH; ++j) it.rx0[j] = __ldg(rx + j * T);
+    }
+    template <class Pipe, class TeamT>
+    __device__ static __forceinline__ void begin_item(Item &it, const LevelDev &L, int, Pipe &, TeamT &team) {
+        if (L.nrhs > 0) load_rx0(it, L, team.tid);
+    }
+    template <class TeamT>
+    __device__ static __forceinline__ void retarget_item(Item &it, const LevelDev &from, const LevelDev &to, TeamT &team) {
+        if (to.nrhs > 0 && to.rhs_x != from.rhs_x) load_rx0(it, to, team.tid);
+    }
+
+    // y += sum_k ct_k X_k, ct = L.rhs_t[i][half * nrhs + k]
+    __device__ static __forceinline__ void add_rhs(double (&y)[EH], const Item &it, const LevelDev &L, int i, int half,
+                                                   int tid) {
+        if (L.nrhs <= 0) return;
+        const double *__restrict__ ctp = L.rhs_t + ((size_t)i * 2 + half) * L.nrhs;
+        const double ct0 = __ldg(ctp);
+#pragma unroll
+        for (int j = 0; j < EH; ++j) y[j] = fma(ct0, it.rx0[j], y[j]);
+        for (int k = 1; k < L.nrhs; ++k) {
+            const double ct = __ldg(ctp + k);
+            const double *__restrict__ rx = L.rhs_x + (size_t)k * EH * T + tid;
+#pragma unroll
+            for (int j = 0; j < EH; ++j) y[j] = fma(ct, __ldg(rx + j * T), y[j]);
+        }
+    }
+
+    template <class TeamT>
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &it, const LevelDev &L, int i,
+                                                 TeamT &team) {
+        const int tid = team.tid;
+        const int nv = L.n - tid * EH;
+        double p[EH], q[EH];
+#pragma unroll
+        for (int j = 0; j < EH; ++j) p[j] = fma(c.a1, x[j], c.b1 * x[EH + j]);
+        add_rhs(p, it, L, i, 0, tid);
+#pragma unroll
+        for (int j = 0; j < EH; ++j) p[j] = (j < nv) ? p[j] : 0.0;
+        if (!c.skip1) H::solve(p, c.s1, L.n, team);
+#pragma unroll
+        for (int j = 0; j < EH; ++j) q[j] = fma(c.a2, x[EH + j], c.b2 * p[j]);
+        add_rhs(q, it, L, i, 1, tid);
+#pragma unroll
+        for (int j = 0; j < EH; ++j) q[j] = (j < nv) ? q[j] : 0.0;
+        H::solve(q, c.s2, L.n, team);
+#pragma unroll
+        for (int j = 0; j < EH; ++j) {
+            x[j] = (j < nv) ? p[j] : 0.0;
+            x[EH + j] = (j < nv) ? q[j] : 0.0;
+        }
+        x[2 * EH] = 0.0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Advection1D.  Step-constant row layout:
 //   [0] rho  [1] sigma  [2] 1/(1-rho^n)  [3] rho^SL  [4..8] B^1,2,4,8,16 (B = rho^E)  [9] B^32
 //   [10..10+SL) rho^(jj+1)   [23] number of scan steps (as for Heat1D)
@@ -239,6 +352,7 @@ struct Advection1D {
         double rho, sig, dinv, rsl, Bd[5], B32, pw[SL], blf, RH[SUB];
         int nscan;
     };
+    __device__ static __forceinline__ int row_n(const LevelDev &L) { return L.n; }
 
     __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int tid) {
         c.rho = __ldg(row + 0);
@@ -348,6 +462,7 @@ struct Heat2D {
         double rx[QMAX][E];
         bool boundary;
     };
+    __device__ static __forceinline__ int row_n(const LevelDev &L) { return L.n; }
 
     __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int) {
         c.dt = __ldg(row);

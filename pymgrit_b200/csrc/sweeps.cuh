@@ -162,7 +162,7 @@ template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_chain(const LevelDev L, const int nw, const int last_only, const int nin) {
     using SH = typename Phi::SH;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenChain> pipe(g_smem, nin, L.tile, L.n, GenChain(L, blockIdx.x, nw, gridDim.x));
+    RowPipe<SH, GenChain> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenChain(L, blockIdx.x, nw, gridDim.x));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(Phi::T) k_c_relax(const LevelDev L, const doub
     using SH = typename Phi::SH;
     const bool weighted = (wgt != 1.0);
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenCRelax> pipe(g_smem, nin, L.tile, L.n, GenCRelax(L, blockIdx.x, nw, gridDim.x, weighted, kbase));
+    RowPipe<SH, GenCRelax> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenCRelax(L, blockIdx.x, nw, gridDim.x, weighted, kbase));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenFas> pipe(g_smem, nin, L.tile, L.n, GenFas(L, G, blockIdx.x, nw, gridDim.x));
+    RowPipe<SH, GenFas> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenFas(L, G, blockIdx.x, nw, gridDim.x));
     pipe.start(team);
     typename Phi::C c;  // reloaded before each Phi: fine and coarse steps use different constants
     for (int w = blockIdx.x; w < nw; w += gridDim.x) {
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(Phi::T) k_down(const LevelDev L, const LevelDe
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenDown> pipe(g_smem, nin, L.tile, L.n, GenDown(L, G, blockIdx.x, nw, gridDim.x));
+    RowPipe<SH, GenDown> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenDown(L, G, blockIdx.x, nw, gridDim.x));
     pipe.start(team);
     typename Phi::C cf, cc;  // fine and coarse step constants (reloaded per step on non-uniform grids)
     Phi::load_consts(cf, L.sconst, team.tid);
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(Phi::T) k_down(const LevelDev L, const LevelDe
         // FAS right-hand side
         if (L.g) {
             const double *gg = pipe.pop_ptr() + team.tid * E;
-            const int nv = L.n - team.tid * E;
+            const int nv = Phi::row_n(L) - team.tid * E;
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 const double r = (((gg[q] - outs[q]) + x[q]) + outs[q]) - stash[q];
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const Leve
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenCorrect> pipe(g_smem, nin, L.tile, L.n, GenCorrect(L, G, blockIdx.x, nw, gridDim.x, frelax != 0, kfirst));
+    RowPipe<SH, GenCorrect> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenCorrect(L, G, blockIdx.x, nw, gridDim.x, frelax != 0, kfirst));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(Phi::T) k_residual(const LevelDev L, double *_
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenResidual> pipe(g_smem, nin, L.tile, L.n, GenResidual(L, blockIdx.x, nw, gridDim.x));
+    RowPipe<SH, GenResidual> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenResidual(L, blockIdx.x, nw, gridDim.x));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(Phi::T) k_residual(const LevelDev L, double *_
         advance<Phi>(x, c, it, L, cp, pipe, team);
         pipe.pop(y, team);
         double acc = 0.0;
-        const int nv = L.n - team.tid * E;
+        const int nv = Phi::row_n(L) - team.tid * E;
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const double r = x[q] - y[q];
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(Phi::T) k_step(const LevelDev L, const int poi
                                                  const int nw, const int nin) {
     using SH = typename Phi::SH;
     Team<Phi::T> team(g_smem);
-    RowPipe<SH, GenStep> pipe(g_smem, nin, L.tile, L.n, GenStep(L, in, point, blockIdx.x, nw, gridDim.x));
+    RowPipe<SH, GenStep> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenStep(L, in, point, blockIdx.x, nw, gridDim.x));
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);

@@ -25,7 +25,7 @@ def test_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.mgb_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.mgb_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_struct_layout_matches_header(lib):
@@ -53,6 +53,20 @@ def test_team_shape_and_consts(lib):
     assert abs(beta + 1 / beta - (2 + 1 / r)) < 1e-14          # root of b^2 - (2 + 1/r) b + 1
     assert abs(row[1] - beta / r) < 1e-18 and abs(row[3] - beta ** 11) < 1e-15
     assert lib.mgb_heat1d_step_consts(-1.0, 1023, 32, 33, row.ctypes.data_as(_lib.c_double_p)) == 1
+
+
+def test_two_point_shape_and_widths(lib):
+    """MGB_APP_HEAT1D_2PTS: chunk = 2 h + 1, a thread owns h elements of each time point of the pair."""
+    from pymgrit_b200 import _lib
+    t, e = C.c_int32(), C.c_int32()
+    assert lib.mgb_team_shape(_lib.APP_HEAT1D_2PTS, 999, C.byref(t), C.byref(e)) == 0
+    assert e.value % 2 == 1 and t.value * ((e.value - 1) // 2) >= 999
+    assert lib.mgb_team_shape(_lib.APP_HEAT1D_2PTS, 9, C.byref(t), C.byref(e)) == 0
+    assert (t.value, e.value) == (32, 3)
+    half = lib.mgb_heat1d_2pts_half_width(32, 19)
+    assert half == lib.mgb_step_consts_width(_lib.APP_HEAT1D, 32, 9)
+    assert lib.mgb_step_consts_width(_lib.APP_HEAT1D_2PTS, 32, 19) == 2 * half + 8
+    assert lib.mgb_team_shape(_lib.APP_HEAT1D_2PTS, 10 ** 6, C.byref(t), C.byref(e)) == 2
 
 
 def test_heat1d_constants_solve_the_system(lib):

@@ -65,6 +65,56 @@ def test_brusselator_step_known_answer(P):       # tests/brusselator/test_brusse
     np.testing.assert_almost_equal(out.get_values(), np.array([0.08240173, 0.01319825]))
 
 
+def test_heat1d_two_point_step_known_answers(P):
+    # tests/heat/test_heat_1d_2pts_bdf1.py:35-54 (dt = dtau: the first of the two solves is the identity)
+    p = P.Heat1DBDF1(a=1, init_cond=lambda x: 2 * x, x_start=0, x_end=1, nx=11, dtau=0.1, t_start=0, t_stop=1, nt=11)
+    out = p.step(u_start=p.vector_t_start, t_start=0, t_stop=0.1)
+    assert isinstance(out, P.VectorHeat1D2Pts)
+    first, second, dtau = out.get_values()
+    np.testing.assert_almost_equal(first, np.array(
+        [0.14498001, 0.28445802, 0.41238183, 0.52154382, 0.6028602, 0.6444626, 0.63051125, 0.53961104, 0.34267192]))
+    np.testing.assert_almost_equal(second, np.array(
+        [0.08691756, 0.16802887, 0.23749726, 0.2894772, 0.31825048, 0.31856279, 0.28628511, 0.21958482, 0.12088191]))
+    assert dtau == 0.1
+    # tests/heat/test_heat_1d_2pts_bdf2.py:12-62
+    z = P.Heat1DBDF2(a=1, x_start=0, x_end=1, nx=11, dtau=0.1, t_start=0, t_stop=1, nt=11)
+    assert z.nx == 9 and isinstance(z.vector_template, P.VectorHeat1D2Pts)
+    np.testing.assert_equal(z.vector_t_start.get_values()[0], np.zeros(9))
+    np.testing.assert_equal(z.vector_t_start.get_values()[1], np.zeros(9))
+    p = P.Heat1DBDF2(a=1, init_cond=lambda x: 2 * x, x_start=0, x_end=1, nx=11, dtau=0.1, t_start=0, t_stop=1, nt=5)
+    np.testing.assert_almost_equal(p.vector_t_start.get_values()[0], np.array([0.2, 0.4, 0.6, 0.8, 1., 1.2, 1.4, 1.6, 1.8]))
+    np.testing.assert_almost_equal(p.vector_t_start.get_values()[1], np.array(
+        [0.15656217, 0.30443677, 0.43319873, 0.52860043, 0.56972221, 0.52478844, 0.34481236, -0.04620125, -0.76645512]))
+    first, second, dtau = p.step(u_start=p.vector_t_start, t_start=0, t_stop=0.2).get_values()
+    np.testing.assert_almost_equal(first, np.array(
+        [0.07115547, 0.13167183, 0.17105162, 0.1794494, 0.1490445, 0.07705183, -0.02834074, -0.1369469, -0.17685485]))
+    np.testing.assert_almost_equal(second, np.array(
+        [0.01235156, 0.02015287, 0.01986458, 0.01000559, -0.00781242, -0.02812508, -0.04182745, -0.03889518,
+         -0.01671786]))
+
+
+def test_heat1d_two_point_vector(P):
+    """tests/heat/test_vector_heat_1d_2pts.py: the pair vector's operations."""
+    v = P.VectorHeat1D2Pts(3, 0.1)
+    v.set_values(np.array([1.0, 2, 3]), np.array([4.0, 5, 6]), 0.1)
+    w = P.VectorHeat1D2Pts(3, 0.1)
+    w.set_values(np.ones(3), 2 * np.ones(3), 0.1)
+    s, d, m = v + w, v - w, v * 3
+    np.testing.assert_array_equal(s.get_values()[0], [2, 3, 4])
+    np.testing.assert_array_equal(s.get_values()[1], [6, 7, 8])
+    np.testing.assert_array_equal(d.get_values()[1], [2, 3, 4])
+    np.testing.assert_array_equal(m.get_values()[0], [3, 6, 9])
+    assert s.get_values()[2] == 0.1 and v.size == 3
+    assert abs(v.norm() - np.linalg.norm([1, 2, 3, 4, 5, 6])) < 1e-14
+    c = v.clone()
+    c.unpack(np.array([[9.0, 9, 9], [8.0, 8, 8]]))
+    np.testing.assert_array_equal(v.pack(), np.array([[1.0, 2, 3], [4.0, 5, 6]]))
+    np.testing.assert_array_equal(c.get_values()[1], [8, 8, 8])
+    assert not np.any(v.clone_zero().get_values()[0]) and v.clone_rand().get_values()[1].shape == (3,)
+    v2 = copy.deepcopy(v)
+    np.testing.assert_array_equal(v2.get_values()[0], [1, 2, 3])
+
+
 def test_phi_step_fixtures(P):
     """Single Phi at BASELINE sizes against the unmodified reference (1e-10 relative)."""
     g = load_golden('phi_steps')
@@ -80,6 +130,17 @@ def test_phi_step_fixtures(P):
         got = a.step(u_start=a.vector_t_start, t_start=0.0, t_stop=dt).get_values()
         ref = g[f'advection_4096/out{k}']
         assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    for method, cls in (('BDF1', P.Heat1DBDF1), ('BDF2', P.Heat1DBDF2)):
+        hb = cls(x_start=0, x_end=1, nx=1001, a=1, dtau=2 / 512, init_cond=C.heat_init, rhs=C.heat_rhs, t_start=0,
+                 t_stop=2, nt=257)
+        start = g[f'heat1d2pts_{method}/in']
+        first, second, _ = hb.vector_t_start.get_values()
+        assert np.max(np.abs(np.stack([first, second]) - start)) <= 1e-10 * np.max(np.abs(start))
+        for k in range(3):
+            dt = float(g[f'heat1d2pts_{method}/dt{k}'][0])
+            first, second, _ = hb.step(u_start=hb.vector_t_start, t_start=0.25, t_stop=0.25 + dt).get_values()
+            ref = g[f'heat1d2pts_{method}/out{k}']
+            assert np.max(np.abs(np.stack([first, second]) - ref)) <= 1e-10 * np.max(np.abs(ref))
     h2 = P.Heat2D(x_start=0, x_end=1, y_start=0, y_end=1, nx=65, ny=49, a=1, rhs=C.heat2d_rhs, init_cond=C.heat2d_init,
                   bc_left=1.0, bc_top=lambda y: 0.5 + 0 * y, t_start=0, t_stop=5, nt=5)
     np.testing.assert_array_equal(h2.vector_t_start.get_values(), g['heat2d_65x49/in'])
@@ -199,7 +260,7 @@ def test_spectral_coarse_solve_matches_phi_chain(P, variant):
 
 @pytest.mark.parametrize('name', ['heat1d_cfg2_nt1025', 'heat1d_nonuniform_t', 'heat1d_rhs_nonsep', 'heat1d_small_f_cf2',
                                   'heat1d_rhs_rank2', 'heat1d_trailing_f', 'heat1d_nx4097', 'advection_cfg4_small',
-                                  'heat2d_bc', 'heat2d_cfg3_small'])
+                                  'heat2d_bc', 'heat2d_cfg3_small', 'heat1d_bdf2_example', 'heat1d_bdf2_small_f'])
 def test_fused_down_sweep_is_bit_identical(P, name, monkeypatch):
     """mgb_down_sweep (C-relaxation + F-relaxation + FAS restriction in one launch) against the three separate
     launches: same residual history and the same solution, bit for bit."""

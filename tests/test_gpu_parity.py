@@ -29,9 +29,16 @@ def _check_against_golden(name):
     return solver, info
 
 
-@pytest.mark.parametrize('name', _cases(('heat1d',)))
+@pytest.mark.parametrize('name', [k for k in _cases(('heat1d',)) if C.CASES[k]['app'] == 'heat1d'])
 def test_heat1d_against_reference_fixture(name):
     _check_against_golden(name)
+
+
+@pytest.mark.parametrize('name', [k for k in C.CASES if C.CASES[k]['app'] == 'heat1d2pts'])
+def test_heat1d_two_point_bdf_against_reference_fixture(name):
+    """heat/heat_1d_2pts_bdf{1,2}.py: pair states, BDF2 over BDF1 levels (examples/example_heat_1d_bdf2.py)."""
+    solver, _ = _check_against_golden(name)
+    assert any(solver._fused_down) == (solver.weight_c == 1.0)
 
 
 @pytest.mark.parametrize('name', _cases(('dahlquist', 'brusselator')))
@@ -57,7 +64,8 @@ def test_heat1d_cfg2_full_size():
     assert len(info['conv']) == 3
 
 
-@pytest.mark.parametrize('name', ['heat1d_small_v', 'heat1d_cfg2_nt1025', 'advection_example'])
+@pytest.mark.parametrize('name', ['heat1d_small_v', 'heat1d_cfg2_nt1025', 'advection_example', 'heat1d_bdf1_small',
+                                  'heat1d_bdf2_nonuniform'])
 def test_against_live_oracle(name):
     """Same seeded inputs through the CPU oracle (C Thomas arithmetic) and the GPU, all level-0 points compared."""
     mg, ref = run_oracle(name, solver='c')

@@ -47,6 +47,29 @@ def test_brusselator_step_known_answer():  # tests/brusselator/test_brusselator.
     np.testing.assert_almost_equal(p.phi(np.zeros(2), 0, 0.1), np.array([0.08240173, 0.01319825]))
 
 
+def test_heat1d_2pts_step_known_answers():
+    # tests/heat/test_heat_1d_2pts_bdf1.py:35-54
+    p = O.Heat1D2PtsOracle(a=1, init_cond=lambda x: 2 * x, x_start=0, x_end=1, nx=11, dtau=0.1, method='BDF1', t_start=0,
+                           t_stop=1, nt=11)
+    got = p.phi(p.u0, 0, 0.1)
+    np.testing.assert_almost_equal(got[0], np.array(
+        [0.14498001, 0.28445802, 0.41238183, 0.52154382, 0.6028602, 0.6444626, 0.63051125, 0.53961104, 0.34267192]))
+    np.testing.assert_almost_equal(got[1], np.array(
+        [0.08691756, 0.16802887, 0.23749726, 0.2894772, 0.31825048, 0.31856279, 0.28628511, 0.21958482, 0.12088191]))
+    # tests/heat/test_heat_1d_2pts_bdf2.py:37-62
+    p = O.Heat1D2PtsOracle(a=1, init_cond=lambda x: 2 * x, x_start=0, x_end=1, nx=11, dtau=0.1, method='BDF2', t_start=0,
+                           t_stop=1, nt=5)
+    np.testing.assert_almost_equal(p.u0[0], np.array([0.2, 0.4, 0.6, 0.8, 1., 1.2, 1.4, 1.6, 1.8]))
+    np.testing.assert_almost_equal(p.u0[1], np.array(
+        [0.15656217, 0.30443677, 0.43319873, 0.52860043, 0.56972221, 0.52478844, 0.34481236, -0.04620125, -0.76645512]))
+    got = p.phi(p.u0, 0, 0.2)
+    np.testing.assert_almost_equal(got[0], np.array(
+        [0.07115547, 0.13167183, 0.17105162, 0.1794494, 0.1490445, 0.07705183, -0.02834074, -0.1369469, -0.17685485]))
+    np.testing.assert_almost_equal(got[1], np.array(
+        [0.01235156, 0.02015287, 0.01986458, 0.01000559, -0.00781242, -0.02812508, -0.04182745, -0.03889518,
+         -0.01671786]))
+
+
 # ---- golden residual files of the reference (tests/mpi/results/*, compared at 4 decimals there) ----
 REF_FILES = {
     'dahlquist_cfg1': [7.186185937025429e-05, 1.246106707585954e-06, 2.1015566149418615e-08, 3.1441273895579124e-10,
@@ -128,6 +151,15 @@ def test_phi_step_fixtures():
             assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref))
     h2 = O.Heat2DOracle(x_start=0, x_end=1, y_start=0, y_end=1, nx=65, ny=49, a=1, rhs=C.heat2d_rhs,
                         init_cond=C.heat2d_init, bc_left=1.0, bc_top=lambda y: 0.5 + 0 * y, t_start=0, t_stop=5, nt=5)
+    for method in ('BDF1', 'BDF2'):
+        hb = O.Heat1D2PtsOracle(x_start=0, x_end=1, nx=1001, a=1, dtau=2 / 512, init_cond=C.heat_init, rhs=C.heat_rhs,
+                                method=method, t_start=0, t_stop=2, nt=257)
+        np.testing.assert_array_equal(hb.u0, g[f'heat1d2pts_{method}/in'])
+        for k in range(3):
+            dt = float(g[f'heat1d2pts_{method}/dt{k}'][0])
+            got = hb.phi(hb.u0, 0.25, 0.25 + dt)
+            ref = g[f'heat1d2pts_{method}/out{k}']
+            assert np.max(np.abs(got - ref)) <= 1e-14 * np.max(np.abs(ref))
     np.testing.assert_array_equal(h2.u0, g['heat2d_65x49/in'])
     for k in range(3):
         dt = float(g[f'heat2d_65x49/dt{k}'][0])
