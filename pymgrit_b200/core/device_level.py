@@ -63,6 +63,9 @@ class DeviceLevel:
         tiny = app.kind in (_lib.APP_DAHLQUIST, _lib.APP_BRUSSELATOR)
         self.pitch = int(app.row_pitch()) if hasattr(app, 'row_pitch') else (self.n if tiny else self.n + (self.n & 1))
         self.team_threads, self.chunk = team_shape(app.kind, self.n)
+        # the (asynchronous) zero fill of the level arrays runs on the device while the host builds the tables
+        self.u = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if u_init is None else u_init
+        self.g = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if with_g else None
         tab = app.level_tables(self.t, self.team_threads, self.chunk)
         self._keep = []                                   # tensors referenced by the struct
         self.h2d_bytes = 0
@@ -83,8 +86,6 @@ class DeviceLevel:
             self._keep.append(ten)
             return ten
 
-        self.u = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if u_init is None else u_init
-        self.g = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if with_g else None
         self.cpts = None if cpts is None else np.asarray(cpts, dtype=np.int32)
         self.cpts_dev = up(self.cpts, np.int32)
         self.t_dev = up(self.t, np.float64)
@@ -171,7 +172,7 @@ def dt_classes(t):
     if len(t) < 2:
         return np.array([1.0]), None
     dt = t[1:] - t[:-1]
-    if np.all(dt == dt[0]):
+    if dt[0] == dt[-1] and dt[0] == dt[len(dt) // 2] and dt.min() == dt.max():      # uniform grid: one pass each
         return dt[:1].copy(), None
     uniq, inv = np.unique(dt, return_inverse=True)
     idx = np.zeros(len(t), dtype=np.int32)

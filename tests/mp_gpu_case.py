@@ -32,7 +32,8 @@ def main():
         solver = P.Mgrit(problem=b200_problem(case), logging_lvl=logging.WARNING, **case['solver'])
         info = solver.solve()
         lv = solver._lv[0]
-        own = lv.values(idx=np.arange(1 if rank > 0 else 0, lv.npts)).reshape(-1, lv.n)     # drop the ghost row
+        own = lv.values(idx=np.arange(1 if rank > 0 else 0, lv.npts))                       # drop the ghost row
+        own = own.reshape(len(own), -1)
         parts = [None] * world
         dist.all_gather_object(parts, own)
         if rank == 0:
