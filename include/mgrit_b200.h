@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 4
+#define MGB_ABI_VERSION 5
 
 /* application kinds (which Phi) */
 #define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
@@ -173,6 +173,31 @@ int mgb_down_sweep(const mgb_level *fine, const mgb_level *coarse, void *stream)
 #define MGB_CORRECT_F_RELAX 1
 #define MGB_CORRECT_GHOST 2
 int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t flags, void *stream);
+
+/* FAS restriction with a spatial grid transfer R != identity (mgrit.py:488-549 with a user GridTransfer,
+ * core/grid_transfer.py:31-55; examples/example_spatial_coarsening.py).  Fine and coarse level differ in spatial size, so
+ * the sweep is split around the transfer:
+ *   mgb_residual_rows(fine, out)      out[j] = Phi_f(u[c_j-1]) - u[c_j] (level 0) or (g[c_j] - u[c_j]) + Phi_f(u[c_j-1]),
+ *                                     j >= 1; out is [ncpts][pitch] in the fine level's row layout
+ *   mgb_heat1d_restrict_rows          coarse.u[j] = R(fine.u[c_j]) (all j), v = copy of coarse.u, rres[j] = R(out[j])
+ *   mgb_fas_coarse_rhs(coarse, v, rres, nrows)   coarse.g[j] = (rres[j] + v[j]) - Phi_c(v[j-1]),  j = 1 .. nrows-1
+ * v (mgrit.py:520) must be stored here: it is no longer a copy of fine-level rows. */
+int mgb_residual_rows(const mgb_level *lvl, double *out_rows_dev, void *stream);
+int mgb_fas_coarse_rhs(const mgb_level *coarse, const double *v_dev, const double *rres_dev, int32_t nrows, void *stream);
+
+/* The spatial transfer of examples/example_spatial_coarsening.py:18-79 for Heat1D rows, n_fine = 2 n_coarse + 1 interior
+ * points, homogeneous Dirichlet boundaries; one launch covers all rows.
+ *   restrict (full weighting):  dst[j][i] = (s[2i]/4 + s[2i+1]/2) + s[2i+2]/4,  s = src[src_index ? src_index[j] : j],
+ *                               j < nrows; the padding of dst rows is zeroed
+ *   interp (linear):            e = a[j] - b[j] (a[j] if b is NULL);  E[2i+1] = e[i], E[2i] = e[i-1]/2 + e[i]/2;
+ *                               dst[r] = accumulate ? dst[r] + E : E,  r = dst_index ? dst_index[j] : j,  first <= j < nrows
+ * With accumulate this is the coarse-grid correction of mgrit.py:715-726 (a = coarse.u, b = v, dst = fine.u, dst_index =
+ * the fine level's C-points), without it the interpolation of nested iteration (mgrit.py:559-563). */
+int mgb_heat1d_restrict_rows(int32_t nrows, const double *src_dev, int32_t src_pitch, const int32_t *src_index_dev,
+                             int32_t n_fine, double *dst_dev, int32_t dst_pitch, void *stream);
+int mgb_heat1d_interp_rows(int32_t nrows, int32_t first, const double *a_dev, const double *b_dev, int32_t c_pitch,
+                           int32_t n_coarse, double *dst_dev, int32_t dst_pitch, const int32_t *dst_index_dev,
+                           int32_t accumulate, void *stream);
 
 /* Sequential solve on the coarsest level, mgrit.py:459-486: u[i] = (g[i] +) Phi(u[i-1]), i = 1..npts-1. */
 int mgb_forward_solve(const mgb_level *lvl, void *stream);

@@ -346,12 +346,43 @@ def simple_hierarchy(problem: OracleProblem, level: int, coarsening: int) -> Lis
 # --------------------------------------------------------------------------------------------
 # Serial MGRIT (FAS) on arrays
 # --------------------------------------------------------------------------------------------
+class CopyTransfer:
+    """core/grid_transfer_copy.py:25-47: the identity in both directions."""
+
+    @staticmethod
+    def restriction(u):
+        return u
+
+    @staticmethod
+    def interpolation(u):
+        return u
+
+
+class Heat1DSpaceTransfer:
+    """The spatial grid transfer of examples/example_spatial_coarsening.py:18-79 (user code of the reference's example,
+    restated on arrays): full-weighting restriction and linear interpolation between 1-D grids of 2 n + 1 and n interior
+    points with homogeneous Dirichlet boundaries.  Sums are taken in the example's order."""
+
+    @staticmethod
+    def restriction(u):
+        return u[0:-2:2] * 1 / 4 + u[1:-1:2] * 1 / 2 + u[2::2] * 1 / 4
+
+    @staticmethod
+    def interpolation(u):
+        out = np.zeros(2 * len(u) + 1)
+        out[0:-2:2] += 1 / 2 * u
+        out[1:-1:2] += u
+        out[2::2] += 1 / 2 * u
+        return out
+
+
 class MgritOracle:
-    """One-rank restatement of core/mgrit.py (identity grid transfer = core/grid_transfer_copy.py)."""
+    """One-rank restatement of core/mgrit.py.  transfer: one object per level pair with restriction(array) /
+    interpolation(array) (core/grid_transfer.py:31-55); default = the identity (core/grid_transfer_copy.py)."""
 
     def __init__(self, problem: Sequence[OracleProblem], weight_c: float = 1.0, max_iter: int = 100,
                  tol: float = 1e-7, nested_iteration: bool = True, cf_iter=1, cycle_type: str = 'V',
-                 t_norm: int = 2, conv_crit: int = 0, phi_counter: Optional[list] = None):
+                 t_norm: int = 2, conv_crit: int = 0, phi_counter: Optional[list] = None, transfer=None):
         if cycle_type not in ('V', 'F'):
             raise Exception("Cycle-type " + str(cycle_type) + " is not implemented. Choose 'V' or 'F'")
         if t_norm not in (1, 2, 3):
@@ -363,6 +394,9 @@ class MgritOracle:
         t0 = time.time()
         self.problem = list(problem)
         self.L = len(self.problem)
+        self.transfer = list(transfer) if transfer is not None else [CopyTransfer() for _ in range(self.L - 1)]
+        if len(self.transfer) != self.L - 1:
+            raise Exception('There should be exactly one transfer operator for each level except the coarsest grid')
         self.cf_iter = [cf_iter] * self.L if isinstance(cf_iter, int) else list(cf_iter)
         self.weight_c = weight_c
         self.tol = tol
@@ -380,8 +414,7 @@ class MgritOracle:
                 self.cpts.append(np.where(np.isin(self.t[l], self.t[l + 1]))[0])
             else:
                 self.cpts.append(np.arange(len(self.t[l])))
-        shape = np.shape(self.problem[0].u0)
-        self.u = [np.zeros((len(self.t[l]),) + shape) for l in range(self.L)]    # mgrit.py:846-858
+        self.u = [np.zeros((len(self.t[l]),) + np.shape(self.problem[l].u0)) for l in range(self.L)]    # mgrit.py:846-858
         self.g = [None] + [np.zeros_like(self.u[l]) for l in range(1, self.L)]
         self.v = [None] + [np.zeros_like(self.u[l]) for l in range(1, self.L)]
         for l in range(self.L):
@@ -425,7 +458,9 @@ class MgritOracle:
     def fas_residual(self, l):                           # mgrit.py:497-547
         u, g = self.u[l], self.g[l]
         c = self.cpts[l]
-        self.u[l + 1][:len(c)] = u[c]                    # injection
+        R = self.transfer[l].restriction
+        for j in range(len(c)):
+            self.u[l + 1][j] = R(u[c[j]])                # restriction of every C-point (injection for the identity)
         self.v[l + 1] = self.u[l + 1].copy()
         v = self.v[l + 1]
         for j in range(1, len(c)):
@@ -433,12 +468,12 @@ class MgritOracle:
                 fine = self.phi(l, u[c[j] - 1], c[j]) - u[c[j]]
             else:
                 fine = g[c[j]] - u[c[j]] + self.phi(l, u[c[j] - 1], c[j])
-            self.g[l + 1][j] = fine + v[j] - self.phi(l + 1, v[j - 1], j)
+            self.g[l + 1][j] = R(fine) + v[j] - self.phi(l + 1, v[j - 1], j)
 
     def error_correction(self, l):                       # mgrit.py:722-726
         c = self.cpts[l]
         for j in range(1, len(c)):
-            e = self.u[l + 1][j] - self.v[l + 1][j]
+            e = self.transfer[l].interpolation(self.u[l + 1][j] - self.v[l + 1][j])
             self.u[l][c[j]] = self.u[l][c[j]] + e
 
     def forward_solve(self, l):                          # mgrit.py:471-481
@@ -470,7 +505,7 @@ class MgritOracle:
         for l in range(self.L - 2, -1, -1):
             c = self.cpts[l]
             for j in range(1, len(c)):
-                self.u[l][c[j]] = self.u[l + 1][j]
+                self.u[l][c[j]] = self.transfer[l].interpolation(self.u[l + 1][j])
             if l > 0:
                 self.iteration(l, 'V', 0, True)
 

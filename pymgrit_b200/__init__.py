@@ -7,12 +7,13 @@ Same names and arguments as `pymgrit` (reference: src/pymgrit/__init__.py); see 
 """
 from pymgrit_b200.core.application import Application, DeviceApplication
 from pymgrit_b200.core.vector import Vector, DeviceVector
-from pymgrit_b200.core.grid_transfer import GridTransfer
+from pymgrit_b200.core.grid_transfer import GridTransfer, DeviceGridTransfer
 from pymgrit_b200.core.grid_transfer_copy import GridTransferCopy
 from pymgrit_b200.core.simple_setup_problem import simple_setup_problem
 from pymgrit_b200.core.mgrit import Mgrit
 from pymgrit_b200.heat.heat_1d import Heat1D, VectorHeat1D
 from pymgrit_b200.heat.heat_2d import Heat2D, VectorHeat2D
+from pymgrit_b200.heat.grid_transfer_heat_1d import GridTransferHeat1D, GridTransferHeat
 from pymgrit_b200.heat.vector_heat_1d_2pts import VectorHeat1D2Pts
 from pymgrit_b200.heat.heat_1d_2pts_bdf1 import Heat1DBDF1
 from pymgrit_b200.heat.heat_1d_2pts_bdf2 import Heat1DBDF2

@@ -21,7 +21,7 @@ from pymgrit_b200 import _lib
 from pymgrit_b200.core.application import Application, DeviceApplication
 from pymgrit_b200.core.comm import SerialComm, as_time_comm
 from pymgrit_b200.core.device_level import DeviceLevel
-from pymgrit_b200.core.grid_transfer import GridTransfer
+from pymgrit_b200.core.grid_transfer import GridTransfer, DeviceGridTransfer
 from pymgrit_b200.core.grid_transfer_copy import GridTransferCopy
 from pymgrit_b200.core import partition
 
@@ -113,14 +113,22 @@ class Mgrit:
             if not isinstance(p, DeviceApplication):
                 raise Exception('pymgrit_b200.Mgrit runs applications derived from DeviceApplication only; '
                                 + type(p).__name__ + ' has no device kernels')
-        for tr in transfer:
-            if type(tr) is not GridTransferCopy:
-                raise Exception('only the identity GridTransferCopy is fused into the device sweeps')
+        # grid transfers: the identity is fused into the sweeps; a DeviceGridTransfer (spatial coarsening as row-wise
+        # kernels) splits the FAS restriction and the correction around it; a transfer written in Python cannot run
+        # inside a sweep
+        for lvl, tr in enumerate(transfer):
+            if type(tr) is GridTransferCopy:
+                if (problem[lvl].kind, problem[lvl].ndof) != (problem[lvl + 1].kind, problem[lvl + 1].ndof):
+                    raise Exception('levels connected by GridTransferCopy must use the same application kind and '
+                                    'spatial size')
+            elif isinstance(tr, DeviceGridTransfer):
+                tr.check(problem[lvl], problem[lvl + 1])
+            else:
+                raise Exception('only GridTransferCopy and device grid transfers (DeviceGridTransfer, e.g. '
+                                'GridTransferHeat1D) run in the device sweeps; ' + type(tr).__name__ + ' does not')
         # conv_crit 2 / 3 (local criteria, mgrit.py:434-454) let a time rank stop once its own points and all earlier
         # ranks have converged.  On one rank that is the global test on the same per-point norms; the rank-by-rank
         # shutdown protocol (message kind 6, sender_finished) is not built.
-        if len({(p.kind, p.ndof) for p in problem}) != 1:
-            raise Exception('all levels must use the same application kind and spatial size')
 
         self.comm_time = as_time_comm(comm_time)
         self.comm_space = comm_space
@@ -188,10 +196,11 @@ class Mgrit:
         # levels whose down-sweep runs as one fused launch (mgb_down_sweep): unweighted C-relaxation, at least one
         # F-point in every interval (on every time rank), team kernels
         import os
+        self._xfer = [None if type(tr) is GridTransferCopy else tr for tr in transfer] + [None]
         self._fused_down = []
         for lvl in range(self.lvl_max - 1):
             cp = self._lv[lvl].cpts
-            ok = (weight_c == 1.0 and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D,
+            ok = (weight_c == 1.0 and self._xfer[lvl] is None and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D,
                                                            _lib.APP_HEAT1D_2PTS)
                   and (cp is None or len(cp) < 2 or int(np.min(np.diff(cp))) >= 2)
                   and os.environ.get('MGB_FUSED_DOWN', '1') != '0')
@@ -208,9 +217,19 @@ class Mgrit:
         self.comm_time.setup_peer_exchange(self)         # ghost rows over peer memory where the ranks can (core/comm.py)
         self.u = [_LevelVectors(lv, 'u') for lv in self._lv]
         self.g = [None] + [_LevelVectors(lv, 'g') for lv in self._lv[1:]]
-        self.v = [None] * self.lvl_max       # never materialised: identical to the fine level's C-point rows
-        self._init_levels()
+        self.v = [None] * self.lvl_max       # never materialised: identical to the fine level's C-point rows ...
+        self._rres = [None] * self.lvl_max   # ... except below a spatial transfer: v, fine residual rows, their restriction
+        self._rresc = [None] * self.lvl_max
         torch = _lib_torch()
+        for lvl in range(self.lvl_max - 1):
+            if self._xfer[lvl] is not None:
+                fine, coarse = self._lv[lvl], self._lv[lvl + 1]
+                ncp = len(fine.cpts)
+                coarse.v = torch.zeros_like(coarse.u)
+                self.v[lvl + 1] = _LevelVectors(coarse, 'v')
+                self._rres[lvl] = torch.zeros((ncp, fine.pitch), dtype=torch.float64, device=fine.u.device)
+                self._rresc[lvl] = torch.zeros((ncp, coarse.pitch), dtype=torch.float64, device=fine.u.device)
+        self._init_levels()
         dev = self._lv[0].u.device
         ncp0 = len(self._lv[0].cpts) if self._lv[0].cpts is not None else 1
         nsys0 = self._lv[0].nsys
@@ -377,6 +396,19 @@ class Mgrit:
     def fas_residual(self, lvl: int) -> None:
         """Injection + FAS right-hand side of the next coarser level (mgrit.py:488-549)."""
         fine, coarse = self._lv[lvl], self._lv[lvl + 1]
+        xfer = self._xfer[lvl]
+        if xfer is not None:
+            # spatial transfer R: fine residual rows, R of every C-point and of the residuals, v = copy, coarse FAS rhs
+            ncp = len(fine.cpts)
+            lib = _lib.lib()
+            _lib.check(lib.mgb_residual_rows(fine.ref, self._rres[lvl].data_ptr(), self._stream()), 'residual_rows')
+            xfer.restrict_rows(ncp, fine.u, fine.cpts_dev, coarse.u, fine.app)
+            coarse.v[:ncp].copy_(coarse.u[:ncp])
+            xfer.restrict_rows(ncp, self._rres[lvl], None, self._rresc[lvl], fine.app)
+            self.launches += 3
+            _lib.check(lib.mgb_fas_coarse_rhs(coarse.ref, coarse.v.data_ptr(), self._rresc[lvl].data_ptr(), ncp,
+                                              self._stream()), 'fas_coarse_rhs')
+            return
         if coarse.npts > 0 and fine.npts > 0:
             coarse.u[0].copy_(fine.u[0])             # the ghost / initial C-point is injected like any other
         _lib.check(_lib.lib().mgb_fas_residual(fine.ref, coarse.ref, self._stream()), 'fas_residual')
@@ -396,6 +428,15 @@ class Mgrit:
 
     def error_correction(self, lvl: int, f_relax: bool = False) -> None:
         """Coarse-grid correction of the C-points (mgrit.py:715-726), optionally fused with the next F-relaxation."""
+        xfer = self._xfer[lvl]
+        if xfer is not None:
+            fine, coarse = self._lv[lvl], self._lv[lvl + 1]
+            first = 0 if self.comm_time_rank > 0 else 1           # ranks > 0 correct their ghost copy themselves
+            xfer.interpolate_rows(len(fine.cpts), first, coarse.u, coarse.v, fine.u, fine.cpts_dev, True, coarse.app)
+            self.launches += 1
+            if f_relax:
+                self.f_relax(lvl)
+            return
         flags = (1 if f_relax else 0) | (2 if self.comm_time_rank > 0 else 0)      # MGB_CORRECT_F_RELAX | MGB_CORRECT_GHOST
         _lib.check(_lib.lib().mgb_error_correction(self._lv[lvl].ref, self._lv[lvl + 1].ref, flags, self._stream()),
                    'error_correction')
@@ -426,7 +467,14 @@ class Mgrit:
         """Coarsest solve, then interpolate upwards with a V-cycle per level (mgrit.py:551-566)."""
         self.forward_solve(self.lvl_max - 1)
         for lvl in range(self.lvl_max - 2, -1, -1):
-            _lib.check(_lib.lib().mgb_inject_up(self._lv[lvl].ref, self._lv[lvl + 1].ref, self._stream()), 'inject_up')
+            if self._xfer[lvl] is not None:
+                fine, coarse = self._lv[lvl], self._lv[lvl + 1]
+                self._xfer[lvl].interpolate_rows(len(fine.cpts), 1, coarse.u, None, fine.u, fine.cpts_dev, False,
+                                                 coarse.app)
+                self.launches += 1
+            else:
+                _lib.check(_lib.lib().mgb_inject_up(self._lv[lvl].ref, self._lv[lvl + 1].ref, self._stream()),
+                           'inject_up')
             self._exchange_ghost(lvl)
             if lvl > 0:
                 self.iteration(lvl=lvl, cycle_type='V', iteration=0, first_f=True)

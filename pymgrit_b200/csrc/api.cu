@@ -435,6 +435,21 @@ int mgb_residual_norms(const mgb_level *lvl, double *out_sq_dev, void *stream) {
     return tab->residual(L, out_sq_dev, st);
 }
 
+int mgb_residual_rows(const mgb_level *lvl, double *out_rows_dev, void *stream) {
+    MGB_PROLOGUE(lvl)
+    if (L.cpts == nullptr || out_rows_dev == nullptr) return fail(MGB_EINVAL, "residual_rows needs C-points and an output%s");
+    if (tab->residual_rows == nullptr) return fail(MGB_ENOSHAPE, "no spatial-transfer sweeps for this application%s");
+    return tab->residual_rows(L, out_rows_dev, st);
+}
+
+int mgb_fas_coarse_rhs(const mgb_level *coarse, const double *v_dev, const double *rres_dev, int32_t nrows, void *stream) {
+    MGB_PROLOGUE(coarse)
+    if (v_dev == nullptr || rres_dev == nullptr || nrows < 0 || nrows > L.npts || L.g == nullptr)
+        return fail(MGB_EINVAL, "fas_coarse_rhs: bad argument%s");
+    if (tab->fas_rhs == nullptr) return fail(MGB_ENOSHAPE, "no spatial-transfer sweeps for this application%s");
+    return tab->fas_rhs(L, v_dev, rres_dev, nrows, st);
+}
+
 int mgb_jump_norms(const mgb_level *lvl, double *last_dev, double *out_sq_dev, void *stream) {
     MGB_PROLOGUE(lvl)
     (void)tab;

@@ -117,9 +117,29 @@ struct Launch {
         return cuda_fail(cudaGetLastError(), "step");
     }
 
+    // out: [ncpts][pitch] rows, row j = fine residual at C-point j (row 0 untouched)
+    static int residual_rows(const LevelDev &L, double *out, cudaStream_t st) {
+        if (L.ncpts < 2) return 0;
+        const int nin = 3, nw = (L.ncpts - 1) * nsys(L);
+        int grid;
+        if (int rc = grid_for(k_residual_rows<Phi>, nw, nin, &grid)) return rc;
+        k_residual_rows<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, out, nw, nin);
+        return cuda_fail(cudaGetLastError(), "residual_rows");
+    }
+
+    // G.g[j] = (RR[j] + V[j]) - Phi_c(V[j-1]), j = 1 .. nrows-1
+    static int fas_rhs(const LevelDev &G, const double *V, const double *RR, int nrows, cudaStream_t st) {
+        if (nrows < 2) return 0;
+        const int nin = 4, nw = (nrows - 1) * nsys(G);
+        int grid;
+        if (int rc = grid_for(k_fas_rhs<Phi>, nw, nin, &grid)) return rc;
+        k_fas_rhs<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(G, V, RR, nw, nin);
+        return cuda_fail(cudaGetLastError(), "fas_coarse_rhs");
+    }
+
     static const SweepTable *table() {
-        static const SweepTable t = {Phi::T,       Phi::E,   &f_relax, &forward_solve, &c_relax,
-                                     &fas_residual, &correct, &residual, &step,         &down};
+        static const SweepTable t = {Phi::T,   Phi::E, &f_relax, &forward_solve,  &c_relax, &fas_residual, &correct,
+                                     &residual, &step,  &down,    &residual_rows, &fas_rhs};
         return &t;
     }
 };

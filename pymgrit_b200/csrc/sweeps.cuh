@@ -394,6 +394,178 @@ __global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// FAS restriction with a spatial grid transfer R (mgrit.py:488-549, transfer != GridTransferCopy).  The fine and the
+// coarse level have different spatial sizes, so the sweep is split around the transfer:
+//   k_residual_rows (fine shape):    out[j] = Phi_f(u[c_j-1]) - u[c_j]               (level 0)
+//                                    out[j] = (g[c_j] - u[c_j]) + Phi_f(u[c_j-1])    (level > 0),  j >= 1
+//   row-wise transfer kernels:       G.u[j] = R(u[c_j]), V = copy of G.u, RR[j] = R(out[j])        (csrc/transfer.cu)
+//   k_fas_rhs (coarse shape):        G.g[j] = (RR[j] + V[j]) - Phi_c(V[j-1]),  j >= 1
+// ------------------------------------------------------------------------------------------------
+struct GenResRows {
+    LevelDev L;
+    int w, nw, stride, stage, sub, j, pro;
+    size_t soff;
+    __device__ GenResRows(const LevelDev &L_, int first, int nw_, int stride_)
+        : L(L_), w(first), nw(nw_), stride(stride_), stage(-2), sub(0), j(0), pro(0), soff(0) {}
+    __device__ bool next(const double *&p) {
+        for (;;) {
+            if (w >= nw) return false;
+            if (stage == -2) {
+                const ItemPos ip = item_pos(L, w, 1);
+                j = ip.k;
+                soff = ip.soff;
+                pro = 0;
+                stage = -1;
+            }
+            const int c = __ldg(L.cpts + j);
+            switch (stage) {
+                case -1:
+                    if (pro < n_prologue(L)) {
+                        p = prologue_row(L, pro++, soff);
+                        return true;
+                    }
+                    stage = 0;
+                    break;
+                case 0:  // u[c-1]
+                    p = L.u + (size_t)(c - 1) * L.pitch + soff;
+                    stage = 1;
+                    sub = 0;
+                    return true;
+                case 1:  // dense rhs row of the fine step
+                    stage = 2;
+                    if (StepRows::next(L, c, sub, p, soff, false)) return true;
+                    break;
+                case 2:  // u[c]
+                    p = L.u + (size_t)c * L.pitch + soff;
+                    stage = 3;
+                    return true;
+                case 3:  // g[c]
+                    stage = 4;
+                    if (L.g) {
+                        p = L.g + (size_t)c * L.pitch + soff;
+                        return true;
+                    }
+                    break;
+                default:
+                    w += stride;
+                    stage = -2;
+            }
+        }
+    }
+};
+
+template <class Phi>
+__global__ void __launch_bounds__(Phi::T) k_residual_rows(const LevelDev L, double *__restrict__ out, const int nw,
+                                                          const int nin) {
+    using SH = typename Phi::SH;
+    constexpr int E = Phi::E;
+    Team<Phi::T> team(g_smem);
+    RowPipe<SH, GenResRows> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenResRows(L, blockIdx.x, nw, gridDim.x));
+    pipe.start(team);
+    typename Phi::C c;
+    Phi::load_consts(c, L.sconst, team.tid);
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(L, w, 1);
+        const int j = ip.k;
+        const int cp = __ldg(L.cpts + j);
+        typename Phi::Item it;
+        Phi::begin_item(it, L, ip.sys, pipe, team);
+        double x[E], y[E];
+        pipe.pop(x, team);
+        advance<Phi>(x, c, it, L, cp, pipe, team, false);  // Phi_f(u[c-1])
+        pipe.pop(y, team);                                 // u[c]
+        if (L.g) {
+            double gg[E];
+            pipe.pop(gg, team);
+#pragma unroll
+            for (int q = 0; q < E; ++q) x[q] = (gg[q] - y[q]) + x[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < E; ++q) x[q] = x[q] - y[q];
+        }
+        pipe.push(x, out + (size_t)j * L.pitch + ip.soff, team);
+    }
+    pipe.finish(team);
+}
+
+struct GenFasRhs {
+    LevelDev G;
+    const double *V, *RR;
+    int w, nw, stride, stage, sub, j, pro;
+    size_t soff;
+    __device__ GenFasRhs(const LevelDev &G_, const double *V_, const double *RR_, int first, int nw_, int stride_)
+        : G(G_), V(V_), RR(RR_), w(first), nw(nw_), stride(stride_), stage(-2), sub(0), j(0), pro(0), soff(0) {}
+    __device__ bool next(const double *&p) {
+        for (;;) {
+            if (w >= nw) return false;
+            if (stage == -2) {
+                const ItemPos ip = item_pos(G, w, 1);
+                j = ip.k;
+                soff = ip.soff;
+                pro = 0;
+                stage = -1;
+            }
+            switch (stage) {
+                case -1:
+                    if (pro < n_prologue(G)) {
+                        p = prologue_row(G, pro++, soff);
+                        return true;
+                    }
+                    stage = 0;
+                    break;
+                case 0:  // V[j-1]
+                    p = V + (size_t)(j - 1) * G.pitch + soff;
+                    stage = 1;
+                    sub = 0;
+                    return true;
+                case 1:  // dense rhs row of the coarse step
+                    stage = 2;
+                    if (StepRows::next(G, j, sub, p, soff, false)) return true;
+                    break;
+                case 2:  // RR[j]
+                    p = RR + (size_t)j * G.pitch + soff;
+                    stage = 3;
+                    return true;
+                case 3:  // V[j]
+                    p = V + (size_t)j * G.pitch + soff;
+                    stage = 4;
+                    return true;
+                default:
+                    w += stride;
+                    stage = -2;
+            }
+        }
+    }
+};
+
+template <class Phi>
+__global__ void __launch_bounds__(Phi::T) k_fas_rhs(const LevelDev G, const double *__restrict__ V,
+                                                    const double *__restrict__ RR, const int nw, const int nin) {
+    using SH = typename Phi::SH;
+    constexpr int E = Phi::E;
+    Team<Phi::T> team(g_smem);
+    RowPipe<SH, GenFasRhs> pipe(g_smem, nin, G.tile, Phi::row_n(G), GenFasRhs(G, V, RR, blockIdx.x, nw, gridDim.x));
+    pipe.start(team);
+    typename Phi::C c;
+    Phi::load_consts(c, G.sconst, team.tid);
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(G, w, 1);
+        const int j = ip.k;
+        typename Phi::Item it;
+        Phi::begin_item(it, G, ip.sys, pipe, team);
+        double x[E], y[E], z[E];
+        pipe.pop(x, team);
+        advance<Phi>(x, c, it, G, j, pipe, team, false);  // Phi_c(V[j-1])
+        pipe.pop(y, team);                                // R(fine residual)
+        pipe.pop(z, team);                                // V[j]
+#pragma unroll
+        for (int q = 0; q < E; ++q) x[q] = (y[q] + z[q]) - x[q];
+        pipe.push(x, G.g + (size_t)j * G.pitch + ip.soff, team);
+    }
+    pipe.finish(team);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Down-sweep of a cycle in one pass (mgrit.py:277-281 + 497-547 for cf_iter's last round, weight 1): C-relaxation,
 // the F-relaxation that follows it and the FAS restriction.  Work item j = 1 .. ncpts-1, a = cpts[j-1], c = cpts[j]:
 //     yc   = (g[c] +) Phi_f(u[c-1])                  C-relaxation of c (from the F-point as it is before this sweep)

@@ -24,6 +24,9 @@ struct SweepTable {
     int (*residual)(const LevelDev &, double *, cudaStream_t);
     int (*step)(const LevelDev &, int, const double *, double *, cudaStream_t);
     int (*down)(const LevelDev &, const LevelDev &, cudaStream_t);  // nullptr: not available for this application
+    // FAS restriction with a spatial grid transfer, split around the transfer (nullptr: not available)
+    int (*residual_rows)(const LevelDev &, double *, cudaStream_t);
+    int (*fas_rhs)(const LevelDev &, const double *, const double *, int, cudaStream_t);
 };
 
 }  // namespace mgb

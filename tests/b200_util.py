@@ -22,11 +22,20 @@ def b200_problem(case):
     return [apps[case['app']](t_interval=t, **C.level_app_kw(case, l)) for l, t in enumerate(grids)]
 
 
+def b200_transfer(case):
+    import pymgrit_b200 as P
+    if 'transfer' not in case:
+        return None
+    return [{'space': P.GridTransferHeat1D, 'copy': P.GridTransferCopy}[k]() for k in case['transfer']]
+
+
 def run_b200(name, **extra):
     import pymgrit_b200 as P
     case = C.CASES[name]
     kw = dict(case['solver'])
     kw.update(extra)
+    if 'transfer' in case:
+        kw['transfer'] = b200_transfer(case)
     solver = P.Mgrit(problem=b200_problem(case), logging_lvl=logging.WARNING, **kw)
     info = solver.solve()
     return solver, info

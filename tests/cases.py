@@ -187,6 +187,24 @@ CASES = {
                                                 init_cond=heat_init, rhs=heat_rhs_rank2)],
                                    t_interval=0.01 + np.linspace(0, 1, 49) ** 1.3 * 1.5, grids=_simple(2, 3),
                                    solver=dict(tol=1e-9, weight_c=0.9, nested_iteration=False)),
+    # examples/example_spatial_coarsening.py -> tests/mpi/results/spatial_coarsening: spatial coarsening by 2 on the
+    # first two level transitions (full weighting / linear interpolation), identity on the last
+    'heat1d_spatial_example': dict(app='heat1d',
+                                   app_kw=[dict(x_start=0, x_end=2, nx=17, a=1, rhs=heat_rhs, init_cond=heat_init),
+                                           dict(x_start=0, x_end=2, nx=9, a=1, rhs=heat_rhs, init_cond=heat_init),
+                                           dict(x_start=0, x_end=2, nx=5, a=1, rhs=heat_rhs, init_cond=heat_init),
+                                           dict(x_start=0, x_end=2, nx=5, a=1, rhs=heat_rhs, init_cond=heat_init)],
+                                   t=(0, 2, 129), grids=_simple(4, 2), transfer=['space', 'space', 'copy'],
+                                   solver=dict()),
+    # larger grids (several lanes / warps per system), F-cycles, FCF twice, trailing F-points, tighter tolerance
+    'heat1d_spatial_large': dict(app='heat1d',
+                                 app_kw=[dict(nx=1025, **HEAT), dict(nx=513, **HEAT), dict(nx=513, **HEAT)],
+                                 t=(0, 2, 98), grids=_simple(3, 3), transfer=['space', 'copy'],
+                                 solver=dict(tol=1e-6, cycle_type='F', cf_iter=2)),
+    'heat1d_spatial_nonested': dict(app='heat1d',
+                                    app_kw=[dict(nx=65, **HEAT), dict(nx=65, **HEAT), dict(nx=33, **HEAT)],
+                                    t=(0, 1, 65), grids=_simple(3, 4), transfer=['copy', 'space'],
+                                    solver=dict(tol=1e-7, nested_iteration=False, weight_c=1.1)),
     # local convergence criteria (mgrit.py:434-454) on one time rank
     'heat1d_small_local_res': dict(app='heat1d', app_kw=dict(nx=17, **HEAT), t=(0, 2, 65), grids=_simple(3, 2),
                                    solver=dict(tol=1e-9, conv_crit=2)),

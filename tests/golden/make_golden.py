@@ -45,6 +45,42 @@ def heat1d2pts(method, **kw):
 APPS['heat1d2pts'] = heat1d2pts
 
 
+from pymgrit.core.grid_transfer import GridTransfer             # noqa: E402
+from pymgrit.core.grid_transfer_copy import GridTransferCopy    # noqa: E402
+from pymgrit.heat.heat_1d import VectorHeat1D                   # noqa: E402
+
+
+class GridTransferHeat(GridTransfer):
+    """User-side transfer class as a user of the reference writes it for examples/example_spatial_coarsening.py: full
+    weighting down, linear interpolation up, on the interior points of Heat1D vectors."""
+
+    def restriction(self, u):
+        sol = u.get_values()
+        out = np.zeros((len(sol) - 1) // 2)
+        for i in range(len(out)):
+            out[i] = sol[2 * i] * 1 / 4 + sol[2 * i + 1] * 1 / 2 + sol[2 * i + 2] * 1 / 4
+        ret = VectorHeat1D(len(out))
+        ret.set_values(out)
+        return ret
+
+    def interpolation(self, u):
+        sol = u.get_values()
+        out = np.zeros(len(sol) * 2 + 1)
+        for i in range(len(sol)):
+            out[i * 2] += 1 / 2 * sol[i]
+            out[i * 2 + 1] += sol[i]
+            out[i * 2 + 2] += 1 / 2 * sol[i]
+        ret = VectorHeat1D(len(out))
+        ret.set_values(out)
+        return ret
+
+
+def build_reference_transfer(case):
+    if 'transfer' not in case:
+        return None
+    return [{'space': GridTransferHeat, 'copy': GridTransferCopy}[k]() for k in case['transfer']]
+
+
 def build_reference_problem(case):
     grids = C.case_time_grids(case)
     return [APPS[case['app']](t_interval=t, **C.level_app_kw(case, l)) for l, t in enumerate(grids)]
@@ -61,7 +97,7 @@ def run_case(name):
     case = C.CASES[name]
     problem = build_reference_problem(case)
     t0 = time.time()
-    solver = Mgrit(problem=problem, logging_lvl=30, **case['solver'])
+    solver = Mgrit(problem=problem, transfer=build_reference_transfer(case), logging_lvl=30, **case['solver'])
     info = solver.solve()
     wall = time.time() - t0
     u = [values_of(v) for v in solver.u[0]]

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.dirname(HERE), HERE]
 
 import cases as C                                    # noqa: E402
-from b200_util import b200_problem                   # noqa: E402
+from b200_util import b200_problem, b200_transfer    # noqa: E402
 from oracle_util import load_golden, assert_history_close, assert_solution_close   # noqa: E402
 
 
@@ -29,7 +29,8 @@ def main():
     failed = []
     for name in sys.argv[1:]:
         case = C.CASES[name]
-        solver = P.Mgrit(problem=b200_problem(case), logging_lvl=logging.WARNING, **case['solver'])
+        solver = P.Mgrit(problem=b200_problem(case), transfer=b200_transfer(case), logging_lvl=logging.WARNING,
+                         **case['solver'])
         info = solver.solve()
         lv = solver._lv[0]
         own = lv.values(idx=np.arange(1 if rank > 0 else 0, lv.npts))                       # drop the ghost row

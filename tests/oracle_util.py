@@ -23,9 +23,15 @@ def oracle_problem(case, solver=None):
     return out
 
 
+def oracle_transfer(case):
+    if 'transfer' not in case:
+        return None
+    return [{'space': O.Heat1DSpaceTransfer, 'copy': O.CopyTransfer}[k]() for k in case['transfer']]
+
+
 def run_oracle(name, solver=None):
     case = C.CASES[name]
-    mg = O.MgritOracle(oracle_problem(case, solver), **case['solver'])
+    mg = O.MgritOracle(oracle_problem(case, solver), transfer=oracle_transfer(case), **case['solver'])
     info = mg.solve()
     return mg, info
 

@@ -115,6 +115,28 @@ def test_heat1d_two_point_vector(P):
     np.testing.assert_array_equal(v2.get_values()[0], [1, 2, 3])
 
 
+def test_grid_transfer_heat1d_vectors(P):
+    """GridTransferHeat1D vector by vector against the arithmetic of examples/example_spatial_coarsening.py:33-79."""
+    tr = P.GridTransferHeat1D()
+    rng = np.random.default_rng(3)
+    sol = rng.standard_normal(15)
+    u = P.VectorHeat1D(15)
+    u.set_values(sol)
+    want = np.array([sol[2 * i] * 1 / 4 + sol[2 * i + 1] * 1 / 2 + sol[2 * i + 2] * 1 / 4 for i in range(7)])
+    r = tr.restriction(u)
+    assert isinstance(r, P.VectorHeat1D)
+    np.testing.assert_array_equal(r.get_values(), want)
+    back = np.zeros(15)
+    for i in range(7):
+        back[2 * i] += 1 / 2 * want[i]
+        back[2 * i + 1] += want[i]
+        back[2 * i + 2] += 1 / 2 * want[i]
+    np.testing.assert_array_equal(tr.interpolation(r).get_values(), back)
+    c = P.GridTransferCopy()
+    np.testing.assert_array_equal(c.restriction(u).get_values(), sol)
+    assert P.GridTransferHeat is P.GridTransferHeat1D
+
+
 def test_phi_step_fixtures(P):
     """Single Phi at BASELINE sizes against the unmodified reference (1e-10 relative)."""
     g = load_golden('phi_steps')

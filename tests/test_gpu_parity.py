@@ -41,6 +41,33 @@ def test_heat1d_two_point_bdf_against_reference_fixture(name):
     assert any(solver._fused_down) == (solver.weight_c == 1.0)
 
 
+def test_spatial_coarsening_matches_reference_result_file():
+    """examples/example_spatial_coarsening.py -> tests/mpi/results/spatial_coarsening (4 decimals there, tests/mpi/mpi.py:49)."""
+    _, info = run_b200('heat1d_spatial_example')
+    np.testing.assert_almost_equal(info['conv'], [0.033795341894154736, 0.0029793978719811257, 0.00032555028064712785,
+                                                  4.042946916072736e-05, 4.93158057838271e-06, 6.178527940638919e-07,
+                                                  7.708784717391436e-08], decimal=9)
+
+
+def test_python_grid_transfer_is_rejected():
+    """A transfer written in Python cannot run inside a sweep: the engine raises instead of falling back."""
+    import pymgrit_b200 as P
+
+    class Mine(P.GridTransfer):
+        def restriction(self, u):
+            return u.clone()
+
+        def interpolation(self, u):
+            return u.clone()
+
+    prob = P.simple_setup_problem(P.Heat1D(nx=17, t_start=0, t_stop=1, nt=9, **C.HEAT), level=2, coarsening=2)
+    with pytest.raises(Exception):
+        P.Mgrit(problem=prob, transfer=[Mine()])
+    with pytest.raises(Exception):      # sizes that do not nest
+        P.Mgrit(problem=[P.Heat1D(nx=17, t_start=0, t_stop=1, nt=9, **C.HEAT),
+                         P.Heat1D(nx=8, t_interval=np.linspace(0, 1, 5), **C.HEAT)], transfer=[P.GridTransferHeat1D()])
+
+
 @pytest.mark.parametrize('name', _cases(('dahlquist', 'brusselator')))
 def test_ode_against_reference_fixture(name):
     _check_against_golden(name)

@@ -89,6 +89,9 @@ REF_FILES = {
     'brusselator_example': [0.014222592121653527, 8.204212669361892e-05, 1.1265397600214108e-07,
                             3.357814854491385e-10],
     'heat2d_example': [5.372296482469411e-15],
+    'heat1d_spatial_example': [0.033795341894154736, 0.0029793978719811257, 0.00032555028064712785,
+                               4.042946916072736e-05, 4.93158057838271e-06, 6.178527940638919e-07,
+                               7.708784717391436e-08],
 }
 
 
