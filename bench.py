@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg5|cfg2]
 
 Workload (BASELINE.json configs[4], the one the metric's target is quoted on; fits one GPU):
-    heat_1d backward Euler, nx = 1025 (1023 dofs), nt = 2^20 + 1 on t in [0, 2], FCF-relaxation V-cycles,
-    coarsening 4, nested iteration, tol 1e-10; strong scaling over the time ranks (one process per GPU).
+    heat_1d backward Euler, nx = 1025 (1023 dofs), nt = 2^20 + 1 on t in [0, 2], FCF-relaxation V-cycles, 4 levels
+    (coarsening 16 x 16 x 8, chosen by the builder: BASELINE leaves it open), nested iteration, tol 1e-10; strong
+    scaling over the time ranks (one process per GPU).
 One "step" = one complete solve: setup (incl. nested iteration) + MGRIT iterations until conv < 1e-10.
 Prints ONE JSON line (rank 0).  `value` times the solve with every table already in HBM; `e2e` times the public API
 from host NumPy inputs (application objects, Mgrit(), solve(), result copied back to the host).
@@ -46,8 +47,10 @@ WORKLOADS = {
     'cfg5': (2 ** 20 + 1, (16, 16, 8)),
     'cfg2': (16385, (4, 4)),
 }
-CPU_SAMPLE = (2049, (16, 16))      # nt and coarsening of the bounded CPU sample on one core (same problem, same cycle)
-CPU_SAMPLE_MP = (8193, (16, 16))   # ... and on several cores (time-parallel workers)
+# Bounded CPU sample: the first nt_sample time points of the SAME problem (same dt = 2 / 2^20, same coarsening factors,
+# same cycle), i.e. a time window of the workload, so that the work per space-time DOF is the workload's.
+CPU_SAMPLE = (2049, (16, 16))          # one core: about 10 s
+CPU_SAMPLE_MP = (32769, (16, 16, 8))   # several cores (time-parallel workers): about 10 s on 16 cores
 HEAT_KW = dict(x_start=0, x_end=1, nx=1025, a=1, init_cond=init_cond, rhs=rhs, t_start=0, t_stop=2)
 SOLVER_KW = dict(cf_iter=1, cycle_type='V', nested_iteration=True, tol=1e-10)
 
@@ -76,32 +79,44 @@ def ncu_traffic(sweep, intervals):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled under load (B200_PROFILING.md).  The timed region of the default
+    run lasts tens of milliseconds, shorter than nvidia-smi's sampling period, so the sampler runs from the warm-up to
+    the end of the per-sweep timing (the GPU is busy throughout); samples that fall inside the timed region are
+    preferred when there are any, and `window` says which were used."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          '-lms', '20', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def mark_timed(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [r for ts, r in self.rows if self.t0 is not None and self.t0 <= ts <= self.t1]
+        window = 'timed region'
+        rows = inside
+        if not rows:
+            rows, window = [r for _, r in self.rows], 'warm-up + timed region + per-sweep timing (all under load)'
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -111,16 +126,19 @@ class ClockSampler:
             except (ValueError, IndexError):
                 pass
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'window': window}
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def hierarchy(make, nt, coarsening):
+def hierarchy(make, nt, coarsening, t_stop=None):
     """[fine, coarse, ...]: level l+1 lives on every coarsening[l]-th point of level l (t_interval = t[::m])."""
     kw = {k: v for k, v in HEAT_KW.items() if k not in ('t_start', 't_stop')}
-    levels = [make(nt=nt, **HEAT_KW)]
+    fine_kw = dict(HEAT_KW)
+    if t_stop is not None:
+        fine_kw['t_stop'] = t_stop
+    levels = [make(nt=nt, **fine_kw)]
     for m in coarsening:
         levels.append(make(t_interval=levels[-1].t[::m], **kw))
     return levels
@@ -144,8 +162,10 @@ def cpu_sample(cores=None, solver='spsolve'):
     from oracle import mgrit_oracle_mp as OM
     cores = cpu_cores() if cores is None else cores
     nt_sample, coarsening = CPU_SAMPLE_MP if cores >= 4 else CPU_SAMPLE
+    nt_full = WORKLOADS['cfg5'][0]
+    t_stop = HEAT_KW['t_stop'] * (nt_sample - 1) / (nt_full - 1)          # same dt as the workload
     t0 = time.time()
-    prob = hierarchy(lambda **kw: O.Heat1DOracle(solver=solver, **kw), nt_sample, coarsening)
+    prob = hierarchy(lambda **kw: O.Heat1DOracle(solver=solver, **kw), nt_sample, coarsening, t_stop=t_stop)
     if cores > 1:
         mg = OM.ParallelMgritOracle(prob, workers=cores, **SOLVER_KW)
     else:
@@ -155,9 +175,10 @@ def cpu_sample(cores=None, solver='spsolve'):
     if cores > 1:
         mg.close()
     its = len(info['conv'])
-    what = (f'{describe("sample", nt_sample, coarsening)} ({its} iterations): per-point Python loop + SciPy SuperLU per '
-            f'step as in the reference, time-parallel over {cores} worker process(es) like its mpi4py time ranks; '
-            f'DOF/s is linear in nt')
+    what = (f'the first {nt_sample} of the workload\'s {nt_full} time points (t in [0, {t_stop:.6g}], same dt, {len(coarsening) + 1}'
+            f'-level, coarsening {"x".join(str(m) for m in coarsening)}, FCF V-cycle, nested iteration, tol 1e-10; {its} '
+            f'iterations): per-point Python loop + SciPy SuperLU per step as in the reference, time-parallel over {cores} '
+            f'worker process(es) like its mpi4py time ranks; DOF/s is linear in nt')
     return 1023 * nt_sample / sec, sec, its, cores, what
 
 
@@ -227,22 +248,23 @@ def gpu_arm(args):
     # ---- device-resident timing: tables in HBM, time setup sweeps (nested iteration) + iterations ----
     solver = P.Mgrit(problem=make_problem(), logging_lvl=logging.WARNING, **SOLVER_KW)
     info = None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         solver.restart()
         info = solver.solve()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = solver.launches
+    wall0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         solver.restart()
         info = solver.solve()
     ev1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.mark_timed(wall0, time.perf_counter())
     ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     launches = (solver.launches - launches0)
     iters = len(info['conv'])
@@ -269,6 +291,7 @@ def gpu_arm(args):
 
     # ---- per-kernel roofline on level 0 (CUDA events around single launches on the solved state) ----
     kernels = solver.time_level0_sweeps(repeats=5)
+    clocks = sampler.stop() if rank == 0 else None
     hbm, which = peaks()
     dom = max([k for k in kernels if k['bound'] == 'hbm'], key=lambda k: k['share_ms'])
     roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
