@@ -197,20 +197,22 @@ class Mgrit:
         # F-point in every interval (on every time rank), team kernels
         import os
         self._xfer = [None if type(tr) is GridTransferCopy else tr for tr in transfer] + [None]
-        self._fused_down = []
+        flags = []
         for lvl in range(self.lvl_max - 1):
             cp = self._lv[lvl].cpts
-            ok = (weight_c == 1.0 and self._xfer[lvl] is None and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D,
-                                                           _lib.APP_HEAT1D_2PTS)
+            ok = (weight_c == 1.0 and self._xfer[lvl] is None
+                  and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D, _lib.APP_HEAT1D_2PTS)
                   and (cp is None or len(cp) < 2 or int(np.min(np.diff(cp))) >= 2)
                   and os.environ.get('MGB_FUSED_DOWN', '1') != '0')
-            self._fused_down.append(self._all_ranks(ok))
-        self._fused_down.append(False)
+            flags.append(ok)
         # the sequential solve on the coarsest level in sine space where the application offers it (Heat1D)
         self._spectral = {}
         last = self._lv[-1]
         maker = getattr(problem[-1], 'spectral_solver', None)
-        if maker is not None and self._all_ranks(last.npts >= getattr(problem[-1], 'SPECTRAL_MIN_POINTS', 1 << 30)):
+        flags.append(maker is not None and last.npts >= getattr(problem[-1], 'SPECTRAL_MIN_POINTS', 1 << 30))
+        flags = self.comm_time.all_true(flags)          # every rank must take the same path: one small all-reduce
+        self._fused_down = flags[:-1] + [False]
+        if flags[-1]:
             sp = maker(last) if last.npts > 0 else None
             if sp is not None:
                 self._spectral[self.lvl_max - 1] = sp
@@ -269,7 +271,7 @@ class Mgrit:
 
     def _all_ranks(self, flag: bool) -> bool:
         """True if `flag` holds on every time rank (all ranks must take the same path through a chain exchange)."""
-        return all(self.comm_time.allgather(bool(flag)))
+        return self.comm_time.all_true([flag])[0]
 
     def log_info(self, message: str) -> None:
         """Only the last time rank logs (mgrit.py:247-259)."""

@@ -217,7 +217,13 @@ class Partition:
             bounds = np.array([n0 - 1])
         else:
             # slab ends must be points of the coarsest grid: spread its intervals over the ranks
-            coarse_idx = np.flatnonzero(np.isin(t0, global_t[-1]))
+            # (level-0 indices of the coarsest points by composing the C-point masks: level l+1 is the C-points of
+            # level l in order, so no search or sort over the 2^20 fine points is needed)
+            coarse_idx = np.flatnonzero(masks[0]) if L > 1 else np.arange(n0)
+            for l in range(1, L - 1):
+                coarse_idx = coarse_idx[masks[l]]
+            if len(coarse_idx) != len(global_t[-1]) or not np.array_equal(t0[coarse_idx], global_t[-1]):
+                coarse_idx = np.flatnonzero(np.isin(t0, global_t[-1]))      # grids with repeated or unsorted points
             nc = len(coarse_idx)
             if nc - 1 < size:
                 raise Exception(f'{size} time ranks need at least {size} intervals on the coarsest grid '

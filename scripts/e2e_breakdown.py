@@ -14,11 +14,22 @@ import torch
 import bench
 import pymgrit_b200 as P
 
+import torch.distributed as dist
+world = int(os.environ.get('WORLD_SIZE', '1'))
+rank = int(os.environ.get('RANK', '0'))
+if world > 1:                       # python -m torch.distributed.run --nproc-per-node N scripts/e2e_breakdown.py
+    torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+    dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+    if rank != 0:
+        sys.stdout = open(os.devnull, 'w')
 wl = sys.argv[1] if len(sys.argv) > 1 else 'cfg5'
 nt, co = bench.WORKLOADS[wl]
 
 
 def run():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t = [time.perf_counter()]
     prob = bench.hierarchy(P.Heat1D, nt, co)
     t.append(time.perf_counter())
