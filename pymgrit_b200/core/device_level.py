@@ -34,6 +34,12 @@ def pinned_array(shape):
 
 
 def team_shape(kind, n):
+    import os
+    ov = os.environ.get('MGB_TEAM_SHAPE')          # "T,E": experiment with another compiled shape (scripts only)
+    if ov and kind == _lib.APP_HEAT1D:
+        t_, e_ = (int(x) for x in ov.split(','))
+        if t_ * e_ >= n:
+            return t_, e_
     t, e = C.c_int32(0), C.c_int32(0)
     _lib.check(_lib.lib().mgb_team_shape(kind, n, C.byref(t), C.byref(e)), 'team_shape')
     return t.value, e.value
