@@ -59,7 +59,10 @@ def step_const_table(kind, values, n, team_threads, chunk):
 class DeviceLevel:
     """Arrays of one level on the current CUDA device + the matching struct mgb_level."""
 
-    def __init__(self, app, t, cpts=None, with_g=False, u_init=None):
+    def __init__(self, app, t, cpts=None, with_g=False, u_init=None, defer_tables=False):
+        """defer_tables: allocate the arrays now, build and upload the Phi tables when finish_tables() is called (the
+        solver does that for level 0 after it has queued the coarse-level work of nested iteration, so that the host
+        evaluates the long level-0 tables while the device is busy)."""
         torch = _torch()
         dev = torch.device('cuda', torch.cuda.current_device())
         self.app = app
@@ -72,9 +75,21 @@ class DeviceLevel:
         # the (asynchronous) zero fill of the level arrays runs on the device while the host builds the tables
         self.u = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if u_init is None else u_init
         self.g = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if with_g else None
-        tab = app.level_tables(self.t, self.team_threads, self.chunk)
+        self.cpts = None if cpts is None else np.asarray(cpts, dtype=np.int32)
         self._keep = []                                   # tensors referenced by the struct
         self.h2d_bytes = 0
+        self.nsys = 1
+        self.c = None
+        if not defer_tables:
+            self.finish_tables()
+
+    def finish_tables(self):
+        if self.c is not None:
+            return
+        torch = _torch()
+        app, dev = self.app, self.u.device
+        tiny = app.kind in (_lib.APP_DAHLQUIST, _lib.APP_BRUSSELATOR)
+        tab = app.level_tables(self.t, self.team_threads, self.chunk)
 
         def up(a, dtype):
             if a is None:
@@ -92,9 +107,8 @@ class DeviceLevel:
             self._keep.append(ten)
             return ten
 
-        self.cpts = None if cpts is None else np.asarray(cpts, dtype=np.int32)
         self.cpts_dev = up(self.cpts, np.int32)
-        self.t_dev = up(self.t, np.float64)
+        self.t_dev = up(self.t, np.float64) if tiny else None     # only the ODE kernels read the time grid
         sconst = up(tab.get('sconst'), np.float64)
         dtidx = up(tab.get('dtidx'), np.int32)
         # tables an application family shares between its levels are handed over as device tensors
@@ -150,6 +164,15 @@ class DeviceLevel:
     def ref(self):
         return C.byref(self.c)
 
+    def ensure_t_dev(self):
+        """Upload the time grid for a kernel family that reads it (the sine-space solve; the ODE kernels always have it)."""
+        if self.t_dev is None:
+            torch = _torch()
+            host = np.ascontiguousarray(self.t, dtype=np.float64)
+            self.t_dev = torch.as_tensor(host).to(self.u.device)
+            self.h2d_bytes += host.nbytes
+            self.c.t_dev = self.t_dev.data_ptr()
+
     # -- values <-> rows (identity for every application except Heat2D, whose rows are in sine space) ----------
     def get_vector(self, arr, i):
         """Time point i of a level array as a Vector of the application (a view where the layout allows it)."""
@@ -172,12 +195,14 @@ class DeviceLevel:
         return out
 
 
-def dt_classes(t):
-    """dt_i = t[i] - t[i-1] grouped by exact value: (distinct values, index per point or None)."""
+def dt_classes(t, dt=None):
+    """dt_i = t[i] - t[i-1] grouped by exact value: (distinct values, index per point or None).  dt: t[1:] - t[:-1] if the
+    caller has it already."""
     t = np.asarray(t, dtype=float)
     if len(t) < 2:
         return np.array([1.0]), None
-    dt = t[1:] - t[:-1]
+    if dt is None:
+        dt = t[1:] - t[:-1]
     if dt[0] == dt[-1] and dt[0] == dt[len(dt) // 2] and dt.min() == dt.max():      # uniform grid: one pass each
         return dt[:1].copy(), None
     uniq, inv = np.unique(dt, return_inverse=True)

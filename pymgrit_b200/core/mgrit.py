@@ -192,7 +192,9 @@ class Mgrit:
         self._lv = []
         for lvl in range(self.lvl_max):
             cp = part.sweep_cpts[lvl] if lvl < self.lvl_max - 1 else None
-            self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0))
+            # level 0's tables (the long ones) are built after the coarse part of nested iteration has been queued
+            defer = lvl == 0 and self.lvl_max > 1 and bool(nested_iteration) and not random_init_guess
+            self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0, defer_tables=defer))
         # levels whose down-sweep runs as one fused launch (mgb_down_sweep): unweighted C-relaxation, at least one
         # F-point in every interval (on every time rank), team kernels
         import os
@@ -232,15 +234,15 @@ class Mgrit:
                 self._rres[lvl] = torch.zeros((ncp, fine.pitch), dtype=torch.float64, device=fine.u.device)
                 self._rresc[lvl] = torch.zeros((ncp, coarse.pitch), dtype=torch.float64, device=fine.u.device)
         self._init_levels()
+        if nested_iteration:
+            self.nested_iteration()
+        self._lv[0].finish_tables()
         dev = self._lv[0].u.device
         ncp0 = len(self._lv[0].cpts) if self._lv[0].cpts is not None else 1
         nsys0 = self._lv[0].nsys
         self._sq = torch.zeros(max(ncp0, 1) * (1 + nsys0 if nsys0 > 1 else 1), dtype=torch.float64, device=dev)
         self._norm_out = torch.zeros(1, dtype=torch.float64, device=dev)
         self._norm_host = torch.zeros(1, dtype=torch.float64).pin_memory()
-
-        if nested_iteration:
-            self.nested_iteration()
 
         if self._jump_crit:
             self.save_values_last_iter = self._lv[0].u.clone()
@@ -469,6 +471,8 @@ class Mgrit:
         """Coarsest solve, then interpolate upwards with a V-cycle per level (mgrit.py:551-566)."""
         self.forward_solve(self.lvl_max - 1)
         for lvl in range(self.lvl_max - 2, -1, -1):
+            if lvl == 0:
+                self._lv[0].finish_tables()      # host work of the setup, overlapped with the sweeps queued above
             if self._xfer[lvl] is not None:
                 fine, coarse = self._lv[lvl], self._lv[lvl + 1]
                 self._xfer[lvl].interpolate_rows(len(fine.cpts), 1, coarse.u, None, fine.u, fine.cpts_dev, False,

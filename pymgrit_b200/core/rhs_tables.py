@@ -176,7 +176,7 @@ class RhsSplit:
             work(0, nt)
             return out
         pool, nthr = _pool()
-        edges = np.linspace(0, nt, 2 * nthr + 1).astype(int)
+        edges = np.linspace(0, nt, nthr + 1).astype(int)        # one chunk per thread: fewest GIL hand-overs
         list(pool.map(lambda ab: work(*ab), zip(edges[:-1], edges[1:])))
         return out
 

@@ -68,13 +68,15 @@ class Heat1D(DeviceApplication):
 
     def level_tables(self, t, team_threads, chunk):
         fac = self.a / self.dx ** 2                                   # heat_1d.py:185
-        dts, dtidx = dl.dt_classes(t)
+        t = np.asarray(t, dtype=float)
+        dt_full = np.empty(len(t))
+        dt_full[0] = 0.0
+        np.subtract(t[1:], t[:-1], out=dt_full[1:])
+        dts, dtidx = dl.dt_classes(t, dt_full[1:])
         tab = dict(ndt=len(dts), dtidx=dtidx,
                    sconst=dl.step_const_table(self.kind, dts * fac, self.nx, team_threads, chunk))
         tab['cw'] = tab['sconst'].shape[1]
         split = self._rhs_split
-        dt_full = np.zeros(len(t))
-        dt_full[1:] = np.diff(t)
         if split.kind == 'separable':
             tab['nrhs'] = split.basis.shape[0]
             tab['rhs_x'] = dl.rhs_x_layout(split.basis, self.nx, team_threads, chunk)
@@ -107,6 +109,7 @@ class SpectralSolve:
         n, pitch = app.nx, level.pitch
         self.n, self.pitch, self.level = n, pitch, level
         self.h2d_bytes = 0
+        level.ensure_t_dev()                     # the scalar recurrences read dt_i = t[i] - t[i-1]
         self.smat = torch.empty((n, n), dtype=torch.float64, device=dev)
         _lib.check(_lib.lib().mgb_sine_matrix(n, self.smat.data_ptr(), n, _lib.current_stream_ptr()), 'sine_matrix')
         k = np.arange(1, n + 1).astype(np.longdouble)
