@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 5
+#define MGB_ABI_VERSION 6
 
 /* application kinds (which Phi) */
 #define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
@@ -254,6 +254,12 @@ int mgb_sine_matrix(int32_t n, double *s_dev, int32_t ld, void *stream);
  * not NULL, row 0 of a is read from there (the level's u[0] next to its g rows). */
 int mgb_rows_gemm(int32_t m, int32_t n, int32_t k, const double *a_dev, int32_t lda, const double *a_row0_dev,
                   const double *b_dev, int32_t ldb, double *c_dev, int32_t ldc, void *stream);
+/* The same product c = a S (k = n) as a fast sine transform, for n + 1 a power of two: one CTA per row, radix-2 FFT of
+ * the odd extension in shared memory, O(n log n) per row.  tw_dev: n + 1 complex doubles filled once by
+ * mgb_dst_twiddles. */
+int mgb_dst_twiddles(int32_t n, double *tw_dev, void *stream);
+int mgb_rows_dst(int32_t m, int32_t n, const double *a_dev, int32_t lda, const double *a_row0_dev, const double *tw_dev,
+                 double *c_dev, int32_t ldc, void *stream);
 /* The n scalar recurrences, in place on work_dev [npts][pitch].  lam_dev [n] = eigenvalues of the spatial operator
  * (a/dx^2) tridiag(-1, 2, -1); rxhat_dev [nrhs][pitch] = the spatial right-hand-side factors times S (rhs_t_dev of the
  * level supplies the time factors).  Needs a separable right-hand side (rhs_dense_dev == NULL), nrhs <= 4. */

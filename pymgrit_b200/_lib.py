@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libmgrit_b200.so')
 
 APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D, APP_HEAT1D_2PTS = 1, 2, 3, 4, 5, 6
 TNORM_ONE, TNORM_TWO, TNORM_INF = 1, 2, 3
-ABI_VERSION = 5
+ABI_VERSION = 6
 F_RELAX_LAST_ONLY = 1
 DAHLQUIST_METHODS = {'BE': 0, 'FE': 1, 'TR': 2, 'MR': 3}
 
@@ -72,6 +72,9 @@ SYMBOLS = {
     'mgb_sine_matrix': (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_rows_gemm': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.c_void_p]),
+    'mgb_dst_twiddles': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p]),
+    'mgb_rows_dst': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                               C.c_void_p]),
     'mgb_heat1d_spectral_recur': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_heat1d_spectral_fixup': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_peer_put_row': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),

@@ -117,6 +117,61 @@ __global__ void __launch_bounds__(256) k_rows_gemm(int M, int N, int K, const do
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same product  c[r] = a[r] S  as a fast sine transform when n + 1 = N is a power of two (nx = 2^k + 1, the usual
+// grids): S is the DST-I, i.e. the imaginary part of the length-2N DFT of the odd extension
+//     z = [0, x_0 .. x_{n-1}, 0, -x_{n-1} .. -x_0],   (x S)_j = -sqrt(2/N) Im(Z_{j+1}) / 2.
+// One CTA per row: the 2N complex points live in shared memory, log2(2N) radix-2 decimation-in-frequency stages
+// (natural order in, bit-reversed out), twiddles exp(-i pi t / N) from a table made once with sincospi (exact argument
+// reduction).  O(n log n) instead of O(n^2) per row: 1025 rows of n = 1023 take 0.115 instead of 2.1 GFLOP.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_dst_twiddles(int N, double2 *__restrict__ w) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    double sn, cs;
+    sincospi(-(double)t / (double)N, &sn, &cs);  // exp(-2 pi i t / (2N))
+    w[t] = make_double2(cs, sn);
+}
+
+__global__ void __launch_bounds__(256) k_rows_dst(const int nrows, const int n, const int log2n2,
+                                                  const double *__restrict__ A, const int lda,
+                                                  const double *__restrict__ a_row0, const double2 *__restrict__ tw,
+                                                  double *__restrict__ Cm, const int ldc) {
+    extern __shared__ double2 z[];  // 2N complex
+    const int N = n + 1, N2 = 2 * N;
+    const double scale = -0.5 * sqrt(2.0 / N);
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+        const double *x = (r == 0 && a_row0 != nullptr) ? a_row0 : A + (long)r * lda;
+        for (int k = threadIdx.x; k < N; k += blockDim.x) {
+            const double v = (k == 0) ? 0.0 : x[k - 1];
+            z[k] = make_double2(v, 0.0);
+            z[(N2 - k) & (N2 - 1)] = make_double2(k == 0 ? 0.0 : -v, 0.0);
+        }
+        if (threadIdx.x == 0) z[N] = make_double2(0.0, 0.0);
+        __syncthreads();
+        for (int s = log2n2 - 1; s >= 0; --s) {
+            const int half = 1 << s;
+            const int tstride = N >> s;  // twiddle index step: W_{2 half}^pos = W_{2N}^(pos N / half)
+            for (int b = threadIdx.x; b < N; b += blockDim.x) {
+                const int pos = b & (half - 1);
+                const int i = ((b >> s) << (s + 1)) + pos, j = i + half;
+                const double2 p = z[i], q = z[j];
+                const double2 w = tw[pos * tstride];
+                const double dr = p.x - q.x, di = p.y - q.y;
+                z[i] = make_double2(p.x + q.x, p.y + q.y);
+                z[j] = make_double2(fma(dr, w.x, -di * w.y), fma(dr, w.y, di * w.x));
+            }
+            __syncthreads();
+        }
+        double *out = Cm + (long)r * ldc;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const unsigned rev = __brev((unsigned)(j + 1)) >> (32 - log2n2);
+            out[j] = scale * z[rev].y;
+        }
+        __syncthreads();
+    }
+}
+
 // In-place scalar recurrences over the rows of W (sine space), one thread per mode k:
 //   W[i][k] = (W[i-1][k] + sum_q rhs_t[i][q] rxh[q][k]) / (1 + (t[i] - t[i-1]) lam[k]) + W[i][k],   i = 1 .. npts-1.
 // Rows are consumed in batches of UN: the next batch's loads are issued (and nothing waits for them) before this batch's
@@ -263,6 +318,39 @@ int mgb_rows_gemm(int32_t m, int32_t n, int32_t k, const double *a_dev, int32_t 
     else
         k_rows_gemm<16><<<dim3(nb, (m + 15) / 16), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc);
     return cuda_fail(cudaGetLastError(), "rows_gemm");
+}
+
+int mgb_dst_twiddles(int32_t n, double *tw_dev, void *stream) {
+    const int N = n + 1;
+    if (n < 1 || (N & (N - 1)) != 0 || tw_dev == nullptr) return heat2d_fail("dst_twiddles: n + 1 must be a power of two");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    k_dst_twiddles<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, (double2 *)tw_dev);
+    return cuda_fail(cudaGetLastError(), "dst_twiddles");
+}
+
+int mgb_rows_dst(int32_t m, int32_t n, const double *a_dev, int32_t lda, const double *a_row0_dev, const double *tw_dev,
+                 double *c_dev, int32_t ldc, void *stream) {
+    const int N = n + 1;
+    if (m < 0 || n < 1 || (N & (N - 1)) != 0 || a_dev == nullptr || tw_dev == nullptr || c_dev == nullptr || lda < n ||
+        ldc < n)
+        return heat2d_fail("rows_dst: bad argument (n + 1 must be a power of two)");
+    const DeviceInfo *di = device_info();
+    if (di == nullptr) return MGB_ECUDA;
+    if (m == 0) return MGB_OK;
+    const size_t smem = (size_t)2 * N * sizeof(double2);
+    if ((int)smem > di->max_smem_optin) return heat2d_fail("rows_dst: row too long for shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_rows_dst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        configured = smem;
+    }
+    int log2n2 = 0;
+    while ((1 << log2n2) < 2 * N) ++log2n2;
+    const int grid = m < 8 * di->sms ? m : 8 * di->sms;
+    k_rows_dst<<<grid, 256, smem, (cudaStream_t)stream>>>(m, n, log2n2, a_dev, lda, a_row0_dev, (const double2 *)tw_dev,
+                                                          c_dev, ldc);
+    return cuda_fail(cudaGetLastError(), "rows_dst");
 }
 
 int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const double *rxhat_dev, double *work_dev,

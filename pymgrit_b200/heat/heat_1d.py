@@ -110,8 +110,16 @@ class SpectralSolve:
         self.n, self.pitch, self.level = n, pitch, level
         self.h2d_bytes = 0
         level.ensure_t_dev()                     # the scalar recurrences read dt_i = t[i] - t[i-1]
-        self.smat = torch.empty((n, n), dtype=torch.float64, device=dev)
-        _lib.check(_lib.lib().mgb_sine_matrix(n, self.smat.data_ptr(), n, _lib.current_stream_ptr()), 'sine_matrix')
+        import os
+        # n + 1 a power of two (nx = 2^k + 1): fast sine transform, one CTA per row; otherwise the product with S
+        self.fast = ((n + 1) & n) == 0 and 32 * (n + 1) <= 200 * 1024 and os.environ.get('MGB_SPECTRAL_FFT', '1') != '0'
+        if self.fast:
+            self.smat = None
+            self.twiddles = torch.empty((n + 1, 2), dtype=torch.float64, device=dev)
+            _lib.check(_lib.lib().mgb_dst_twiddles(n, self.twiddles.data_ptr(), _lib.current_stream_ptr()), 'dst_twiddles')
+        else:
+            self.smat = torch.empty((n, n), dtype=torch.float64, device=dev)
+            _lib.check(_lib.lib().mgb_sine_matrix(n, self.smat.data_ptr(), n, _lib.current_stream_ptr()), 'sine_matrix')
         k = np.arange(1, n + 1).astype(np.longdouble)
         pi = np.longdouble('3.14159265358979323846264338327950288')
         fac = np.longdouble(app.a) / np.longdouble(app.dx) ** 2                       # heat_1d.py:185
@@ -131,6 +139,11 @@ class SpectralSolve:
 
     def _gemm(self, src, dst, rows, row0=None):
         """dst[:rows, :n] = src[:rows, :n] S (row 0 of src taken from row0 if given)."""
+        if self.fast:
+            _lib.check(_lib.lib().mgb_rows_dst(rows, self.n, src.data_ptr(), self.pitch,
+                                               None if row0 is None else row0.data_ptr(), self.twiddles.data_ptr(),
+                                               dst.data_ptr(), self.pitch, _lib.current_stream_ptr()), 'rows_dst')
+            return
         _lib.check(_lib.lib().mgb_rows_gemm(rows, self.n, self.n, src.data_ptr(), self.pitch,
                                             None if row0 is None else row0.data_ptr(), self.smat.data_ptr(), self.n,
                                             dst.data_ptr(), self.pitch, _lib.current_stream_ptr()), 'rows_gemm')

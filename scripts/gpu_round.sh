@@ -14,7 +14,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/${tag}_ncu_bench.log 2>&1
 echo "ncu launches rc=$?"
 # second pass of scripts/profile_sweeps.py: f_relax, f_relax(last), c_relax, fas_residual, down_sweep, correct+F, residual
-COARSENING=16 LEVELS=3 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_chain|k_c_relax|k_fas_residual|k_down|k_correct|k_residual" -s 7 -c 7 \
+COARSENING=64 LEVELS=3 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_chain|k_c_relax|k_fas_residual|k_down|k_correct|k_residual" -s 7 -c 7 \
     -o gpurun_out/${tag}_sweeps -f python scripts/profile_sweeps.py > gpurun_out/${tag}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 python scripts/solve_timeline.py cfg5 > gpurun_out/${tag}_timeline.txt 2>&1

@@ -247,7 +247,7 @@ def test_solver_state_is_user_visible(P):
     assert np.max(np.abs(solver.u[0][5].get_values() - v.get_values())) <= 1e-13
 
 
-@pytest.mark.parametrize('variant', ['uniform', 'nonuniform_t', 'zero_rhs', 'rank2_rhs'])
+@pytest.mark.parametrize('variant', ['uniform', 'nonuniform_t', 'zero_rhs', 'rank2_rhs', 'nx1001_product'])
 def test_spectral_coarse_solve_matches_phi_chain(P, variant):
     """The coarsest-level solve in sine space (csrc/spectral.cu) against the chain of tridiagonal Phi applications it
     replaces (mgrit.py:459-486), on the same u[0] and FAS right-hand side g: 1e-12 relative."""
@@ -258,6 +258,8 @@ def test_spectral_coarse_solve_matches_phi_chain(P, variant):
         kw.pop('rhs')
     if variant == 'rank2_rhs':
         kw['rhs'] = C.heat_rhs_rank2
+    if variant == 'nx1001_product':          # n + 1 not a power of two: the product with the sine matrix, no FFT
+        kw['nx'] = 1001
     t = np.linspace(0, 2, 513)
     if variant == 'nonuniform_t':
         t = 2 * np.linspace(0, 1, 513) ** 1.3
@@ -265,6 +267,7 @@ def test_spectral_coarse_solve_matches_phi_chain(P, variant):
     coarse = P.Heat1D(t_interval=t[::2], **kw)
     solver = P.Mgrit(problem=[fine, coarse], nested_iteration=False, logging_lvl=logging.WARNING)
     assert 1 in solver._spectral
+    assert solver._spectral[1].fast == (variant != 'nx1001_product')
     lv = solver._lv[1]
     gen = torch.Generator(device='cuda').manual_seed(7)
     lv.g[:, :lv.n] = torch.randn((lv.npts, lv.n), generator=gen, device='cuda', dtype=torch.float64) * 1e-2
