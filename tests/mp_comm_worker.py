@@ -56,6 +56,12 @@ def worker(rank, size, port, out_dir):
     part_sum = torch.tensor([float(rank + 1)], dtype=torch.float64)
     assert comm.reduce_norm(part_sum.clone(), 2).item() == size * (size + 1) / 2
     assert comm.reduce_norm(part_sum.clone(), 3).item() == size
+    # path flags: element-wise AND over the ranks in one all-reduce
+    assert comm.all_true([True, rank == 0, False, rank < size]) == [True, False, False, True]
+    assert comm.all_true([True]) == [True]
+    # no CUDA tensors over gloo: the peer-memory mailbox is not set up, NCCL/gloo send-recv stays (checked above)
+    comm.setup_peer_exchange(solver)
+    assert comm.mailbox is None
     gathered = comm.allgather(part.window)
     np.save(os.path.join(out_dir, f'windows_{rank}.npy'), np.array(gathered))
     comm.barrier()
