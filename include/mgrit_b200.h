@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 6
+#define MGB_ABI_VERSION 7
 
 /* application kinds (which Phi) */
 #define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
@@ -201,6 +201,12 @@ int mgb_heat1d_interp_rows(int32_t nrows, int32_t first, const double *a_dev, co
 
 /* Sequential solve on the coarsest level, mgrit.py:459-486: u[i] = (g[i] +) Phi(u[i-1]), i = 1..npts-1. */
 int mgb_forward_solve(const mgb_level *lvl, void *stream);
+
+/* AT-MGRIT, core/at_mgrit.py:75-86 (one time rank): instead of the sequential solve, every point p >= 1 of the coarsest
+ * level is the end of its own local coarse grid of at most k points started from the previous iterate,
+ *   x = old[max(0, p-k+1)];  for i = max(1, p-k+2) .. p:  x = (g[i] +) Phi(x);   u[p] = x,
+ * all points in one launch.  old_dev: a copy of u made before the call ([npts][pitch]). */
+int mgb_local_coarse_solve(const mgb_level *lvl, const double *old_dev, int32_t k, void *stream);
 
 /* Space-time residual at the C-points of level 0, mgrit.py:387-413: out_sq_dev[j] = ||Phi(u[c_j-1]) -
  * u[c_j]||_2^2 for j >= 1 (out_sq_dev[0] = 0).  out_sq_dev holds ncpts doubles, or ncpts * (1 + nsys) when the

@@ -532,6 +532,28 @@ class MgritOracle:
                 'time_solve': time.time() - t0}
 
 
+class AtMgritOracle(MgritOracle):
+    """core/at_mgrit.py:16-88 on one time rank: the coarsest level is not solved sequentially; every coarsest point is the
+    end of its own local coarse grid of at most k points, started from the previous iterate (at_mgrit.py:75-86)."""
+
+    def __init__(self, problem, k, **kw):
+        self.k = k
+        if kw.get('conv_crit', 0) not in (0, 1):
+            raise Exception('Local convergence criteria are not implemented for AT-MGRIT. Please select a global criterion.')
+        super().__init__(problem, **kw)
+
+    def forward_solve(self, l):                          # at_mgrit.py:37-88 (comm_time_size == 1 branch)
+        if self.L == 1:
+            return
+        u, g = self.u[l], self.g[l]
+        old = u.copy()
+        for point in range(len(u)):
+            tmp = old[max(0, point - self.k + 1)]
+            for i in range(max(1, point - self.k + 2), point + 1):
+                tmp = g[i] + self.phi(l, tmp, i)
+            u[point] = tmp
+
+
 def time_stepping(problem: OracleProblem) -> np.ndarray:
     """Sequential time stepping u_i = Phi(u_{i-1}) (the 1-level case, tests/core/test_mgrit.py:72-84)."""
     u = np.zeros((len(problem.t),) + np.shape(problem.u0))

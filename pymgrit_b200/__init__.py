@@ -11,6 +11,7 @@ from pymgrit_b200.core.grid_transfer import GridTransfer, DeviceGridTransfer
 from pymgrit_b200.core.grid_transfer_copy import GridTransferCopy
 from pymgrit_b200.core.simple_setup_problem import simple_setup_problem
 from pymgrit_b200.core.mgrit import Mgrit
+from pymgrit_b200.core.at_mgrit import AtMgrit
 from pymgrit_b200.heat.heat_1d import Heat1D, VectorHeat1D
 from pymgrit_b200.heat.heat_2d import Heat2D, VectorHeat2D
 from pymgrit_b200.heat.grid_transfer_heat_1d import GridTransferHeat1D, GridTransferHeat

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libmgrit_b200.so')
 
 APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D, APP_HEAT1D_2PTS = 1, 2, 3, 4, 5, 6
 TNORM_ONE, TNORM_TWO, TNORM_INF = 1, 2, 3
-ABI_VERSION = 6
+ABI_VERSION = 7
 F_RELAX_LAST_ONLY = 1
 DAHLQUIST_METHODS = {'BE': 0, 'FE': 1, 'TR': 2, 'MR': 3}
 
@@ -53,6 +53,7 @@ SYMBOLS = {
     'mgb_down_sweep': (C.c_int, [_LP, _LP, C.c_void_p]),
     'mgb_error_correction': (C.c_int, [_LP, _LP, C.c_int32, C.c_void_p]),
     'mgb_forward_solve': (C.c_int, [_LP, C.c_void_p]),
+    'mgb_local_coarse_solve': (C.c_int, [_LP, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_residual_norms': (C.c_int, [_LP, C.c_void_p, C.c_void_p]),
     'mgb_jump_norms': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_residual_rows': (C.c_int, [_LP, C.c_void_p, C.c_void_p]),

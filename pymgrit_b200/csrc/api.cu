@@ -429,6 +429,13 @@ int mgb_forward_solve(const mgb_level *lvl, void *stream) {
     return tab->forward_solve(L, st);
 }
 
+int mgb_local_coarse_solve(const mgb_level *lvl, const double *old_dev, int32_t k, void *stream) {
+    MGB_PROLOGUE(lvl)
+    if (old_dev == nullptr || k < 1 || old_dev == L.u) return fail(MGB_EINVAL, "local_coarse_solve: needs k >= 1 and a copy of u%s");
+    if (tab->window == nullptr) return fail(MGB_ENOSHAPE, "no local coarse-grid solve for this application%s");
+    return tab->window(L, old_dev, k, st);
+}
+
 int mgb_residual_norms(const mgb_level *lvl, double *out_sq_dev, void *stream) {
     MGB_PROLOGUE(lvl)
     if (L.cpts == nullptr || out_sq_dev == nullptr) return fail(MGB_EINVAL, "residual_norms needs C-points and an output%s");

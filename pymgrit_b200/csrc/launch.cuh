@@ -137,9 +137,22 @@ struct Launch {
         return cuda_fail(cudaGetLastError(), "fas_coarse_rhs");
     }
 
+    // u[p] = end of the chain of at most k-1 steps from old[max(0, p-k+1)], p = 1 .. npts-1
+    static int window(const LevelDev &L0, const double *old, int k, cudaStream_t st) {
+        LevelDev L = L0;
+        L.cpts = nullptr;
+        L.ncpts = 0;
+        if (L.npts < 2) return 0;
+        const int nin = 2 + rows_extra(L), nw = (L.npts - 1) * nsys(L);
+        int grid;
+        if (int rc = grid_for(k_window<Phi>, nw, nin, &grid)) return rc;
+        k_window<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, old, k, nw, nin);
+        return cuda_fail(cudaGetLastError(), "local_coarse_solve");
+    }
+
     static const SweepTable *table() {
         static const SweepTable t = {Phi::T,   Phi::E, &f_relax, &forward_solve,  &c_relax, &fas_residual, &correct,
-                                     &residual, &step,  &down,    &residual_rows, &fas_rhs};
+                                     &residual, &step,  &down,    &residual_rows, &fas_rhs,  &window};
         return &t;
     }
 };

@@ -184,6 +184,78 @@ __global__ void __launch_bounds__(Phi::T) k_chain(const LevelDev L, const int nw
 }
 
 // ------------------------------------------------------------------------------------------------
+// AT-MGRIT, local coarse grids on the coarsest level (core/at_mgrit.py:75-86, one time rank): every point p >= 1 is the
+// end of its own chain of at most k-1 steps that starts from the PREVIOUS iterate,
+//   x = old[max(0, p-k+1)];  for i = max(1, p-k+2) .. p:  x = (g[i] +) Phi_i(x);   u[p] = x.
+// The chains are independent (they read `old`, a copy of u made before the launch), one work item per point.
+// ------------------------------------------------------------------------------------------------
+struct GenWindow {
+    LevelDev L;
+    const double *old;
+    int k, w, nw, stride;
+    int s, e, i, stage, pro;
+    size_t soff;
+    __device__ GenWindow(const LevelDev &L_, const double *old_, int k_, int first, int nw_, int stride_)
+        : L(L_), old(old_), k(k_), w(first), nw(nw_), stride(stride_), s(0), e(0), i(0), stage(-2), pro(0), soff(0) {}
+    __device__ bool next(const double *&p) {
+        for (;;) {
+            if (w >= nw) return false;
+            if (stage == -2) {
+                const ItemPos ip = item_pos(L, w, 1);
+                e = ip.k + 1;  // one past the point this item produces
+                s = ip.k - k + 1;
+                if (s < 0) s = 0;
+                soff = ip.soff;
+                pro = 0;
+                stage = -1;
+            }
+            if (stage == -1) {
+                if (pro < n_prologue(L)) {
+                    p = prologue_row(L, pro++, soff);
+                    return true;
+                }
+                p = old + (size_t)s * L.pitch + soff;
+                i = s + 1;
+                stage = 0;
+                return true;
+            }
+            if (i >= e) {
+                w += stride;
+                stage = -2;
+                continue;
+            }
+            if (StepRows::next(L, i, stage, p, soff)) return true;
+            ++i;
+            stage = 0;
+        }
+    }
+};
+
+template <class Phi>
+__global__ void __launch_bounds__(Phi::T) k_window(const LevelDev L, const double *__restrict__ old, const int k,
+                                                   const int nw, const int nin) {
+    using SH = typename Phi::SH;
+    Team<Phi::T> team(g_smem);
+    RowPipe<SH, GenWindow> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenWindow(L, old, k, blockIdx.x, nw, gridDim.x));
+    pipe.start(team);
+    typename Phi::C c;
+    Phi::load_consts(c, L.sconst, team.tid);
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const ItemPos ip = item_pos(L, w, 1);
+        const int pt = ip.k;
+        int s = pt - k + 1;
+        if (s < 0) s = 0;
+        typename Phi::Item it;
+        Phi::begin_item(it, L, ip.sys, pipe, team);
+        double x[Phi::E];
+        pipe.pop(x, team);
+        for (int i = s + 1; i <= pt; ++i) advance<Phi>(x, c, it, L, i, pipe, team);
+        pipe.push(x, L.u + (size_t)pt * L.pitch + ip.soff, team);
+    }
+    pipe.finish(team);
+}
+
+// ------------------------------------------------------------------------------------------------
 // C-relaxation (mgrit.py:354-368): for each C-point c = cpts[k], k >= 1:
 //   u[c] = ((g[c] +) Phi_c(u[c-1])) * w + u[c] * (1 - w)
 // ------------------------------------------------------------------------------------------------

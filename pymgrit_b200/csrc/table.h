@@ -27,6 +27,8 @@ struct SweepTable {
     // FAS restriction with a spatial grid transfer, split around the transfer (nullptr: not available)
     int (*residual_rows)(const LevelDev &, double *, cudaStream_t);
     int (*fas_rhs)(const LevelDev &, const double *, const double *, int, cudaStream_t);
+    // AT-MGRIT local coarse grids (nullptr: not available)
+    int (*window)(const LevelDev &, const double *, int, cudaStream_t);
 };
 
 }  // namespace mgb

@@ -36,7 +36,10 @@ def run_b200(name, **extra):
     kw.update(extra)
     if 'transfer' in case:
         kw['transfer'] = b200_transfer(case)
-    solver = P.Mgrit(problem=b200_problem(case), logging_lvl=logging.WARNING, **kw)
+    if 'at_k' in case:
+        solver = P.AtMgrit(problem=b200_problem(case), k=case['at_k'], logging_lvl=logging.WARNING, **kw)
+    else:
+        solver = P.Mgrit(problem=b200_problem(case), logging_lvl=logging.WARNING, **kw)
     info = solver.solve()
     return solver, info
 

@@ -205,6 +205,15 @@ CASES = {
                                     app_kw=[dict(nx=65, **HEAT), dict(nx=65, **HEAT), dict(nx=33, **HEAT)],
                                     t=(0, 1, 65), grids=_simple(3, 4), transfer=['copy', 'space'],
                                     solver=dict(tol=1e-7, nested_iteration=False, weight_c=1.1)),
+    # AT-MGRIT (core/at_mgrit.py) on one time rank: tests/core/test_at_mgrit.py:33-45 (k = 2), and longer local grids
+    'heat1d_atmgrit_test': dict(app='heat1d', app_kw=dict(x_start=0, x_end=2, nx=5, a=1, rhs=heat_rhs,
+                                                          init_cond=heat_init),
+                                t=(0, 2, 65), grids=('nt', [65, 17, 5]), at_k=2,
+                                solver=dict(cf_iter=1, nested_iteration=False, max_iter=2)),
+    'heat1d_atmgrit_k8': dict(app='heat1d', app_kw=dict(nx=129, **HEAT), t=(0, 2, 513), grids=_simple(3, 4), at_k=8,
+                              solver=dict(tol=1e-8, nested_iteration=True)),
+    'heat1d_atmgrit_k5_f': dict(app='heat1d', app_kw=dict(nx=33, **HEAT), t=(0, 1, 257), grids=_simple(3, 4), at_k=5,
+                                solver=dict(tol=1e-8, cycle_type='F', conv_crit=1, nested_iteration=False)),
     # local convergence criteria (mgrit.py:434-454) on one time rank
     'heat1d_small_local_res': dict(app='heat1d', app_kw=dict(nx=17, **HEAT), t=(0, 2, 65), grids=_simple(3, 2),
                                    solver=dict(tol=1e-9, conv_crit=2)),

@@ -25,6 +25,7 @@ sys.path[:0] = [os.path.join(ROOT, 'oracle', 'stubs'), '/root/reference/src', os
 warnings.filterwarnings('ignore')
 
 from pymgrit.core.mgrit import Mgrit                      # noqa: E402
+from pymgrit.core.at_mgrit import AtMgrit                 # noqa: E402
 from pymgrit.heat.heat_1d import Heat1D                   # noqa: E402
 from pymgrit.heat.heat_2d import Heat2D                   # noqa: E402
 from pymgrit.heat.heat_1d_2pts_bdf1 import Heat1DBDF1     # noqa: E402
@@ -97,7 +98,10 @@ def run_case(name):
     case = C.CASES[name]
     problem = build_reference_problem(case)
     t0 = time.time()
-    solver = Mgrit(problem=problem, transfer=build_reference_transfer(case), logging_lvl=30, **case['solver'])
+    if 'at_k' in case:
+        solver = AtMgrit(problem=problem, k=case['at_k'], logging_lvl=30, **case['solver'])
+    else:
+        solver = Mgrit(problem=problem, transfer=build_reference_transfer(case), logging_lvl=30, **case['solver'])
     info = solver.solve()
     wall = time.time() - t0
     u = [values_of(v) for v in solver.u[0]]

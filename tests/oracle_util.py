@@ -31,6 +31,9 @@ def oracle_transfer(case):
 
 def run_oracle(name, solver=None):
     case = C.CASES[name]
+    if 'at_k' in case:
+        mg = O.AtMgritOracle(oracle_problem(case, solver), k=case['at_k'], **case['solver'])
+        return mg, mg.solve()
     mg = O.MgritOracle(oracle_problem(case, solver), transfer=oracle_transfer(case), **case['solver'])
     info = mg.solve()
     return mg, info

@@ -29,7 +29,7 @@ def _check_against_golden(name):
     return solver, info
 
 
-@pytest.mark.parametrize('name', [k for k in _cases(('heat1d',)) if C.CASES[k]['app'] == 'heat1d'])
+@pytest.mark.parametrize('name', [k for k in _cases(('heat1d',)) if C.CASES[k]['app'] == 'heat1d' and 'at_k' not in C.CASES[k]])
 def test_heat1d_against_reference_fixture(name):
     _check_against_golden(name)
 
@@ -39,6 +39,17 @@ def test_heat1d_two_point_bdf_against_reference_fixture(name):
     """heat/heat_1d_2pts_bdf{1,2}.py: pair states, BDF2 over BDF1 levels (examples/example_heat_1d_bdf2.py)."""
     solver, _ = _check_against_golden(name)
     assert any(solver._fused_down) == (solver.weight_c == 1.0)
+
+
+@pytest.mark.parametrize('name', [k for k in C.CASES if 'at_k' in C.CASES[k]])
+def test_at_mgrit_against_reference_fixture(name):
+    """core/at_mgrit.py on one time rank: local coarse grids on the coarsest level in one launch."""
+    solver, info = _check_against_golden(name)
+    if name == 'heat1d_atmgrit_test':              # tests/core/test_at_mgrit.py:33-45
+        np.testing.assert_almost_equal(info['conv'], np.array([0.1767778, 0.01223507]))
+    import pymgrit_b200 as P
+    with pytest.raises(Exception):
+        P.AtMgrit(problem=solver.problem, k=2, conv_crit=2)
 
 
 def test_spatial_coarsening_matches_reference_result_file():
