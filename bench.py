@@ -223,8 +223,6 @@ def gpu_arm(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     nt, coarsening = WORKLOADS[args.workload]
     if args.coarsening:
@@ -330,10 +328,17 @@ def main():
     ap.add_argument('--coarsening', default='', help='comma-separated coarsening factors per level (overrides the workload)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: whatever libraries print to file descriptor 1 meanwhile (NCCL's version
+    # banner when NCCL_DEBUG is set in the environment, torchrun notices) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, 'w', buffering=1)
     if args.impl == 'reference':
         reference_arm(args)
     else:
         gpu_arm(args)
+    sys.stdout.flush()
 
 
 if __name__ == '__main__':

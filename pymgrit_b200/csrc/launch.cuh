@@ -1,6 +1,7 @@
 // launch.cuh -- host-side launchers for the team kernels of sweeps.cuh, one table per (Phi, T, E).
 #pragma once
 #include <cstdlib>
+#include <mutex>
 
 #include "sweeps.cuh"
 #include "table.h"
@@ -13,19 +14,40 @@ struct Launch {
 
     static size_t smem_bytes(int nin) { return kHeaderBytes + (size_t)(nin + 1) * SH::SLOT_BYTES; }
 
-    // persistent grid: as many CTAs as fit on the device at once, but no more than there are items
+    // persistent grid: as many CTAs as fit on the device at once, but no more than there are items.  The shared-memory
+    // opt-in and the occupancy query are done once per (kernel, slot count, device) and remembered: on the coarse levels
+    // a sweep runs for ~10 us, so two runtime calls per launch are not free.
     template <class K>
     static int grid_for(K kernel, int nitems, int nin, int *grid) {
         const size_t smem = smem_bytes(nin);
         const DeviceInfo *di = device_info();
         if (di == nullptr) return 3;
         if ((int)smem > di->max_smem_optin) return 2;
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Phi::T, smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-        if (per_sm < 1) return 2;
+        struct Entry {
+            const void *fn;
+            int nin, dev, per_sm;
+        };
+        static Entry cache[64];
+        static int ncache = 0;
+        static std::mutex mu;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int per_sm = -1;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            for (int q = 0; q < ncache; ++q)
+                if (cache[q].fn == (const void *)kernel && cache[q].nin == nin && cache[q].dev == dev) per_sm = cache[q].per_sm;
+        }
+        if (per_sm < 0) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+            per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Phi::T, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+            if (per_sm < 1) return 2;
+            std::lock_guard<std::mutex> lock(mu);
+            if (ncache < 64) cache[ncache++] = Entry{(const void *)kernel, nin, dev, per_sm};
+        }
         const long cap = (long)per_sm * di->sms;
         *grid = (int)(nitems < cap ? nitems : cap);
         if (*grid < 1) *grid = 1;
