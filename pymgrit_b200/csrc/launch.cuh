@@ -26,6 +26,7 @@ struct Launch {
         struct Entry {
             const void *fn;
             int nin, dev, per_sm;
+            size_t smem;
         };
         static Entry cache[64];
         static int ncache = 0;
@@ -33,20 +34,25 @@ struct Launch {
         int dev = 0;
         cudaGetDevice(&dev);
         int per_sm = -1;
+        size_t opted = 0;  // largest dynamic shared memory this kernel has been opted in for (the limit only ever grows)
         {
             std::lock_guard<std::mutex> lock(mu);
             for (int q = 0; q < ncache; ++q)
-                if (cache[q].fn == (const void *)kernel && cache[q].nin == nin && cache[q].dev == dev) per_sm = cache[q].per_sm;
+                if (cache[q].fn == (const void *)kernel && cache[q].dev == dev) {
+                    if (cache[q].nin == nin) per_sm = cache[q].per_sm;
+                    if (cache[q].smem > opted) opted = cache[q].smem;
+                }
         }
         if (per_sm < 0) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaSuccess;
+            if (smem > opted) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
             per_sm = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Phi::T, smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
             if (per_sm < 1) return 2;
             std::lock_guard<std::mutex> lock(mu);
-            if (ncache < 64) cache[ncache++] = Entry{(const void *)kernel, nin, dev, per_sm};
+            if (ncache < 64) cache[ncache++] = Entry{(const void *)kernel, nin, dev, per_sm, smem};
         }
         const long cap = (long)per_sm * di->sms;
         *grid = (int)(nitems < cap ? nitems : cap);
