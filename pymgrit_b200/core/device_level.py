@@ -1,7 +1,6 @@
 """One level of the time-grid hierarchy in HBM: the arrays and the struct mgb_level handed to the
 C ABI (include/mgrit_b200.h).  PyTorch owns the buffers; nothing here computes."""
 import ctypes as C
-
 import weakref
 
 import numpy as np
@@ -34,12 +33,6 @@ def pinned_array(shape):
 
 
 def team_shape(kind, n):
-    import os
-    ov = os.environ.get('MGB_TEAM_SHAPE')          # "T,E": experiment with another compiled shape (scripts only)
-    if ov and kind == _lib.APP_HEAT1D:
-        t_, e_ = (int(x) for x in ov.split(','))
-        if t_ * e_ >= n:
-            return t_, e_
     t, e = C.c_int32(0), C.c_int32(0)
     _lib.check(_lib.lib().mgb_team_shape(kind, n, C.byref(t), C.byref(e)), 'team_shape')
     return t.value, e.value
