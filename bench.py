@@ -295,6 +295,7 @@ def gpu_arm(args):
     dom = max([k for k in kernels if k['bound'] == 'hbm'], key=lambda k: k['share_ms'])
     roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
                 'frac': dom['gbs'] / hbm, 'traffic': ncu_traffic(dom['name'], dom['intervals']), 'peak_source': which,
+                'frac_of_nominal_7700': dom['gbs'] / 7700.0,          # HGX B200 data-sheet figure (B200_PROFILING.md)
                 'algorithmic_bytes': dom['algorithmic_bytes'], 'ms': dom['ms']}
 
     if rank == 0:
