@@ -301,8 +301,16 @@ def gpu_arm(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            dofs, sec, its, cores, what = cpu_sample()
-            cpu = {'value': dofs, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': what + f' ({sec:.1f} s)'}
+            # in a fresh process: the CPU port forks its time-parallel workers, which a process that has initialised CUDA
+            # and started threads should not do
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1',
+                                '--warmup', '0', '--workload', args.workload], stdout=subprocess.PIPE,
+                               stderr=subprocess.DEVNULL, text=True, timeout=900)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+            if lines:
+                ref = json.loads(lines[-1])
+                cpu = dict(ref['cpu_baseline'])
+                cpu['sample'] += f" ({ref['ms_per_step'] / 1e3:.1f} s)"
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic',

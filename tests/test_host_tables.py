@@ -53,7 +53,17 @@ def test_callable_that_does_not_broadcast_falls_back_to_point_evaluation():
     assert np.max(np.abs(sp.coefficients(T) @ sp.basis - want)) <= 1e-12
 
 
-def test_long_grid_goes_through_the_thread_pool_unchanged():
+@pytest.fixture
+def fresh_pool():
+    """Stop the table threads after the test: later tests fork worker processes (oracle/mgrit_oracle_mp.py)."""
+    from pymgrit_b200.core import rhs_tables
+    yield
+    if rhs_tables._POOL is not None:
+        rhs_tables._POOL[0].shutdown(wait=True)
+        rhs_tables._POOL = None
+
+
+def test_long_grid_goes_through_the_thread_pool_unchanged(fresh_pool):
     t = np.linspace(0, 2, (1 << 16) + 1)
     sp = RhsSplit(C.heat_rhs_rank2, X).analyse(t)
     scale = np.full(len(t), t[1] - t[0])
