@@ -39,6 +39,9 @@ class SerialComm:
     def setup_peer_exchange(self, solver):
         return None
 
+    def sum_rows(self, rows):
+        return None
+
     def reduce_norm(self, partial, t_norm):
         return partial
 
@@ -226,6 +229,10 @@ class TorchDistComm:
     def all_gather_rows(self, out, mine):
         """out[r] = rank r's `mine` (device tensors; the sine-space coarsest solve, heat/heat_1d.py)."""
         self.dist.all_gather_into_tensor(out, mine, group=self.group)
+
+    def sum_rows(self, rows):
+        """In-place sum of a device array over the ranks (AT-MGRIT: every rank contributes its own rows, zeros elsewhere)."""
+        self.dist.all_reduce(rows, op=self.dist.ReduceOp.SUM, group=self.group)
 
     def reduce_norm(self, partial, t_norm):
         op = self.dist.ReduceOp.MAX if t_norm == 3 else self.dist.ReduceOp.SUM

@@ -29,8 +29,11 @@ def main():
     failed = []
     for name in sys.argv[1:]:
         case = C.CASES[name]
-        solver = P.Mgrit(problem=b200_problem(case), transfer=b200_transfer(case), logging_lvl=logging.WARNING,
-                         **case['solver'])
+        if 'at_k' in case:
+            solver = P.AtMgrit(problem=b200_problem(case), k=case['at_k'], logging_lvl=logging.WARNING, **case['solver'])
+        else:
+            solver = P.Mgrit(problem=b200_problem(case), transfer=b200_transfer(case), logging_lvl=logging.WARNING,
+                             **case['solver'])
         info = solver.solve()
         lv = solver._lv[0]
         own = lv.values(idx=np.arange(1 if rank > 0 else 0, lv.npts))                       # drop the ghost row

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = ['heat1d_small_v', 'heat1d_small_f_cf2', 'heat1d_cfg2_nt1025', 'heat1d_small_jump', 'heat1d_small_tnorminf',
          'heat1d_small_weight', 'heat1d_trailing_f', 'dahlquist_cfg1', 'dahlquist_ml1', 'advection_example',
          'brusselator_example', 'heat1d_example', 'heat1d_bdf2_example', 'heat1d_bdf1_small', 'heat2d_cn_3lvl',
-         'heat1d_spatial_example', 'heat1d_spatial_large']
+         'heat1d_spatial_example', 'heat1d_spatial_large', 'heat1d_atmgrit_k8', 'heat1d_atmgrit_k5_f']
 
 
 def _free_port():
