@@ -167,3 +167,59 @@ def test_heat2d_sine_space_tables_reproduce_the_oracle(lib, name):
         row, u = x, orc.phi(u, t[i - 1], t[i])
         assert np.max(np.abs(from_rows(row) - u)) <= 1e-12 * np.max(np.abs(u))
         assert abs(np.linalg.norm(row) - np.linalg.norm(u)) <= 1e-12 * np.linalg.norm(u)      # Parseval
+
+
+@pytest.mark.parametrize('name', ['heat1d_bdf2_nonuniform', 'heat1d_bdf1_small', 'heat1d_bdf2_small_f'])
+def test_two_point_tables_reproduce_the_oracle(lib, name):
+    """Host-side check of the two-point design (pymgrit_b200/heat/heat_1d_2pts.py, csrc/phi.cuh Heat1D2Pts): the
+    step-constant rows (two Heat1D blocks + a1 b1 a2 b2 skip1), the dt classes, the thread-transposed spatial factors
+    and the [npts][2 q] time factors the host builds, pushed through a numpy restatement of the kernel's arithmetic
+    (Toeplitz recurrences + Sherman-Morrison, as in test_heat1d_constants_solve_the_system), give the oracle's BDF step
+    on every level of the case."""
+    import cases as CS
+    import pymgrit_b200 as P
+    from pymgrit_b200 import _lib
+    from oracle import mgrit_oracle as O
+    case = CS.CASES[name]
+    grids = CS.case_time_grids(case)
+
+    def solve(row, b, n):
+        beta, cs, kappa = row[0], row[1], row[2]
+        y, acc = np.zeros(n), 0.0
+        for i in range(n):
+            acc = beta * acc + b[i] * cs
+            y[i] = acc
+        z, acc = np.zeros(n), 0.0
+        for i in range(n - 1, -1, -1):
+            acc = beta * acc + y[i]
+            z[i] = acc
+        i = np.arange(n)
+        h = (beta ** (i + 1.0) - beta ** (2.0 * n + 1 - i)) / (1 - beta * beta)
+        return z - kappa * z[0] * h
+
+    for lvl, t in enumerate(grids):
+        kw = CS.level_app_kw(case, lvl)
+        method = kw.pop('method')
+        app = {'BDF1': P.Heat1DBDF1, 'BDF2': P.Heat1DBDF2}[method](t_interval=t, **kw)
+        orc = O.Heat1D2PtsOracle(t_interval=t, method=method, **kw)
+        T, E, h = app._shape()
+        n = app.nx
+        assert E == 2 * h + 1 and T * h >= n and app.row_pitch() == T * E
+        tab = app.level_tables(t, T, E)
+        half = lib.mgb_heat1d_2pts_half_width(T, E)
+        assert tab['cw'] == 2 * half + 8 == tab['sconst'].shape[1]
+        q = tab['nrhs']
+        rx = tab['rhs_x'].transpose(0, 2, 1).reshape(q, T * h)[:, :n]          # back from [q][h][T] to [q][n]
+        assert np.array_equal(rx, app._rhs_split.basis)
+        assert tab['rhs_t'].shape == (len(t), 2 * q)
+        rng = np.random.default_rng(11 + lvl)
+        u = rng.standard_normal((2, n))
+        for i in (1, len(t) // 2, len(t) - 1):
+            row = tab['sconst'][0 if tab['dtidx'] is None else tab['dtidx'][i]]
+            a1, b1, a2, b2, skip1 = row[2 * half:2 * half + 5]
+            s1 = a1 * u[0] + b1 * u[1] + tab['rhs_t'][i, :q] @ rx
+            tmp1 = s1 if skip1 else solve(row[:half], s1, n)
+            s2 = a2 * u[1] + b2 * tmp1 + tab['rhs_t'][i, q:] @ rx
+            tmp2 = solve(row[half:2 * half], s2, n)
+            want = orc.phi(u, t[i - 1], t[i])
+            assert np.max(np.abs(np.stack([tmp1, tmp2]) - want)) <= 1e-11 * np.max(np.abs(want)), (name, lvl, i)
