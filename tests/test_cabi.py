@@ -223,3 +223,32 @@ def test_two_point_tables_reproduce_the_oracle(lib, name):
             tmp2 = solve(row[half:2 * half], s2, n)
             want = orc.phi(u, t[i - 1], t[i])
             assert np.max(np.abs(np.stack([tmp1, tmp2]) - want)) <= 1e-11 * np.max(np.abs(want)), (name, lvl, i)
+
+
+@pytest.mark.parametrize('n', [7, 63, 1023])
+def test_fast_sine_transform_algorithm(n):
+    """numpy restatement of k_rows_dst (csrc/spectral.cu), index for index: odd extension to 2N points, radix-2
+    decimation-in-frequency stages with twiddles W_{2N}^(pos N / half), bit-reversed read-out, -sqrt(2/N)/2 Im(.).
+    It must equal the product with the orthonormal sine matrix that mgb_rows_gemm computes."""
+    N, N2 = n + 1, 2 * (n + 1)
+    bits = N2.bit_length() - 1
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    z = np.zeros(N2, dtype=complex)
+    z[1:N] = x
+    z[N2 - np.arange(1, N)] = -x
+    tw = np.exp(-1j * np.pi * np.arange(N) / N)
+    b = np.arange(N)
+    for s in range(bits - 1, -1, -1):
+        half = 1 << s
+        pos = b & (half - 1)
+        i = ((b >> s) << (s + 1)) + pos
+        j = i + half
+        p, q = z[i].copy(), z[j].copy()
+        z[i] = p + q
+        z[j] = (p - q) * tw[pos * (N >> s)]
+    rev = np.array([int(format(k + 1, '0%db' % bits)[::-1], 2) for k in range(n)])
+    got = -0.5 * np.sqrt(2.0 / N) * z[rev].imag
+    k = np.arange(1, n + 1)
+    want = x @ (np.sqrt(2.0 / N) * np.sin(np.pi * np.outer(k, k) / N))
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.sqrt(n)
