@@ -123,3 +123,28 @@ def test_device_vector_host_side():
     first, second, dtau = pair.get_values()
     assert first.tolist() == [1, 1, 1] and second.tolist() == [2, 2, 2] and dtau == 0.1 and pair.size == 3
     np.testing.assert_array_equal(pair.pack(), [[1, 1, 1], [2, 2, 2]])
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure and /root/reference is not on the GPU box: no file of the package (or of the C ABI)
+    may import, open or link either; only tests/, bench.py's CPU legs and __graft_entry__.smoke() use the oracle."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = []
+    for base in ('pymgrit_b200', 'include'):
+        for dirpath, _, files in os.walk(os.path.join(root, base)):
+            if os.sep + 'build' in dirpath or os.sep + 'lib' in dirpath:
+                continue
+            for f in files:
+                if not f.endswith(('.py', '.cu', '.cuh', '.h')):
+                    continue
+                text = open(os.path.join(dirpath, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle\b', text, re.M) or 'mgrit_oracle' in text or \
+                        re.search(r'open\([^)]*/root/reference', text) or 'sys.path' in text and '/root/reference' in text:
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    bench = open(os.path.join(root, 'bench.py')).read()
+    assert '/root/reference' not in bench            # nothing run on the GPU box reads the reference tree
+    entry = open(os.path.join(root, '__graft_entry__.py')).read()
+    assert '/root/reference' not in entry
