@@ -179,7 +179,7 @@ class Mgrit:
         self.output_fcn = output_fcn if output_fcn is not None and callable(output_fcn) else None
 
         # index tables (mgrit.py:206-222, 742-827) and level storage in HBM (mgrit.py:840-858)
-        self.global_t = [np.copy(p.t) for p in problem]
+        self.global_t = [np.asarray(p.t, dtype=float) for p in problem]      # read-only here: no 8 MB copies at nt = 2^20
         part = partition.Partition(self.global_t, self.comm_time_size, self.comm_time_rank, masks=masks)
         self._part = part
         self.m = part.m

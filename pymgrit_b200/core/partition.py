@@ -29,6 +29,18 @@ def split_points(length: int, size: int, rank: int):
     return split[rank], (np.sum(split[:rank]) if split[rank] > 0 else 0)
 
 
+class _Mask(np.ndarray):
+    """Boolean C-point mask that remembers when it is regular (every `stride`-th point from 0): index lists then come
+    from arithmetic instead of a scan over up to 2^20 flags."""
+    stride = 0
+
+
+def _strided(mask, stride):
+    out = mask.view(_Mask)
+    out.stride = int(stride)
+    return out
+
+
 def c_point_masks(global_t):
     """is_c[l][i]: point i of level l is also a point of level l+1 (mgrit.py:212, 768-770); all True on the coarsest."""
     masks = []
@@ -42,6 +54,7 @@ def c_point_masks(global_t):
         increasing = bool(np.all(t[1:] > t[:-1]))
         if increasing and stride > 0 and np.array_equal(t[::stride], tc):
             mask[::stride] = True                        # the usual case t_coarse = t[::m]: no search needed
+            mask = _strided(mask, stride)
         elif increasing:                       # sorted grid: binary search instead of np.isin's sort
             idx = np.minimum(np.searchsorted(t, tc), len(t) - 1)
             mask[idx[t[idx] == tc]] = True
@@ -56,8 +69,10 @@ def coarsening_factors(global_t, masks):
     out = []
     for l in range(len(global_t)):
         if l + 1 < len(global_t):
-            idx = np.flatnonzero(masks[l])
-            out.append(int(idx[1] - idx[0]) if len(idx) > 1 else 1)
+            mask = np.asarray(masks[l])
+            first = int(np.argmax(mask))                 # the first two C-points; argmax stops at the first True
+            rest = mask[first + 1:]
+            out.append(1 + int(np.argmax(rest)) if mask[first] and rest.any() else 1)
         else:
             out.append(1)
     return out
@@ -189,8 +204,12 @@ def _slab_tables(global_t, masks, lvl, rank, window):
     ghost = rank != 0 and n_own > 0
     off = 1 if ghost else 0
     own = lambda: np.arange(a, b + 1)
-    sub = is_c[a:b + 1]
-    local_c = np.flatnonzero(sub)                    # positions inside the owned range
+    sub = np.asarray(is_c[a:b + 1])
+    stride = getattr(is_c, 'stride', 0)
+    if stride > 0:                                   # regular coarsening: every stride-th point from 0
+        local_c = np.arange((-a) % stride, n_own, stride)
+    else:
+        local_c = np.flatnonzero(sub)                # positions inside the owned range
     t_local = t[a - off:b + 1] if n_own else t[0:0]
 
     def f_list():
