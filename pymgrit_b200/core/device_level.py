@@ -52,10 +52,11 @@ def step_const_table(kind, values, n, team_threads, chunk):
 class DeviceLevel:
     """Arrays of one level on the current CUDA device + the matching struct mgb_level."""
 
-    def __init__(self, app, t, cpts=None, with_g=False, u_init=None, defer_tables=False):
+    def __init__(self, app, t, cpts=None, with_g=False, u_init=None, defer_tables=False, zero_u=True):
         """defer_tables: allocate the arrays now, build and upload the Phi tables when finish_tables() is called (the
         solver does that for level 0 after it has queued the coarse-level work of nested iteration, so that the host
-        evaluates the long level-0 tables while the device is busy)."""
+        evaluates the long level-0 tables while the device is busy).  zero_u=False: leave u uninitialised (the caller
+        guarantees that every row is written before it is read, as nested iteration + one cycle do)."""
         torch = _torch()
         dev = torch.device('cuda', torch.cuda.current_device())
         self.app = app
@@ -66,7 +67,12 @@ class DeviceLevel:
         self.pitch = int(app.row_pitch()) if hasattr(app, 'row_pitch') else (self.n if tiny else self.n + (self.n & 1))
         self.team_threads, self.chunk = team_shape(app.kind, self.n)
         # the (asynchronous) zero fill of the level arrays runs on the device while the host builds the tables
-        self.u = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if u_init is None else u_init
+        if u_init is not None:
+            self.u = u_init
+        elif zero_u:
+            self.u = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev)
+        else:
+            self.u = torch.empty((self.npts, self.pitch), dtype=torch.float64, device=dev)
         self.g = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if with_g else None
         self.cpts = None if cpts is None else np.asarray(cpts, dtype=np.int32)
         self._keep = []                                   # tensors referenced by the struct

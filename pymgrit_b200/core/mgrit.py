@@ -194,7 +194,13 @@ class Mgrit:
             cp = part.sweep_cpts[lvl] if lvl < self.lvl_max - 1 else None
             # level 0's tables (the long ones) are built after the coarse part of nested iteration has been queued
             defer = lvl == 0 and self.lvl_max > 1 and bool(nested_iteration) and not random_init_guess
-            self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0, defer_tables=defer))
+            # ... and its 8.6 GB array is not zero-filled when nested iteration and at least one cycle follow: the
+            # C-points come from the interpolation, the F-points from the F-relaxations, before anything reads them
+            # (restart() relies on the same fact).  Only a user who looks at F-points of level 0 between the
+            # constructor and the first iteration would see the difference, so a per-iteration output_fcn keeps the fill.
+            self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0, defer_tables=defer,
+                                        zero_u=not (defer and max_iter > 0 and not (callable(output_fcn) and
+                                                                                    output_lvl == 2))))
         # levels whose down-sweep runs as one fused launch (mgb_down_sweep): unweighted C-relaxation, at least one
         # F-point in every interval (on every time rank), team kernels
         import os
