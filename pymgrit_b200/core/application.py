@@ -12,53 +12,58 @@ import numpy as np
 from pymgrit_b200.core.vector import Vector
 
 
+class _Required:
+    """Descriptor for an attribute every application has to assign in its constructor (stored as `_<name>`).  Reading it
+    before it was assigned raises AttributeError, which is what the check after construction looks for."""
+
+    def __set_name__(self, owner, name):
+        self.name, self.slot = name, '_' + name
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        try:
+            return obj.__dict__[self.slot]
+        except KeyError:
+            raise AttributeError(self.name) from None
+
+    def __set__(self, obj, value):
+        obj.__dict__[self.slot] = value
+
+
 class MetaApplication(ABCMeta):
-    """Checks that the required attributes exist after construction (core/application.py:17-29)."""
+    """After an application object has been built, every name in `required_attributes` must exist
+    (core/application.py:17-29 raises ValueError otherwise)."""
     required_attributes = []
 
     def __call__(cls, *args, **kwargs):
         obj = super().__call__(*args, **kwargs)
-        for name in obj.required_attributes:
-            if not hasattr(obj, name):
-                raise ValueError('required attribute (%s) not set' % name)
+        missing = [name for name in obj.required_attributes if not hasattr(obj, name)]
+        if missing:
+            raise ValueError('required attribute (%s) not set' % missing[0])
         return obj
 
 
+def _time_grid(t_start, t_stop, nt, t_interval):
+    """(grid, first, last, count) from either form of the constructor arguments (core/application.py:45-68)."""
+    if t_interval is not None:
+        if not isinstance(t_interval, np.ndarray):
+            raise Exception('t_interval has the wrong type. Should be a numpy array')
+        return t_interval, t_interval[0], t_interval[-1], len(t_interval)
+    if t_start is None or t_stop is None or nt is None:
+        raise Exception('Specify an interval by t_start, t_stop and nt or by t_interval')
+    return np.linspace(t_start, t_stop, nt), t_start, t_stop, nt
+
+
 class Application(object, metaclass=MetaApplication):
+    """Time integrator plug-in: a time grid, a template vector, the state at t_start and step()."""
     required_attributes = ['vector_template', 'vector_t_start']
+    vector_template = _Required()        # a Vector that clone_zero() / clone_rand() can be called on
+    vector_t_start = _Required()         # the solution at the first time point
 
     def __init__(self, t_start: float = None, t_stop: float = None, nt: int = None,
                  t_interval: np.ndarray = None) -> None:
-        if t_interval is None:
-            if t_start is None or t_stop is None or nt is None:
-                raise Exception('Specify an interval by t_start, t_stop and nt or by t_interval')
-            self.t_start = t_start
-            self.t_end = t_stop
-            self.nt = nt
-            self.t = np.linspace(self.t_start, self.t_end, nt)
-        else:
-            if not isinstance(t_interval, np.ndarray):
-                raise Exception('t_interval has the wrong type. Should be a numpy array')
-            self.t_start = t_interval[0]
-            self.t_end = t_interval[-1]
-            self.nt = len(t_interval)
-            self.t = t_interval
-
-    @property
-    def vector_template(self) -> Vector:
-        return self._vector_template
-
-    @vector_template.setter
-    def vector_template(self, value: Vector) -> None:
-        self._vector_template = value
-
-    @property
-    def vector_t_start(self) -> Vector:
-        return self._vector_t_start
-
-    @vector_t_start.setter
-    def vector_t_start(self, value: Vector) -> None:
-        self._vector_t_start = value
+        self.t, self.t_start, self.t_end, self.nt = _time_grid(t_start, t_stop, nt, t_interval)
 
     @abstractmethod
     def step(self, u_start: Vector, t_start: float, t_stop: float) -> Vector:
