@@ -148,3 +148,24 @@ def test_product_never_touches_the_oracle_or_the_reference():
     assert '/root/reference' not in bench            # nothing run on the GPU box reads the reference tree
     entry = open(os.path.join(root, '__graft_entry__.py')).read()
     assert '/root/reference' not in entry
+
+
+def test_every_case_reaches_the_device_boundary():
+    """Without a GPU every parity case must get through the whole host-side setup that precedes the first device call
+    (application constructors, right-hand-side analysis, argument checks, transfers) and then fail for the one reason
+    that there is no CUDA device -- never with an AttributeError or a silent CPU result."""
+    import logging
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA device present')
+    from b200_util import b200_problem, b200_transfer
+    for name, case in C.CASES.items():
+        kw = dict(case['solver'])
+        if 'transfer' in case:
+            kw['transfer'] = b200_transfer(case)
+        with pytest.raises(Exception) as err:
+            if 'at_k' in case:
+                P.AtMgrit(problem=b200_problem(case), k=case['at_k'], logging_lvl=logging.WARNING, **kw)
+            else:
+                P.Mgrit(problem=b200_problem(case), logging_lvl=logging.WARNING, **kw)
+        assert 'CUDA' in str(err.value), (name, str(err.value))
