@@ -252,3 +252,111 @@ def test_fast_sine_transform_algorithm(n):
     k = np.arange(1, n + 1)
     want = x @ (np.sqrt(2.0 / N) * np.sin(np.pi * np.outer(k, k) / N))
     assert np.max(np.abs(got - want)) <= 1e-13 * np.sqrt(n)
+
+
+def _emulate_team_solve(row, b, n, T, E):
+    """numpy restatement of Heat1D::solve (csrc/phi.cuh) thread by thread: per-thread chunks of E elements in SUB
+    sub-chains, the constant-ratio exclusive scans over the team truncated to `nscan` doubling steps (common.cuh
+    scan_fwd / scan_bwd incl. the cross-warp carry), and the Sherman-Morrison correction with the per-thread PH / QH."""
+    SUB = 3 if E % 3 == 0 else 1
+    SL, PT = E // SUB, 2 + 2 * (3 if E % 3 == 0 else 1)
+    beta, cs, kappa, bsl = row[0], row[1], row[2], row[3]
+    Bd, B32, pw, nscan = row[4:9], row[9], row[10:10 + SL], int(row[23])
+    per = row[24:24 + T * PT].reshape(T, PT)
+    blf, blb, PH, QH = per[:, 0], per[:, 1], per[:, 2:2 + SUB], per[:, 2 + SUB:2 + 2 * SUB]
+    x = np.zeros((T, E))
+    x.reshape(-1)[:n] = b                                     # elements beyond n are 0 on entry
+    nv = n - np.arange(T) * E
+
+    def scan(a, forward):
+        a = a.copy()
+        lane, warp = np.arange(T) % 32, np.arange(T) // 32
+        for k in range(5):
+            if k >= nscan:
+                break
+            d = 1 << k
+            t = np.zeros(T)
+            for w in range(T // 32):                          # shuffles stay inside a warp
+                seg = a[32 * w:32 * w + 32]
+                t[32 * w:32 * w + 32] = np.concatenate([seg[:d], seg[:-d]]) if forward else np.concatenate([seg[d:], seg[-d:]])
+            upd = (lane >= d) if forward else (lane + d < 32)
+            a = np.where(upd, Bd[k] * t + a, a)
+        excl = np.zeros(T)
+        for w in range(T // 32):
+            seg = a[32 * w:32 * w + 32]
+            excl[32 * w:32 * w + 32] = np.concatenate([[0.0], seg[:-1]]) if forward else np.concatenate([seg[1:], [0.0]])
+        if T > 32:
+            W = T // 32
+            tot = a[31::32] if forward else a[0::32]          # each warp's inclusive total
+            for w in range(W):
+                carry = 0.0
+                rng = range(w) if forward else range(W - 1, w, -1)
+                for v in rng:
+                    carry = B32 * carry + tot[v]
+                sel = warp == w
+                excl[sel] = (blf if forward else blb)[sel] * carry + excl[sel]
+        return excl
+
+    e = np.zeros((T, SUB))
+    for jj in range(SL):
+        for s in range(SUB):
+            j = s * SL + jj
+            e[:, s] = beta * e[:, s] + x[:, j] * cs
+            x[:, j] = e[:, s]
+    a = e[:, 0].copy()
+    for s in range(1, SUB):
+        a = bsl * a + e[:, s]
+    inflow = scan(a, True)
+    if n % E == 0:
+        inflow = np.where(nv > 0, inflow, 0.0)
+    for s in range(SUB):
+        for jj in range(SL):
+            j = s * SL + jj
+            y = pw[jj] * inflow + x[:, j]
+            x[:, j] = y if n % E == 0 else np.where(j < nv, y, 0.0)
+        inflow = bsl * inflow + e[:, s]
+    f = np.zeros((T, SUB))
+    for jj in range(SL - 1, -1, -1):
+        for s in range(SUB):
+            j = s * SL + jj
+            f[:, s] = beta * f[:, s] + x[:, j]
+            x[:, j] = f[:, s]
+    a2 = f[:, SUB - 1].copy()
+    for s in range(SUB - 2, -1, -1):
+        a2 = bsl * a2 + f[:, s]
+    inb = np.zeros((T, SUB))
+    inb[:, SUB - 1] = scan(a2, False)
+    for s in range(SUB - 2, -1, -1):
+        inb[:, s] = bsl * inb[:, s + 1] + f[:, s + 1]
+    z0 = pw[SL - 1] * inb[0, 0] + x[0, 0]
+    gamma = kappa * z0
+    for s in range(SUB):
+        Bc = gamma * QH[:, s] + inb[:, s]
+        Ac = -gamma * PH[:, s]
+        for jj in range(SL):
+            j = s * SL + jj
+            x[:, j] = pw[SL - 1 - jj] * Bc + (pw[jj] * Ac + x[:, j])
+    return x.reshape(-1)[:n]
+
+
+@pytest.mark.parametrize('n, T, E', [(1023, 32, 33), (38, 32, 3), (15, 32, 1), (480, 32, 15), (999, 128, 9), (4095, 128, 33),
+                                     (65, 32, 5)])
+def test_team_solve_with_the_host_constants(lib, n, T, E):
+    """The full constant row mgb_heat1d_step_consts writes (scalars, power table, scan depth, per-thread B^lane, PH, QH),
+    used exactly as the kernel uses it, solves (I + r tridiag(-1, 2, -1)) x = b -- on the CPU, for the shapes of the
+    headline workload, the multi-warp teams and the half-chunks of the two-point rows."""
+    from pymgrit_b200 import _lib
+    for r in (2.0, 128.0, 0.03, 8192.0):
+        cw = lib.mgb_step_consts_width(_lib.APP_HEAT1D, T, E)
+        row = np.zeros(cw)
+        assert lib.mgb_heat1d_step_consts(r, n, T, E, row.ctypes.data_as(_lib.c_double_p)) == 0
+        rng = np.random.default_rng(n + T)
+        b = rng.standard_normal(n)
+        x = _emulate_team_solve(row, b, n, T, E)
+        from scipy.linalg import solve_banded
+        ab = np.zeros((3, n))
+        ab[0, 1:] = -r
+        ab[1] = 1 + 2 * r
+        ab[2, :-1] = -r
+        want = solve_banded((1, 1), ab, b)
+        assert np.max(np.abs(x - want)) <= 1e-11 * np.max(np.abs(want)), (n, T, E, r)
