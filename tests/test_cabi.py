@@ -360,3 +360,78 @@ def test_team_solve_with_the_host_constants(lib, n, T, E):
         ab[2, :-1] = -r
         want = solve_banded((1, 1), ab, b)
         assert np.max(np.abs(x - want)) <= 1e-11 * np.max(np.abs(want)), (n, T, E, r)
+
+
+@pytest.mark.parametrize('n, T, E', [(4095, 128, 33), (128, 32, 5), (5, 32, 1), (256, 32, 9)])
+def test_advection_team_solve_with_the_host_constants(lib, n, T, E):
+    """Advection1D::apply (csrc/phi.cuh) restated in numpy with the row of mgb_advection1d_step_consts: the cyclic lower
+    bidiagonal system (1 + nu) y_i - nu y_{i-1} = u_i (advection_1d.py:101-143) is solved by the forward recurrence, one
+    exclusive scan over the team and the closure y_{n-1} = p_{n-1} / (1 - rho^n)."""
+    from pymgrit_b200 import _lib
+    SUB = 3 if E % 3 == 0 else 1
+    SL, PT = E // SUB, 2 + 2 * SUB
+    for nu in (0.0625, 1.0, 37.5):
+        cw = lib.mgb_step_consts_width(_lib.APP_ADVECTION1D, T, E)
+        row = np.zeros(cw)
+        assert lib.mgb_advection1d_step_consts(nu, n, T, E, row.ctypes.data_as(_lib.c_double_p)) == 0
+        rho, sig, dinv, rsl = row[0], row[1], row[2], row[3]
+        Bd, B32, pw, nscan = row[4:9], row[9], row[10:10 + SL], int(row[23])
+        per = row[24:24 + T * PT].reshape(T, PT)
+        blf, RH = per[:, 0], per[:, 2:2 + SUB]
+        rng = np.random.default_rng(n)
+        u = rng.standard_normal(n)
+        x = np.zeros((T, E))
+        x.reshape(-1)[:n] = u
+        e = np.zeros((T, SUB))
+        for jj in range(SL):
+            for s in range(SUB):
+                j = s * SL + jj
+                e[:, s] = rho * e[:, s] + x[:, j] * sig
+                x[:, j] = e[:, s]
+        a = e[:, 0].copy()
+        for s in range(1, SUB):
+            a = rsl * a + e[:, s]
+        # exclusive forward scan with ratio B = rho^E (common.cuh scan_fwd, truncated to nscan doubling steps)
+        lane, warp = np.arange(T) % 32, np.arange(T) // 32
+        acc = a.copy()
+        for k in range(min(nscan, 5)):
+            d = 1 << k
+            t = np.zeros(T)
+            for w in range(T // 32):
+                seg = acc[32 * w:32 * w + 32]
+                t[32 * w:32 * w + 32] = np.concatenate([seg[:d], seg[:-d]])
+            acc = np.where(lane >= d, Bd[k] * t + acc, acc)
+        inflow = np.zeros(T)
+        for w in range(T // 32):
+            seg = acc[32 * w:32 * w + 32]
+            inflow[32 * w:32 * w + 32] = np.concatenate([[0.0], seg[:-1]])
+        if T > 32:
+            tot = acc[31::32]
+            for w in range(T // 32):
+                carry = 0.0
+                for v in range(w):
+                    carry = B32 * carry + tot[v]
+                inflow[warp == w] = blf[warp == w] * carry + inflow[warp == w]
+        last = n - 1
+        ins = np.zeros((T, SUB))
+        ylast = 0.0
+        inn = inflow.copy()
+        for s in range(SUB):
+            ins[:, s] = inn
+            for jj in range(SL):
+                j = s * SL + jj
+                y = pw[jj] * inn + x[:, j]
+                if last // E < T and last - (last // E) * E == j:
+                    ylast = y[last // E]
+            inn = rsl * inn + e[:, s]
+        Y = ylast * dinv
+        for s in range(SUB):
+            cf = RH[:, s] * Y + ins[:, s]
+            for jj in range(SL):
+                j = s * SL + jj
+                x[:, j] = pw[jj] * cf + x[:, j]
+        got = x.reshape(-1)[:n]
+        A = np.diag(np.full(n, 1 + nu)) - np.diag(np.full(n - 1, nu), -1)
+        A[0, n - 1] -= nu
+        want = np.linalg.solve(A, u)
+        assert np.max(np.abs(got - want)) <= 1e-11 * np.max(np.abs(want)), (n, T, E, nu)
