@@ -296,6 +296,7 @@ def gpu_arm(args):
     roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
                 'frac': dom['gbs'] / hbm, 'traffic': ncu_traffic(dom['name'], dom['intervals']), 'peak_source': which,
                 'frac_of_nominal_7700': dom['gbs'] / 7700.0,          # HGX B200 data-sheet figure (B200_PROFILING.md)
+                'frac_of_nominal_8000': dom['gbs'] / 8000.0,          # the ~8 TB/s BASELINE.json's north star quotes
                 'algorithmic_bytes': dom['algorithmic_bytes'], 'ms': dom['ms']}
 
     if rank == 0:
