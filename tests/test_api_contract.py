@@ -169,3 +169,28 @@ def test_every_case_reaches_the_device_boundary():
             else:
                 P.Mgrit(problem=b200_problem(case), logging_lvl=logging.WARNING, **kw)
         assert 'CUDA' in str(err.value), (name, str(err.value))
+
+
+@pytest.mark.parametrize('name', ['example_dahlquist', 'example_heat_1d', 'example_heat_1d_bdf2',
+                                  'example_spatial_coarsening', 'example_heat_2d', 'example_at_mgrit'])
+def test_examples_reach_the_device_boundary(name):
+    """examples/*.py (the reference's examples with the import swapped): the host-side setup of each runs on the CPU and
+    the solver constructor then stops for the one reason that there is no CUDA device."""
+    import importlib
+    import logging
+    import os
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA device present')
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'examples')
+    sys.path.insert(0, here)
+    try:
+        mod = importlib.import_module(name)
+        kw = mod.build()
+        cls = P.AtMgrit if 'k' in kw else P.Mgrit
+        with pytest.raises(Exception) as err:
+            cls(logging_lvl=logging.WARNING, **kw)
+        assert 'CUDA' in str(err.value), str(err.value)
+    finally:
+        sys.path.remove(here)
