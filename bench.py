@@ -64,7 +64,7 @@ def peaks():
     return 6650.0, 'fallback'
 
 
-def ncu_traffic(sweep, intervals):
+def ncu_traffic(sweep, intervals, m0=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `sweep` from the committed ncu --set full capture
     (profiles/ncu_traffic.json, written by scripts/ncu_summary.py traffic), scaled to this run's number of coarse
     intervals (traffic is proportional to it); None if the sweep was not captured."""
@@ -74,8 +74,8 @@ def ncu_traffic(sweep, intervals):
     with open(path) as f:
         cap = json.load(f)
     ent = cap['sweeps'].get(sweep)
-    if ent is None:
-        return None
+    if ent is None or (m0 is not None and cap.get('coarsening') not in (None, m0)):
+        return None                    # not captured, or captured for intervals of another length
     return (ent['dram_read_bytes'] + ent['dram_write_bytes']) * intervals / cap['intervals']
 
 
@@ -294,7 +294,7 @@ def gpu_arm(args):
     hbm, which = peaks()
     dom = max([k for k in kernels if k['bound'] == 'hbm'], key=lambda k: k['share_ms'])
     roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': hbm, 'unit': 'GB/s',
-                'frac': dom['gbs'] / hbm, 'traffic': ncu_traffic(dom['name'], dom['intervals']), 'peak_source': which,
+                'frac': dom['gbs'] / hbm, 'traffic': ncu_traffic(dom['name'], dom['intervals'], coarsening[0]), 'peak_source': which,
                 'frac_of_nominal_7700': dom['gbs'] / 7700.0,          # HGX B200 data-sheet figure (B200_PROFILING.md)
                 'frac_of_nominal_8000': dom['gbs'] / 8000.0,          # the ~8 TB/s BASELINE.json's north star quotes
                 'algorithmic_bytes': dom['algorithmic_bytes'], 'ms': dom['ms']}
