@@ -2,7 +2,7 @@
 
     python scripts/ncu_summary.py launches gpurun_out/r01_launches.csv      # per-kernel totals of a launch list
     python scripts/ncu_summary.py full gpurun_out/r01_sweeps.ncu-rep        # key metrics of a --set full capture
-    python scripts/ncu_summary.py traffic gpurun_out/r01_sweeps.ncu-rep name1,name2,... <intervals> profiles/ncu_traffic.json
+    python scripts/ncu_summary.py traffic gpurun_out/r01_sweeps.ncu-rep name1,name2,... <intervals> profiles/ncu_traffic.json [m]
 """
 import collections
 import csv
@@ -69,7 +69,7 @@ def full(path):
             pass
 
 
-def traffic(path, names, intervals, out_path):
+def traffic(path, names, intervals, out_path, coarsening=None):
     """profiles/ncu_traffic.json for bench.py: DRAM bytes (read + write) per captured launch, keyed by the sweep names
     given in launch order (scripts/profile_sweeps.py), with the number of coarse intervals the capture ran on."""
     import json
@@ -79,6 +79,8 @@ def traffic(path, names, intervals, out_path):
     scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     ir, iw = h.index('dram__bytes_read.sum'), h.index('dram__bytes_write.sum')
     res = {'source': path, 'intervals': int(intervals), 'sweeps': {}}
+    if coarsening is not None:
+        res['coarsening'] = int(coarsening)          # length of the level-0 intervals of the capture (bench.py checks it)
     for name, r in zip(names.split(','), rows[2:]):
         rd = float(r[ir].replace(',', '')) * scale[units[ir]]
         wr = float(r[iw].replace(',', '')) * scale[units[iw]]
@@ -90,6 +92,6 @@ def traffic(path, names, intervals, out_path):
 
 if __name__ == '__main__':
     if sys.argv[1] == 'traffic':
-        traffic(*sys.argv[2:6])
+        traffic(*sys.argv[2:7])
     else:
         {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2])
