@@ -163,6 +163,8 @@ def cpu_sample(cores=None, solver='spsolve'):
     from oracle import mgrit_oracle_mp as OM
     cores = cpu_cores() if cores is None else cores
     nt_sample, coarsening = CPU_SAMPLE_MP if cores >= 4 else CPU_SAMPLE
+    if os.environ.get('MGRIT_BENCH_CPU_SAMPLE_NT'):          # tests/test_bench_cpu.py: a sample that runs in a second
+        nt_sample = int(os.environ['MGRIT_BENCH_CPU_SAMPLE_NT'])
     nt_full = WORKLOADS['cfg5'][0]
     t_stop = HEAT_KW['t_stop'] * (nt_sample - 1) / (nt_full - 1)          # same dt as the workload
     t0 = time.time()
