@@ -18,18 +18,17 @@ from pymgrit_b200.core.rhs_tables import RhsSplit
 _SPLITS = {}          # (id(rhs), grid) -> RhsSplit, a handful of entries
 
 
-def _shared_split(rhs, x, t):
+def _shared_split(rhs, x, t, also=()):
+    """The split of `rhs` on the grid x, valid at every time of t (and of the grids in `also`).  Levels of a hierarchy
+    (deep copies made by simple_setup_problem or separately constructed applications) share one split object, hence one
+    table of spatial factors on the device; each level validates it on its own time points (RhsSplit.validate)."""
     key = (id(rhs), len(x), float(x[0]), float(x[-1]))
     split = _SPLITS.get(key)
-    if split is not None and split.sampler.rhs is rhs:
-        if split.kind == 'separable' and split.reproduces(t):
-            return split
-        if split.kind == 'zero':
-            tt = np.asarray(t, dtype=float)
-            pick = tt[np.unique(np.round(np.linspace(0, len(tt) - 1, min(len(tt), 5))).astype(int))]
-            if not np.any(split._rows(pick)):
-                return split
-    split = RhsSplit(rhs, x).analyse(t)
+    if split is None or split.sampler.rhs is not rhs or split.kind == 'dense':
+        split = RhsSplit(rhs, x).analyse(t)
+    for grid in (t,) + tuple(also):
+        if split.validate(grid) == 'dense':
+            break
     if len(_SPLITS) > 16:
         _SPLITS.clear()
     if split.kind != 'dense':

@@ -38,7 +38,7 @@ class Heat1D2Pts(DeviceApplication):
         self.init_cond = init_cond
         self.vector_template = VectorHeat1D2Pts(self.nx, dtau)
         self.vector_t_start = VectorHeat1D2Pts(self.nx, dtau)
-        self._rhs_split = _shared_split(self.rhs, self.x, self.t)
+        self._rhs_split = _shared_split(self.rhs, self.x, self.t, also=(np.asarray(self.t, dtype=float) + dtau,))
         if self._rhs_split.kind == 'dense':
             raise Exception('the two-point heat applications need a right-hand side that is a short sum of products '
                             'X(x) T(t) (at most 4 terms); this one is not')

@@ -53,6 +53,35 @@ def test_callable_that_does_not_broadcast_falls_back_to_point_evaluation():
     assert np.max(np.abs(sp.coefficients(T) @ sp.basis - want)) <= 1e-12
 
 
+def _pulse(t):
+    return np.where((0.42 < t) & (t < 0.44), 1.0, 0.0)
+
+
+@pytest.mark.parametrize('nt', [1025, (1 << 17) + 1])           # every (x, t) compared / sampled check points, all t
+@pytest.mark.parametrize('rhs, terms', [
+    (lambda x, t: np.sin(np.pi * x) * _pulse(t), 1),                                       # nothing at the sampled times
+    (lambda x, t: np.sin(np.pi * x) * np.cos(t) + np.exp(-100 * (x - .3) ** 2) * _pulse(t), 2),   # a second shape, briefly
+])
+def test_forcing_active_only_between_the_sampled_times_is_kept(rhs, terms, nt):
+    """The reference evaluates rhs(x, t_stop) in every step (heat/heat_1d.py:214): a pulse that the dozen sampled times
+    miss must still reach the tables (it used to be classified 'zero' / rank 1)."""
+    t = np.linspace(0, 1, nt)
+    sp = RhsSplit(rhs, X).analyse(t)
+    assert sp.kind == 'separable' and sp.basis.shape[0] == terms
+    pick = np.unique(np.concatenate([np.flatnonzero(_pulse(t) > 0)[::max(1, nt // 2000)], np.arange(0, nt, max(1, nt // 50))]))
+    want = _direct(rhs, t[pick])
+    got = sp.coefficients(t)[pick] @ sp.basis
+    assert np.max(np.abs(got - want)) <= 1e-12
+
+
+def test_forcing_that_fits_no_short_split_becomes_dense():
+    def rhs(x, t):                                              # a travelling bump switched on for a while: rank > 4
+        return np.exp(-200 * (x - t) ** 2) * _pulse(t)
+    t = np.linspace(0, 1, 1025)
+    sp = RhsSplit(rhs, X).analyse(t)
+    assert sp.kind == 'dense'
+
+
 @pytest.fixture
 def fresh_pool():
     """Stop the table threads after the test: later tests fork worker processes (oracle/mgrit_oracle_mp.py)."""
