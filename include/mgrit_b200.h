@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 7
+#define MGB_ABI_VERSION 8
 
 /* application kinds (which Phi) */
 #define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
@@ -46,6 +46,11 @@ extern "C" {
 #define MGB_APP_HEAT1D_2PTS 6 /* heat/heat_1d_2pts_bdf1.py:90-117, heat_1d_2pts_bdf2.py:92-138: a time point is    */
                               /* the pair (u(t), u(t + dtau)), Phi = two Toeplitz tridiagonal solves; BDF1 or     */
                               /* BDF2 is a property of the level's step constants (see "two-point rows" below)    */
+
+#define MGB_APP_HEAT1D_SINE 7 /* heat/heat_1d.py:198-217 with the level rows kept in sine space (rows hold u S, S the   */
+                              /* orthonormal sine matrix that diagonalises the Toeplitz operator): Phi is one FMA and  */
+                              /* one multiplication per unknown; values are transformed where they enter or leave     */
+                              /* (mgb_rows_dst / mgb_rows_gemm).  See "Heat1D in sine space" below                    */
 
 /* error codes */
 #define MGB_OK 0
@@ -102,6 +107,9 @@ typedef struct mgb_level {
                             /* first tile of boundary nodes)                                      */
     const double *sig_dev;  /* HEAT2D: [pitch] fx*lambda_k + fy*mu_l per sine coefficient, the    */
                             /* Dirichlet value per boundary node, 0 in the padding; else NULL     */
+    const double *diag_dev; /* HEAT1D_SINE: [2][chunk][team_threads] thread-transposed: the       */
+                            /* eigenvalues lam_k of (a/dx^2) tridiag(-1,2,-1), then 1/(1+dt lam_k)*/
+                            /* for the level's dt (used when ndt == 1); else NULL                 */
 } mgb_level;
 
 int mgb_abi_version(void);
@@ -170,8 +178,13 @@ int mgb_down_sweep(const mgb_level *fine, const mgb_level *coarse, void *stream)
  *                        correct it too, exactly as its owner does, so that no exchange is needed before the
  *                        F-relaxation of the first interval.  On time rank 0 point 0 is the initial condition
  *                        and is never corrected (mgrit.py:723). */
+/*   MGB_CORRECT_LAST_ONLY  (with MGB_CORRECT_F_RELAX) store only the last F-point of every interval: it is all that the
+ *                        residual (mgrit.py:405-413) and the next C-relaxation read.  The solver uses it on level 0 while
+ *                        it iterates and materialises the F-points with one mgb_f_relax when the iteration stops -- the
+ *                        values are the ones the reference holds (F-points are Phi chains from the C-points). */
 #define MGB_CORRECT_F_RELAX 1
 #define MGB_CORRECT_GHOST 2
+#define MGB_CORRECT_LAST_ONLY 4
 int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t flags, void *stream);
 
 /* FAS restriction with a spatial grid transfer R != identity (mgrit.py:488-549 with a user GridTransfer,
@@ -278,6 +291,18 @@ int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const
  * times it.  One collective of 16 KB per rank instead of nranks - 1 dependent sends. */
 int mgb_heat1d_spectral_fixup(const mgb_level *lvl, const double *lam_dev, double *work_dev, const double *all_ends_dev,
                               int32_t rank, void *stream);
+
+/* ---- Heat1D in sine space (MGB_APP_HEAT1D_SINE) ------------------------------------------------------------------ */
+/* Level rows hold x = u S.  Per level: diag_dev (above), sconst_dev rows [dt, use_reciprocals, 0...] (width 8), rhs_x_dev =
+ * [nrhs][chunk][team_threads] thread-transposed X_q S, rhs_t_dev as for HEAT1D.  All sweeps above work on such levels.
+ * The sequential solve of mgrit.py:459-486 on such a level needs no transforms at all and is done time-parallel:
+ * mgb_sine_level_solve cuts the level's steps into chunks, runs every chunk's scalar recurrences from zero, combines the
+ * chunk results (value, product of the step factors) in order and reruns the chunks from their true start values:
+ *     u[i][k] = (u[i-1][k] + sum_q rhs_t[i][q] rxh[q][k]) / (1 + (t[i] - t[i-1]) lam[k]) + g[i][k],   i = 1 .. npts-1
+ * lam_dev [n], rxh_dev [nrhs][pitch] in natural order, lvl->t_dev the level's time grid.  ends_dev / zero_start as for
+ * mgb_heat1d_spectral_recur (time ranks > 0 start from zero and are fixed up by mgb_heat1d_spectral_fixup on u). */
+int mgb_sine_level_solve(const mgb_level *lvl, const double *lam_dev, const double *rxh_dev, double *ends_dev,
+                         int32_t zero_start, void *stream);
 
 /* ---- Ghost rows between time ranks over peer memory (csrc/peer.cu) ----------------------------------------- */
 /* Replaces the reference's kind-0/4 messages (mgrit.py:305-310, 510-517, 693-713: pickled vector, isend/recv) by direct

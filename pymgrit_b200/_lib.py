@@ -10,10 +10,11 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libmgrit_b200.so')
 
-APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D, APP_HEAT1D_2PTS = 1, 2, 3, 4, 5, 6
+APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D, APP_HEAT1D_2PTS, APP_HEAT1D_SINE = 1, 2, 3, 4, 5, 6, 7
 TNORM_ONE, TNORM_TWO, TNORM_INF = 1, 2, 3
-ABI_VERSION = 7
+ABI_VERSION = 8
 F_RELAX_LAST_ONLY = 1
+CORRECT_F_RELAX, CORRECT_GHOST, CORRECT_LAST_ONLY = 1, 2, 4
 DAHLQUIST_METHODS = {'BE': 0, 'FE': 1, 'TR': 2, 'MR': 3}
 
 c_double_p = C.POINTER(C.c_double)
@@ -32,7 +33,7 @@ class MgbLevel(C.Structure):
         ('rhs_x_dev', C.c_void_p), ('rhs_t_dev', C.c_void_p), ('rhs_dense_dev', C.c_void_p),
         ('t_dev', C.c_void_p),
         ('p', C.c_double * 8), ('ip', C.c_int32 * 4),
-        ('sig_dev', C.c_void_p),
+        ('sig_dev', C.c_void_p), ('diag_dev', C.c_void_p),
     ]
 
 
@@ -77,6 +78,7 @@ SYMBOLS = {
     'mgb_rows_dst': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                C.c_void_p]),
     'mgb_heat1d_spectral_recur': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    'mgb_sine_level_solve': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_heat1d_spectral_fixup': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_peer_put_row': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     'mgb_peer_wait_row': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),

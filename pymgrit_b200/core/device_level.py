@@ -20,19 +20,50 @@ def _torch():
 class _PinnedArray(np.ndarray):
     """ndarray view of a page-locked torch tensor (kept alive by the view)."""
     _owner = None
+    _slot = None
+    _base_tensor = None
+
+
+_PINNED_POOL = {}         # bytes -> list of [page-locked tensor, CUDA event of the last upload from it or None]
 
 
 def pinned_array(shape):
-    """Uninitialised float64 host array in page-locked memory (torch's caching host allocator: no cudaHostAlloc after
-    the first use of a size), so that DeviceLevel uploads it with one asynchronous copy and no staging pass."""
+    """Uninitialised float64 host array in page-locked memory, so that DeviceLevel uploads it with one asynchronous
+    copy and no staging pass.  cudaHostAlloc costs ~5 ms per megabyte-sized buffer, more than the whole solve of the
+    headline workload, so the buffers are kept in a small pool for the life of the process: a buffer is handed out again
+    once the array that used it is gone and the upload queued from it has completed (its event is waited for)."""
+    import sys
     torch = _torch()
-    ten = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
-    arr = ten.numpy().view(_PinnedArray)
-    arr._owner = ten
+    shape = tuple(int(v) for v in shape)
+    nbytes = 8 * int(np.prod(shape)) if shape else 8
+    ten = None
+    for ent in _PINNED_POOL.setdefault(nbytes, []):
+        if sys.getrefcount(ent[0]) <= 2:                # only the pool (and this call) hold it: its array was dropped
+            if ent[1] is not None:
+                ent[1].synchronize()
+                ent[1] = None
+            ten, slot = ent[0], ent
+            break
+    if ten is None:
+        ten = torch.empty((nbytes // 8,), dtype=torch.float64, pin_memory=True)
+        slot = [ten, None]
+        if len(_PINNED_POOL[nbytes]) < 4:
+            _PINNED_POOL[nbytes].append(slot)
+    view = ten.view(shape) if shape else ten
+    arr = view.numpy().view(_PinnedArray)
+    arr._owner = view
+    arr._slot = slot
+    arr._base_tensor = ten
     return arr
 
 
 def team_shape(kind, n):
+    import os
+    forced = os.environ.get('MGB_SHAPE_%d' % kind)            # experiments: "threads,chunk" for application kind `kind`
+    if forced:
+        t, e = (int(v) for v in forced.split(','))
+        if t * e >= n + (n & 1):
+            return t, e
     t, e = C.c_int32(0), C.c_int32(0)
     _lib.check(_lib.lib().mgb_team_shape(kind, n, C.byref(t), C.byref(e)), 'team_shape')
     return t.value, e.value
@@ -96,6 +127,11 @@ class DeviceLevel:
             owner = getattr(a, '_owner', None)
             if owner is not None and a.dtype == dtype:        # page-locked already: asynchronous copy, no staging
                 ten = owner.to(dev, non_blocking=True)
+                slot = getattr(a, '_slot', None)
+                if slot is not None:                           # the pool reuses the buffer after this upload has run
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    slot[1] = ev
                 self._keep.append(owner)                       # alive until the copy has run
                 self.h2d_bytes += a.nbytes
                 self._keep.append(ten)
@@ -150,6 +186,8 @@ class DeviceLevel:
         c.nrhs = int(tab.get('nrhs', 0))
         c.nsys = int(tab.get('nsys', 1))
         c.sig_dev = ptr(sig)
+        diag = up(tab.get('diag'), np.float64)
+        c.diag_dev = ptr(diag)
         self.nsys = c.nsys
         c.rhs_x_dev, c.rhs_t_dev, c.rhs_dense_dev = ptr(rhs_x), ptr(rhs_t), ptr(rhs_dense)
         c.t_dev = ptr(self.t_dev)

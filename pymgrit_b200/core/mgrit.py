@@ -29,10 +29,12 @@ from pymgrit_b200.core import partition
 class _LevelVectors:
     """`mgrit.u[lvl]`: sequence of Vector views onto the rows of a level array (row i = local point i)."""
 
-    def __init__(self, level: DeviceLevel, which: str):
-        self._level, self._which = level, which
+    def __init__(self, level: DeviceLevel, which: str, before_read=None):
+        self._level, self._which, self._before_read = level, which, before_read
 
     def _array(self):
+        if self._before_read is not None:
+            self._before_read()              # level 0: F-points that were left out while iterating are computed now
         return getattr(self._level, self._which)
 
     def __len__(self):
@@ -71,6 +73,14 @@ class Mgrit:
         logging.basicConfig(format='%(levelname)s - %(asctime)s - %(message)s', datefmt='%d-%m-%y %H:%M:%S',
                             level=logging_lvl, stream=sys.stdout)
         self._log_lvl = logging_lvl
+        self.setup_phases = []                 # (name, host milliseconds) of the constructor's phases, for profiles/
+        _t_phase = [time.perf_counter()]
+
+        def phase(name):
+            now = time.perf_counter()
+            self.setup_phases.append((name, 1e3 * (now - _t_phase[0])))
+            _t_phase[0] = now
+        self._phase = phase
 
         if transfer is None:
             transfer = [GridTransferCopy() for _ in range(len(problem) - 1)]
@@ -108,6 +118,7 @@ class Mgrit:
                             'Specify a list of values for all but the coarsest level or an integer '
                             '( used for all levels).')
 
+        problem = self._choose_representation(problem, transfer)
         # what the device path does not cover fails loudly (no per-point fallback)
         for p in problem:
             if not isinstance(p, DeviceApplication):
@@ -130,6 +141,7 @@ class Mgrit:
         # ranks have converged.  On one rank that is the global test on the same per-point norms; the rank-by-rank
         # shutdown protocol (message kind 6, sender_finished) is not built.
 
+        phase('argument checks, C-point masks, representation')
         self.comm_time = as_time_comm(comm_time)
         self.comm_space = comm_space
         self.comm_time_rank = self.comm_time.Get_rank()
@@ -151,6 +163,9 @@ class Mgrit:
                           f"the time points of one process")
 
         self.launches = 0
+        self._f_stale = False
+        import os as _os
+        self._lazy_f = _os.environ.get('MGB_LAZY_F', '1') != '0'
         self.problem = problem
         self.weight_c = weight_c
         self.lvl_max = len(problem)
@@ -189,6 +204,7 @@ class Mgrit:
         self.t = part.t_local
         self.int_start, self.int_stop = part.int_start, part.int_stop
         self.send_to, self.get_from = part.send_to, part.get_from
+        phase('partition')
         self._lv = []
         for lvl in range(self.lvl_max):
             cp = part.sweep_cpts[lvl] if lvl < self.lvl_max - 1 else None
@@ -201,6 +217,7 @@ class Mgrit:
             self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0, defer_tables=defer,
                                         zero_u=not (defer and max_iter > 0 and not (callable(output_fcn) and
                                                                                     output_lvl == 2))))
+        phase('level arrays + coarse-level tables')
         # levels whose down-sweep runs as one fused launch (mgb_down_sweep): unweighted C-relaxation, at least one
         # F-point in every interval (on every time rank), team kernels
         import os
@@ -209,7 +226,8 @@ class Mgrit:
         for lvl in range(self.lvl_max - 1):
             cp = self._lv[lvl].cpts
             ok = (weight_c == 1.0 and self._xfer[lvl] is None
-                  and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D, _lib.APP_HEAT1D_2PTS)
+                  and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D, _lib.APP_HEAT1D_2PTS,
+                                            _lib.APP_HEAT1D_SINE)
                   and (cp is None or len(cp) < 2 or int(np.min(np.diff(cp))) >= 2)
                   and os.environ.get('MGB_FUSED_DOWN', '1') != '0')
             flags.append(ok)
@@ -217,7 +235,8 @@ class Mgrit:
         self._spectral = {}
         last = self._lv[-1]
         maker = getattr(problem[-1], 'spectral_solver', None)
-        flags.append(maker is not None and last.npts >= getattr(problem[-1], 'SPECTRAL_MIN_POINTS', 1 << 30))
+        min_pts = problem[-1].spectral_min_points() if hasattr(problem[-1], 'spectral_min_points') else 1 << 30
+        flags.append(maker is not None and last.npts >= min_pts)
         flags = self.comm_time.all_true(flags)          # every rank must take the same path: one small all-reduce
         self._fused_down = flags[:-1] + [False]
         if flags[-1]:
@@ -225,7 +244,7 @@ class Mgrit:
             if sp is not None:
                 self._spectral[self.lvl_max - 1] = sp
         self.comm_time.setup_peer_exchange(self)         # ghost rows over peer memory where the ranks can (core/comm.py)
-        self.u = [_LevelVectors(lv, 'u') for lv in self._lv]
+        self.u = [_LevelVectors(lv, 'u', self._materialise_f_points if k == 0 else None) for k, lv in enumerate(self._lv)]
         self.g = [None] + [_LevelVectors(lv, 'g') for lv in self._lv[1:]]
         self.v = [None] * self.lvl_max       # never materialised: identical to the fine level's C-point rows ...
         self._rres = [None] * self.lvl_max   # ... except below a spatial transfer: v, fine residual rows, their restriction
@@ -239,10 +258,13 @@ class Mgrit:
                 self.v[lvl + 1] = _LevelVectors(coarse, 'v')
                 self._rres[lvl] = torch.zeros((ncp, fine.pitch), dtype=torch.float64, device=fine.u.device)
                 self._rresc[lvl] = torch.zeros((ncp, coarse.pitch), dtype=torch.float64, device=fine.u.device)
+        phase('path flags, coarsest solver, peer exchange')
         self._init_levels()
+        phase('initial condition')
         if nested_iteration:
             self.nested_iteration()
         self._lv[0].finish_tables()
+        phase('nested iteration queued + level-0 tables')
         dev = self._lv[0].u.device
         ncp0 = len(self._lv[0].cpts) if self._lv[0].cpts is not None else 1
         nsys0 = self._lv[0].nsys
@@ -255,7 +277,9 @@ class Mgrit:
 
         if self.iter_max == 0:
             self.comm_time.barrier()
+        phase('norm buffers')
         torch.cuda.synchronize()
+        phase('wait for the device')
         self.runtime_setup = time.time() - runtime_setup_start
 
         if self.output_fcn is not None and self.output_lvl == 2:
@@ -264,6 +288,35 @@ class Mgrit:
         self.log_info(f"Setup took {self.runtime_setup} s")
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _choose_representation(problem, transfer):
+        """A hierarchy of Heat1D levels of one spatial size connected by the identity transfer runs with its rows in sine
+        space (heat/heat_1d.py, csrc/phi.cuh Heat1DSine): Phi is then diagonal and every sweep HBM-bound.  Returns the
+        list of applications the solver runs (twins of the user's objects, or the objects themselves)."""
+        from pymgrit_b200.heat.heat_1d import Heat1D
+        if not all(type(tr) is GridTransferCopy for tr in transfer):
+            return problem
+        if not all(isinstance(p, Heat1D) and p.kind == _lib.APP_HEAT1D for p in problem):
+            return problem
+        if len({(p.nx, float(p.a), float(p.dx)) for p in problem}) != 1:
+            return problem
+        want = [p.sine_space for p in problem]
+        if not all(p.can_sine() for p in problem):
+            if any(w is True for w in want):
+                raise Exception('sine_space=True needs a zero or separable right-hand side on every level and a supported '
+                                'spatial size')
+            return problem
+        return [p.as_sine() for p in problem]
+
+    def _materialise_f_points(self):
+        """Level 0 while iterating keeps only the C-points and the last F-point of every interval up to date (all that the
+        residual and the next C-relaxation read, mgb_error_correction MGB_CORRECT_LAST_ONLY).  Before anybody looks at
+        the level -- the end of solve(), an output function, Mgrit.u[0][i] -- one F-relaxation computes the others: the
+        values the reference holds at that moment (its F-points are the Phi chains from the C-points, mgrit.py:287)."""
+        if self._f_stale:
+            self._f_stale = False
+            self.f_relax(lvl=0)
+
     def _init_levels(self):
         """mgrit.py:846-858: zero (or random) initial guess, initial condition at the first point of rank 0."""
         if self.random_init_guess:
@@ -300,6 +353,7 @@ class Mgrit:
                 lv.g.zero_()
         self.conv = np.zeros(self.iter_max + 1)
         self.solve_iter = 0
+        self._f_stale = False
         self._init_levels()
         if self.nes_it:
             self.nested_iteration()
@@ -312,13 +366,15 @@ class Mgrit:
         return (sum(lv.h2d_bytes for lv in self._lv) + 8 * self._lv[0].n * self.lvl_max +
                 sum(sp.h2d_bytes for sp in self._spectral.values()))
 
-    def time_level0_sweeps(self, repeats: int = 5):
+    def time_level0_sweeps(self, repeats: int = 5, iterations: int = 1, hbm_gbs: float = None):
         """CUDA-event timing of each level-0 sweep alone (bench.py roofline).  Per sweep: the algorithmic bytes (every
         row an interval must read or write, counted once), ms, GB/s, how often it runs per
-        iteration of this solver, and what bounds it: 'hbm', or 'fp64' for the chains that read one row and write one
-        per interval but apply m Phi in between (then `fp64_frac` = Phi applications x 251 FP64 warp instructions per
-        33 elements per Phi / the measured issue rate of the FP64 pipe, 1 warp instruction per 2.07 cycles and
-        scheduler)."""
+        iteration / per solve of this solver, and what bounds it.  Two lower bounds are computed per sweep: the
+        algorithmic bytes at the HBM peak, and -- for the heat_1d kernels, whose FP64 instruction count per Phi is known
+        from the SASS (251 per 33 unknowns for the Toeplitz solve; 1 + nrhs per unknown in sine space) -- the FP64 warp
+        instructions at the issue rate of the pipe measured by scripts/micro/fp64_latency.cu (one warp instruction per
+        2.07 cycles and scheduler; self-measured, MEASURED_PEAKS.json has no FP64 entry).  `bound` names the larger one,
+        `frac` = that bound / measured time."""
         torch = _lib_torch()
         lv = self._lv[0]
         if self.lvl_max < 2 or lv.cpts is None:
@@ -328,26 +384,42 @@ class Mgrit:
         row = 8.0 * lv.n
         fused = self._fused_down[0]
         cf = self.cf_iter[0]
+        lazy = self._lazy_f
+        its = max(1, int(iterations))
+        first_f = 1                     # the F-relaxation that opens iteration 0 (mgrit.py:274-275)
         sweeps = [
-            # name, launch, rows per interval, Phi per interval, launches per iteration, bound
-            ('f_relax', lambda: self.f_relax(0), m, m - 1, 0, 'hbm'),               # public sweep: stores every F-point
+            # name, launch, rows per interval, Phi per interval, launches per iteration, launches per solve
+            ('f_relax', lambda: self.f_relax(0), m, m - 1, 0, 1 if lazy else 0),
             ('f_relax(last point only)', lambda: self.f_relax(0, last_only=True), 2, m - 1,
-             0 if fused and cf == 1 else cf - (1 if fused else 0), 'fp64'),
+             cf - 1, first_f),
             ('c_relax', lambda: self.c_relax(0), 2 + (1 if self.weight_c != 1.0 else 0), 1,
-             cf - (1 if fused else 0), 'hbm'),
-            ('fas_residual', lambda: self.fas_residual(0), 4, 2, 0 if fused else 1, 'hbm'),
-            ('error_correction+f_relax', lambda: self.error_correction(0, f_relax=True), m + 2, m - 1, 1, 'hbm'),
-            ('residual_norms', lambda: self.compute_residual(), 2, 1, 1, 'hbm'),
+             cf - (1 if fused else 0), 0),
+            ('fas_residual', lambda: self.fas_residual(0), 4, 2, 0 if fused else 1, 0),
+            ('error_correction+f_relax', lambda: self.error_correction(0, f_relax=True), m + 2, m - 1,
+             0 if lazy else 1, 0),
+            ('error_correction+f_relax(last point only)',
+             lambda: self.error_correction(0, f_relax=True, last_only=True), 4, m - 1, 1 if lazy else 0, 0),
+            ('residual_norms', lambda: self.compute_residual(), 2, 1, 1, 0),
         ]
         if fused:
-            sweeps.insert(4, ('down_sweep(c_relax+f_relax+fas_residual)', lambda: self.down_sweep(0), 4, m + 3, 1, 'fp64'))
+            sweeps.insert(4, ('down_sweep(c_relax+f_relax+fas_residual)', lambda: self.down_sweep(0), 4, m + 3, 1, 0))
+        else:
+            sweeps[1] = sweeps[1][:4] + (cf, first_f)
         props = torch.cuda.get_device_properties(lv.u.device)
         sms = props.multi_processor_count
         clock_hz = float(getattr(props, 'clock_rate', 1965000)) * 1e3          # maximum SM clock (kHz -> Hz)
         fp64_peak = sms * 4 * clock_hz / 2.07            # FP64 warp instructions per second (scripts/micro/fp64_latency.cu)
-        team_elems = self._lv[0].team_threads * self._lv[0].chunk
+        kind = self.problem[0].kind
+        nrhs = int(lv.c.nrhs)
+        if kind == _lib.APP_HEAT1D:
+            per_elem = 251.0 / 33.0
+        elif kind == _lib.APP_HEAT1D_SINE:
+            per_elem = 1.0 + nrhs
+        else:
+            per_elem = None
+        team_elems = lv.team_threads * lv.chunk * max(1, lv.nsys)
         out = []
-        for name, fn, rows, nphi, per_iter, bound in sweeps:
+        for name, fn, rows, nphi, per_iter, per_solve in sweeps:
             fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -358,12 +430,22 @@ class Mgrit:
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / repeats
             nbytes = rows * k0 * row
-            # 251 FP64 warp instructions per Phi of a 32 x 33 team (ncu source view); scaled by the team size
-            fp64_instr = nphi * k0 * 251.0 * team_elems / (32 * 33)
-            out.append({'name': name, 'bound': bound, 'rows_per_interval': rows, 'phi_per_interval': nphi, 'intervals': k0,
-                        'algorithmic_bytes': nbytes, 'ms': ms, 'gbs': nbytes / (ms * 1e-3) / 1e9,
-                        'fp64_frac': fp64_instr / (ms * 1e-3) / fp64_peak, 'launches_per_iteration': per_iter,
-                        'share_ms': ms * per_iter})
+            ent = {'name': name, 'rows_per_interval': rows, 'phi_per_interval': nphi, 'intervals': k0,
+                   'algorithmic_bytes': nbytes, 'ms': ms, 'gbs': nbytes / (ms * 1e-3) / 1e9,
+                   'launches_per_iteration': per_iter, 'launches_per_solve': per_solve,
+                   'share_ms': ms * (per_iter * its + per_solve)}
+            t_hbm = nbytes / (hbm_gbs * 1e9) * 1e3 if hbm_gbs else None
+            t_fp = None
+            if per_elem is not None:
+                fp64_instr = nphi * k0 * per_elem * team_elems / 32.0       # warp instructions
+                t_fp = fp64_instr / fp64_peak * 1e3
+                ent['fp64_frac'] = t_fp / ms
+            if t_hbm is not None:
+                ent['hbm_frac'] = t_hbm / ms
+            ent['bound'] = 'fp64' if (t_fp is not None and t_hbm is not None and t_fp > t_hbm) else 'hbm'
+            ent['frac'] = max(v for v in (t_hbm, t_fp) if v is not None) / ms if (t_hbm or t_fp) else None
+            out.append(ent)
+        self.restart_needed = True
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -388,7 +470,12 @@ class Mgrit:
         if not fused:
             self.fas_residual(lvl=lvl)
         self.iteration(lvl=lvl + 1, cycle_type=cycle_type, iteration=iteration, first_f=True)
-        self.error_correction(lvl=lvl, f_relax=True)        # correction + the F-relaxation of mgrit.py:287, one launch
+        # correction + the F-relaxation of mgrit.py:287, one launch; on level 0 only the last F-point of every interval
+        # is stored while the solver iterates (_materialise_f_points)
+        lazy = lvl == 0 and self._lazy_f and self.lvl_max > 1
+        self.error_correction(lvl=lvl, f_relax=True, last_only=lazy)
+        if lazy:
+            self._f_stale = True
         if lvl != 0 and cycle_type == 'F':
             self.iteration(lvl=lvl, cycle_type='V', iteration=iteration, first_f=False)
 
@@ -419,8 +506,8 @@ class Mgrit:
             _lib.check(lib.mgb_fas_coarse_rhs(coarse.ref, coarse.v.data_ptr(), self._rresc[lvl].data_ptr(), ncp,
                                               self._stream()), 'fas_coarse_rhs')
             return
-        if coarse.npts > 0 and fine.npts > 0:
-            coarse.u[0].copy_(fine.u[0])             # the ghost / initial C-point is injected like any other
+        if coarse.npts > 0 and fine.npts > 0 and len(fine.cpts) < 2:
+            coarse.u[0].copy_(fine.u[0])             # no interval: the kernel (which injects point 0 too) has no work
         _lib.check(_lib.lib().mgb_fas_residual(fine.ref, coarse.ref, self._stream()), 'fas_residual')
 
     def down_sweep(self, lvl: int) -> None:
@@ -432,12 +519,13 @@ class Mgrit:
             if self.comm_time_rank + 1 < self.comm_time_size and fine.npts > 1:
                 _lib.check(_lib.lib().mgb_c_relax_last(fine.ref, 1.0, self._stream()), 'c_relax_last')
             self._exchange_ghost(lvl)
-        if coarse.npts > 0 and fine.npts > 0:
-            coarse.u[0].copy_(fine.u[0])
+        if coarse.npts > 0 and fine.npts > 0 and len(fine.cpts) < 2:
+            coarse.u[0].copy_(fine.u[0])             # no interval: the kernel (which injects point 0 too) has no work
         _lib.check(_lib.lib().mgb_down_sweep(fine.ref, coarse.ref, self._stream()), 'down_sweep')
 
-    def error_correction(self, lvl: int, f_relax: bool = False) -> None:
-        """Coarse-grid correction of the C-points (mgrit.py:715-726), optionally fused with the next F-relaxation."""
+    def error_correction(self, lvl: int, f_relax: bool = False, last_only: bool = False) -> None:
+        """Coarse-grid correction of the C-points (mgrit.py:715-726), optionally fused with the next F-relaxation
+        (last_only: of which only the last point of every interval is stored)."""
         xfer = self._xfer[lvl]
         if xfer is not None:
             fine, coarse = self._lv[lvl], self._lv[lvl + 1]
@@ -445,9 +533,10 @@ class Mgrit:
             xfer.interpolate_rows(len(fine.cpts), first, coarse.u, coarse.v, fine.u, fine.cpts_dev, True, coarse.app)
             self.launches += 1
             if f_relax:
-                self.f_relax(lvl)
+                self.f_relax(lvl, last_only=last_only)
             return
-        flags = (1 if f_relax else 0) | (2 if self.comm_time_rank > 0 else 0)      # MGB_CORRECT_F_RELAX | MGB_CORRECT_GHOST
+        flags = ((_lib.CORRECT_F_RELAX if f_relax else 0) | (_lib.CORRECT_GHOST if self.comm_time_rank > 0 else 0) |
+                 (_lib.CORRECT_LAST_ONLY if f_relax and last_only else 0))
         _lib.check(_lib.lib().mgb_error_correction(self._lv[lvl].ref, self._lv[lvl + 1].ref, flags, self._stream()),
                    'error_correction')
         # no exchange: every rank corrects its ghost copy itself (MGB_CORRECT_GHOST)
@@ -464,14 +553,7 @@ class Mgrit:
             _lib.check(_lib.lib().mgb_forward_solve(lv.ref, self._stream()), 'forward_solve')
             self.comm_time.send_chain(self, lvl)
             return
-        sp.transform_in()
-        if self.comm_time_size > 1:
-            sp.recur_time_parallel(self.comm_time)
-            self.launches += 1 if self.comm_time_rank > 0 else 0
-        else:
-            sp.recur()
-        sp.transform_out(first_row=0 if self.comm_time_rank > 0 else 1)
-        self.launches += 3
+        self.launches += sp.solve(self.comm_time)
 
     def nested_iteration(self) -> None:
         """Coarsest solve, then interpolate upwards with a V-cycle per level (mgrit.py:551-566)."""
@@ -576,10 +658,12 @@ class Mgrit:
                               '{0: <35}'.format(f" | runtime: {time_it_stop - time_it_start} s"))
 
             if self.output_fcn is not None and self.output_lvl == 2:
+                self._materialise_f_points()
                 self.output_fcn(self)
 
             if self.conv[iteration + 1] < self.tol or iteration == self.iter_max - 1:
                 break
+        self._materialise_f_points()
         torch.cuda.synchronize()
         self.comm_time.barrier()
         self.runtime_solve = time.time() - runtime_solve_start

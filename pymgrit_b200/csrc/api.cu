@@ -52,6 +52,7 @@ const DeviceInfo *device_info() {
 #define MGB_APP_Advection1D MGB_APP_ADVECTION1D
 #define MGB_APP_Heat2D MGB_APP_HEAT2D
 #define MGB_APP_Heat1D2Pts MGB_APP_HEAT1D_2PTS
+#define MGB_APP_Heat1DSine MGB_APP_HEAT1D_SINE
 #define MGB_SHAPE(APP, T, E) const SweepTable *mgb_table_##APP##_##T##_##E();
 #include "shapes.inc"
 #undef MGB_SHAPE
@@ -100,6 +101,16 @@ static int check_level(const mgb_level *l, const SweepTable **tab, LevelDev *out
             return fail(MGB_EINVAL, "missing right-hand-side tables%s");
         if (l->rhs_dense_dev != nullptr)
             return fail(MGB_EINVAL, "two-point heat levels take a separable right-hand side only%s");
+    } else if (l->app == MGB_APP_HEAT1D_SINE) {
+        if (l->pitch % 2) return fail(MGB_EINVAL, "pitch must be even%s (got %ld)", "", l->pitch);
+        if ((long)l->team_threads * l->chunk < l->pitch)
+            return fail(MGB_EINVAL, "team shape%s %ld x %ld does not cover a row", "", l->team_threads, l->chunk);
+        if (l->diag_dev == nullptr || l->sconst_dev == nullptr || l->ndt < 1 || (l->ndt > 1 && l->dtidx_dev == nullptr))
+            return fail(MGB_EINVAL, "missing eigenvalue or step-constant table of a sine-space level%s");
+        if (l->nrhs > 0 && (l->rhs_x_dev == nullptr || l->rhs_t_dev == nullptr))
+            return fail(MGB_EINVAL, "missing right-hand-side tables%s");
+        if (l->rhs_dense_dev != nullptr)
+            return fail(MGB_EINVAL, "sine-space heat levels take a separable right-hand side only%s");
     } else if (!tiny) {
         if (l->pitch % 2) return fail(MGB_EINVAL, "pitch must be even%s (got %ld)", "", l->pitch);
         if ((long)l->team_threads * l->chunk < l->pitch)
@@ -134,6 +145,7 @@ static int check_level(const mgb_level *l, const SweepTable **tab, LevelDev *out
     out->tile = multi ? l->team_threads * l->chunk : l->pitch;
     out->nrow = (l->app == MGB_APP_HEAT1D_2PTS) ? l->pitch : l->n;  // doubles of a row the row-wise helpers touch
     out->sig = multi ? l->sig_dev : nullptr;
+    out->diag = (l->app == MGB_APP_HEAT1D_SINE) ? l->diag_dev : nullptr;
     if (multi) out->n = out->tile;
     if (tiny && l->t_dev == nullptr) return fail(MGB_EINVAL, "ODE applications need the time grid t_dev%s");
     return MGB_OK;
@@ -300,7 +312,7 @@ int mgb_team_shape(int32_t app, int32_t n, int32_t *team_threads, int32_t *chunk
 }
 
 int mgb_step_consts_width(int32_t app, int32_t team_threads, int32_t chunk) {
-    if (app == MGB_APP_HEAT2D) return 8;  // [0] dt
+    if (app == MGB_APP_HEAT2D || app == MGB_APP_HEAT1D_SINE) return 8;  // [0] dt
     if (app == MGB_APP_HEAT1D_2PTS) return 2 * mgb_heat1d_2pts_half_width(team_threads, chunk) + 8;
     const int sub = (chunk % 3 == 0) ? 3 : 1;
     return kScalarConsts + team_threads * (2 + 2 * sub);
@@ -421,7 +433,8 @@ int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t
     LevelDev G;
     if (int rc = check_level(coarse, &tab2, &G)) return rc;
     if (int rc = check_pair(fine, coarse)) return rc;
-    return tab->correct(L, G, (flags & MGB_CORRECT_F_RELAX) ? 1 : 0, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
+    const int frelax = (flags & MGB_CORRECT_F_RELAX) ? ((flags & MGB_CORRECT_LAST_ONLY) ? 2 : 1) : 0;
+    return tab->correct(L, G, frelax, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
 }
 
 int mgb_forward_solve(const mgb_level *lvl, void *stream) {

@@ -118,7 +118,9 @@ struct Launch {
 
     static int correct(const LevelDev &L, const LevelDev &G, int frelax, int kfirst, cudaStream_t st) {
         if (L.ncpts < 1) return 0;
-        const int nin = 3 + rows_extra(L), nw = L.ncpts * nsys(L);
+        // every F-point stored: the sweep is a stream of rows, three input slots keep the loads ahead; last point only: two
+        // rows in per interval, fewer slots leave room for more resident teams
+        const int nin = (frelax == 2 ? 2 : 3) + rows_extra(L), nw = L.ncpts * nsys(L);
         int grid;
         if (int rc = grid_for(k_correct<Phi>, nw, nin, &grid)) return rc;
         k_correct<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, frelax, kfirst, nw, nin);

@@ -45,6 +45,7 @@ struct LevelDev {
     int tile;
     int nrow;
     const double *sig;  // [pitch] per-element symbol of the spatial operator (Heat2D), row layout; NULL otherwise
+    const double *diag; // Heat1DSine: [2][E][T] thread-transposed eigenvalues lam_k and reciprocals 1/(1 + dt lam_k)
 };
 
 // Applications without per-element item data
@@ -69,6 +70,9 @@ struct SubSplit {
 template <int T_, int E_>
 struct Heat1D {
     using SH = Shape<T_, E_>;
+    static constexpr bool kTightChain = false;
+    static constexpr bool kCtArg = false;
+    static constexpr bool kItemInvariant = true;  // begin_item depends on the level only, not on the work item
     static constexpr int T = T_, E = E_;
     static constexpr int SUB = SubSplit<E_>::SUB, SL = SubSplit<E_>::SL;
     static constexpr int PT = 2 + 2 * SUB;
@@ -129,7 +133,7 @@ struct Heat1D {
     }
 
     template <class TeamT>
-    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &it, const LevelDev &L, int i,
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, Item &it, const LevelDev &L, int i,
                                                  TeamT &team) {
         const int tid = team.tid;
         // b = u + dt * rhs(x, t_i)                                           heat_1d.py:214
@@ -253,6 +257,9 @@ struct Heat1D {
 template <int T_, int E_>
 struct Heat1D2Pts {
     using SH = Shape<T_, E_>;
+    static constexpr bool kTightChain = false;
+    static constexpr bool kCtArg = false;
+    static constexpr bool kItemInvariant = true;  // begin_item depends on the level only, not on the work item
     static constexpr int T = T_, E = E_;
     static constexpr int EH = (E_ - 1) / 2;
     using H = Heat1D<T_, EH>;
@@ -309,7 +316,7 @@ struct Heat1D2Pts {
     }
 
     template <class TeamT>
-    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &it, const LevelDev &L, int i,
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, Item &it, const LevelDev &L, int i,
                                                  TeamT &team) {
         const int tid = team.tid;
         const int nv = L.n - tid * EH;
@@ -344,6 +351,9 @@ struct Heat1D2Pts {
 template <int T_, int E_>
 struct Advection1D {
     using SH = Shape<T_, E_>;
+    static constexpr bool kTightChain = false;
+    static constexpr bool kCtArg = false;
+    static constexpr bool kItemInvariant = true;  // begin_item depends on the level only, not on the work item
     static constexpr int T = T_, E = E_;
     static constexpr int SUB = SubSplit<E_>::SUB, SL = SubSplit<E_>::SL;
     static constexpr int PT = 2 + 2 * SUB;
@@ -378,7 +388,7 @@ struct Advection1D {
     __device__ static __forceinline__ void retarget_item(Item &, const LevelDev &, const LevelDev &, TeamT &) {}
 
     template <class TeamT>
-    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &, const LevelDev &L, int i,
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, Item &, const LevelDev &L, int i,
                                                  TeamT &team) {
         const int tid = team.tid;
         const int last = L.n - 1;
@@ -450,6 +460,9 @@ constexpr int kHeat2DMaxTerms = 3;
 template <int T_, int E_>
 struct Heat2D {
     using SH = Shape<T_, E_>;
+    static constexpr bool kTightChain = false;
+    static constexpr bool kCtArg = false;
+    static constexpr bool kItemInvariant = false;  // begin_item depends on the level only, not on the work item
     static constexpr int T = T_, E = E_;
     static constexpr int QMAX = kHeat2DMaxTerms;
 
@@ -482,8 +495,8 @@ struct Heat2D {
     __device__ static __forceinline__ void retarget_item(Item &, const LevelDev &, const LevelDev &, TeamT &) {}
 
     template <class TeamT>
-    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, const Item &it, const LevelDev &L, int i,
-                                                 TeamT &) {
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, Item &it, const LevelDev &L, int i,
+                                                 TeamT &team) {
         if (it.boundary) {
 #pragma unroll
             for (int j = 0; j < E; ++j) x[j] = it.sig[j];
@@ -505,6 +518,150 @@ struct Heat2D {
 #pragma unroll
             for (int j = 0; j < E; ++j) x[j] = __ddiv_rn(x[j], fma(c.dt, it.sig[j], 1.0));
         }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Heat1DSine: Heat1D (heat/heat_1d.py:198-217) with the level rows kept in sine space.
+//
+// L = (a/dx^2) tridiag(-1, 2, -1) is diagonalised by the orthonormal sine matrix S (S = S^T = S^-1, spectral.cu):
+// L = S diag(lam) S.  Every operation of MGRIT on level rows (sums, differences, injection, 2-norms, ghost copies) is
+// linear or orthogonally invariant, so a hierarchy whose rows hold  x = u S  instead of u runs the same algorithm, and
+//     Phi(x)_k = (x_k + sum_q ct_q(i) rxh_q[k]) / (1 + dt_i lam_k)
+// is one FMA and one multiplication per unknown instead of the 7.6 FP64 instructions of the Toeplitz solve: the sweeps
+// become HBM-bound.  It is the same direct solve of the same linear system as the reference's spsolve, with a different
+// order of rounding errors (tests: <= 1e-12 relative against the tridiagonal kernels).  Values are transformed only
+// where they enter or leave (initial condition, spatial right-hand-side factors, Mgrit.u[l][i].get_values()).
+//   diag (per level): [0][j*T + tid] = lam_k, [1][j*T + tid] = 1/(1 + dt lam_k) for the level's dt, k = tid*E + j
+//   step-constant row: [0] dt  [1] != 0: the level is uniform in time, use the reciprocals (else divide per step)
+//   rhs_x: [nrhs][E][T] thread-transposed rxh_q = X_q S
+// ---------------------------------------------------------------------------------------------
+template <int T_, int E_>
+struct Heat1DSine {
+    using SH = Shape<T_, E_>;
+    static constexpr int T = T_, E = E_;
+    static constexpr bool kItemInvariant = true;
+
+    struct C {
+        double dt;
+        bool recip;
+    };
+    struct Item {
+        double d[E];        // 1/(1 + dt lam) (uniform level) or lam, of the level the item was begun for
+        double rx0[E];      // first spatial right-hand-side factor
+        const double *dsrc; // the table d was loaded from: a step of another level (the coarse step of the FAS restriction)
+                            // reads its factors straight from that level's table instead of evicting these registers
+    };
+    __device__ static __forceinline__ int row_n(const LevelDev &L) { return L.n; }
+
+    __device__ static __forceinline__ void load_consts(C &c, const double *__restrict__ row, int) {
+        c.dt = __ldg(row);
+        c.recip = __ldg(row + 1) != 0.0;
+    }
+    __device__ static __forceinline__ const double *dtable(const LevelDev &L) { return L.diag + (L.ndt == 1 ? T * E : 0); }
+    template <class Pipe, class TeamT>
+    __device__ static __forceinline__ void begin_item(Item &it, const LevelDev &L, int, Pipe &, TeamT &team) {
+        it.dsrc = dtable(L);
+        const double *__restrict__ d = it.dsrc + team.tid;
+#pragma unroll
+        for (int j = 0; j < E; ++j) it.d[j] = __ldg(d + j * T);
+        if (L.nrhs > 0) {
+            const double *__restrict__ rx = L.rhs_x + team.tid;
+#pragma unroll
+            for (int j = 0; j < E; ++j) it.rx0[j] = __ldg(rx + j * T);
+        }
+    }
+    template <class TeamT>
+    __device__ static __forceinline__ void retarget_item(Item &it, const LevelDev &from, const LevelDev &to, TeamT &team) {
+        if (to.nrhs > 0 && to.rhs_x != from.rhs_x) {
+            const double *__restrict__ rx = to.rhs_x + team.tid;
+#pragma unroll
+            for (int j = 0; j < E; ++j) it.rx0[j] = __ldg(rx + j * T);
+        }
+    }
+
+    // Time factor of the first right-hand-side term for step i, loaded ahead of the step (the load is a dependent L2
+    // access of several hundred cycles that the few resident warps cannot hide once Phi is this cheap).
+    static constexpr bool kCtArg = true;
+    __device__ static __forceinline__ double ct_load(const LevelDev &L, int i) {
+        return L.nrhs > 0 ? __ldg(L.rhs_t + (size_t)i * L.nrhs) : 0.0;
+    }
+
+    // Steps i0 .. i1-1 of a level without g rows and without a dense right-hand side, nothing stored in between (the
+    // F-relaxations of a down-sweep).  Uniform level, at most one right-hand-side term: the time factors of 32 steps come
+    // with ONE coalesced load per warp (lane l holds step base + l; the next 32 are in flight while these are used) and a
+    // step is a shuffle, E FMAs and E multiplications -- nothing else in the loop.  Same arithmetic as apply().
+    // chain_prefetch() issues the first of those loads; call it before waiting for the item's rows.
+    static constexpr bool kTightChain = true;
+    __device__ static __forceinline__ bool chain_ok(const C &c, const LevelDev &L) {
+        return c.recip && L.ndt == 1 && L.nrhs <= 1;
+    }
+    __device__ static __forceinline__ double chain_prefetch(const LevelDev &L, int i0, int i1, int lane) {
+        return (L.nrhs == 1 && i0 + lane < i1) ? __ldg(L.rhs_t + i0 + lane) : 0.0;
+    }
+    template <class TeamT>
+    __device__ static __forceinline__ void chain(double (&x)[E], const C &c, Item &it, const LevelDev &L, int i0, int i1,
+                                                 TeamT &team, double first) {
+        if (L.nrhs == 0) {
+            for (int i = i0; i < i1; ++i) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) x[j] = x[j] * it.d[j];
+            }
+            return;
+        }
+        const double *__restrict__ ctp = L.rhs_t;
+        double nxt = first;
+        for (int base = i0; base < i1; base += 32) {
+            const double cur = nxt;
+            const int nb = base + 32 + team.lane;
+            nxt = (nb < i1) ? __ldg(ctp + nb) : 0.0;
+            const int cnt = min(32, i1 - base);
+#pragma unroll 1
+            for (int s = 0; s < cnt; ++s) {
+                const double ct = __shfl_sync(0xffffffffu, cur, s);
+#pragma unroll
+                for (int j = 0; j < E; ++j) x[j] = fma(ct, it.rx0[j], x[j]) * it.d[j];
+            }
+        }
+    }
+
+    template <class TeamT>
+    __device__ static __forceinline__ void apply_ct(double (&x)[E], const C &c, Item &it, const LevelDev &L, int i,
+                                                    TeamT &team, const double ct0) {
+        if (L.nrhs > 0) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) x[j] = fma(ct0, it.rx0[j], x[j]);
+        }
+        for (int k = 1; k < L.nrhs; ++k) {
+            const double ct = __ldg(L.rhs_t + (size_t)i * L.nrhs + k);
+            const double *__restrict__ rx = L.rhs_x + (size_t)k * E * T + team.tid;
+#pragma unroll
+            for (int j = 0; j < E; ++j) x[j] = fma(ct, __ldg(rx + j * T), x[j]);
+        }
+        const double *dt = dtable(L);
+        if (dt == it.dsrc) {
+            if (c.recip) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) x[j] = x[j] * it.d[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < E; ++j) x[j] = __ddiv_rn(x[j], fma(c.dt, it.d[j], 1.0));
+            }
+        } else {  // a step of another level than the item's: its factors straight from the table
+            const double *__restrict__ d = dt + team.tid;
+            if (c.recip) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) x[j] = x[j] * __ldg(d + j * T);
+            } else {
+#pragma unroll
+                for (int j = 0; j < E; ++j) x[j] = __ddiv_rn(x[j], fma(c.dt, __ldg(d + j * T), 1.0));
+            }
+        }
+    }
+    template <class TeamT>
+    __device__ static __forceinline__ void apply(double (&x)[E], const C &c, Item &it, const LevelDev &L, int i,
+                                                 TeamT &team) {
+        apply_ct(x, c, it, L, i, team, ct_load(L, i));
     }
 };
 

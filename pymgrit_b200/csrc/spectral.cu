@@ -172,86 +172,111 @@ __global__ void __launch_bounds__(256) k_rows_dst(const int nrows, const int n, 
     }
 }
 
-// In-place scalar recurrences over the rows of W (sine space), one thread per mode k:
-//   W[i][k] = (W[i-1][k] + sum_q rhs_t[i][q] rxh[q][k]) / (1 + (t[i] - t[i-1]) lam[k]) + W[i][k],   i = 1 .. npts-1.
-// Rows are consumed in batches of UN: the next batch's loads are issued (and nothing waits for them) before this batch's
-// reciprocals, right-hand-side sums and dependent chain (one add, one FMA per step) run.
-constexpr int kSpectralMaxTerms = 4;
-constexpr int UN = 8;
-
-template <int NRHS>
-struct RecurBatch {
-    double w[UN], tv[UN + 1], ct[UN][NRHS > 0 ? NRHS : 1];
-    // raw loads of rows i0 .. i0+UN-1 (all in range): issued back to back, nothing consumes them here
-    __device__ __forceinline__ void load(const double *__restrict__ W, int pitch, int k, const double *__restrict__ t,
-                                         const double *__restrict__ rhs_t, int i0) {
-#pragma unroll
-        for (int j = 0; j < UN; ++j) w[j] = W[(long)(i0 + j) * pitch + k];
-#pragma unroll
-        for (int j = 0; j <= UN; ++j) tv[j] = __ldg(t + i0 - 1 + j);
-#pragma unroll
-        for (int j = 0; j < UN; ++j)
-#pragma unroll
-            for (int q = 0; q < NRHS; ++q) ct[j][q] = __ldg(rhs_t + (long)(i0 + j) * NRHS + q);
-    }
-};
-
-// ends != nullptr (time rank > 0 of a time-parallel solve): the recurrence starts from 0 instead of W[0] and the kernel
-// also returns, in ends[0][k] and ends[1][k], its last value and the product of all its step factors 1 / (1 + dt_i lam_k):
-// with them every rank can work out the true value at its slab start without waiting for its predecessors' recurrences
+// The scalar recurrences of the sine-space solve, one per mode k, time-parallel:
+//   U[i][k] = (U[i-1][k] + sum_q rhs_t[i][q] rxh[q][k]) / (1 + (t[i] - t[i-1]) lam[k]) + G[i][k],   i = 1 .. npts-1
+// (G == U: in place on work rows that hold the transformed g; G == nullptr: no g, level 0).  A step is the affine map
+// u -> A u + B with A = 1/(1 + dt lam): a CTA holds 32 modes x NCH chunks of `len` consecutive steps;
+//   pass 1  every (mode, chunk) thread composes the maps of its chunk from (A, B) = (1, 0) -> shared memory
+//   combine every thread pushes the start value U[0][k] through the chunks before its own (<= NCH - 1 FMAs)
+//   pass 2  the chunk's steps are rerun from the true start value and stored: the values are those of the sequential
+//           recurrence up to the rounding of the chunk start values.
+// 2 len + NCH dependent steps instead of npts - 1: 1025 points in 32 chunks -> 96 instead of 1024.
+// ends != nullptr (time rank > 0 of a time-parallel solve): the recurrence starts from 0 instead of U[0] (zero_start) and
+// the kernel also returns, in ends[0][k] and ends[1][k], its last value and the product of all its step factors: with
+// them every rank can work out the true value at its slab start without waiting for its predecessors' recurrences
 // (k_spectral_fixup).  On rank 0 ends[1] is not needed; ends[0] is the true last value.
-template <int NRHS>
-__global__ void __launch_bounds__(128) k_spectral_recur(double *__restrict__ W, int pitch, int n, int npts,
-                                                        const double *__restrict__ t, const double *__restrict__ lam,
-                                                        const double *__restrict__ rhs_t, const double *__restrict__ rxh,
-                                                        double *__restrict__ ends, int zero_start) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const double lk = lam[k];
-    double rx[NRHS > 0 ? NRHS : 1];
+constexpr int kSpectralMaxTerms = 4;
+constexpr int UN = 8;   // steps per batch of the fix-up pass
+constexpr int kMaxChunks = 32;
+
+template <int NRHS, bool STORE>
+__device__ __forceinline__ void sine_chunk(double &u, double &prod, double *__restrict__ U, const double *__restrict__ G,
+                                           const int pitch, const int k, const bool act, const int i0, const int i1,
+                                           const double *__restrict__ t, const double lk, const double *__restrict__ rhs_t,
+                                           const double (&rx)[NRHS > 0 ? NRHS : 1]) {
+    constexpr int B = 4;
+    int i = i0;
+    for (; i + B <= i1; i += B) {
+        double gv[B], tv[B + 1], ct[B][NRHS > 0 ? NRHS : 1];
 #pragma unroll
-    for (int q = 0; q < NRHS; ++q) rx[q] = rxh[(long)q * pitch + k];
-    double u = zero_start ? 0.0 : W[k];
-    double prod = 1.0;
-    const int nfull = (npts - 1) / UN;  // batches of UN steps; the remainder is stepped one by one below
-    RecurBatch<NRHS> cur, nxt;
-    if (nfull > 0) cur.load(W, pitch, k, t, rhs_t, 1);
-    for (int b = 0; b < nfull; ++b) {
-        const int i0 = 1 + b * UN;
-        if (b + 1 < nfull) nxt.load(W, pitch, k, t, rhs_t, i0 + UN);
-        // off the dependent chain: reciprocal denominators and right-hand-side sums of this batch
-        double inv[UN], s[UN];
+        for (int j = 0; j < B; ++j) gv[j] = G ? G[(long)(i + j) * pitch + k] : 0.0;
 #pragma unroll
-        for (int j = 0; j < UN; ++j) {
-            inv[j] = __drcp_rn(fma(__dsub_rn(cur.tv[j + 1], cur.tv[j]), lk, 1.0));
+        for (int j = 0; j <= B; ++j) tv[j] = __ldg(t + i - 1 + j);
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+#pragma unroll
+            for (int q = 0; q < NRHS; ++q) ct[j][q] = __ldg(rhs_t + (long)(i + j) * NRHS + q);
+        double inv[B], sm[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            inv[j] = __drcp_rn(fma(__dsub_rn(tv[j + 1], tv[j]), lk, 1.0));
             double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q < NRHS; ++q) acc = fma(cur.ct[j][q], rx[q], acc);
-            s[j] = acc;
+            for (int q = 0; q < NRHS; ++q) acc = fma(ct[j][q], rx[q], acc);
+            sm[j] = acc;
         }
 #pragma unroll
-        for (int j = 0; j < UN; ++j) {
-            u = fma(__dadd_rn(u, s[j]), inv[j], cur.w[j]);
-            W[(long)(i0 + j) * pitch + k] = u;
+        for (int j = 0; j < B; ++j) {
+            u = fma(__dadd_rn(u, sm[j]), inv[j], gv[j]);
+            if (STORE) {
+                if (act) U[(long)(i + j) * pitch + k] = u;
+            } else {
+                prod *= inv[j];
+            }
         }
-        if (ends != nullptr) {
-#pragma unroll
-            for (int j = 0; j < UN; ++j) prod *= inv[j];
-        }
-        cur = nxt;
     }
-    for (int i = 1 + nfull * UN; i < npts; ++i) {
+    for (; i < i1; ++i) {
         const double inv = __drcp_rn(fma(__dsub_rn(__ldg(t + i), __ldg(t + i - 1)), lk, 1.0));
         double acc = 0.0;
 #pragma unroll
         for (int q = 0; q < NRHS; ++q) acc = fma(__ldg(rhs_t + (long)i * NRHS + q), rx[q], acc);
-        u = fma(__dadd_rn(u, acc), inv, W[(long)i * pitch + k]);
-        W[(long)i * pitch + k] = u;
-        prod *= inv;
+        u = fma(__dadd_rn(u, acc), inv, G ? G[(long)i * pitch + k] : 0.0);
+        if (STORE) {
+            if (act) U[(long)i * pitch + k] = u;
+        } else {
+            prod *= inv;
+        }
     }
-    if (ends != nullptr) {
+}
+
+template <int NRHS>
+__global__ void __launch_bounds__(1024) k_sine_solve(double *__restrict__ U, const double *G, const int pitch, const int n,
+                                                     const int npts, const double *__restrict__ t,
+                                                     const double *__restrict__ lam, const double *__restrict__ rhs_t,
+                                                     const double *__restrict__ rxh, double *__restrict__ ends,
+                                                     const int zero_start, const int len) {
+    __shared__ double sA[kMaxChunks][32], sB[kMaxChunks][32];
+    const int tx = threadIdx.x, c = threadIdx.y, nch = blockDim.y;
+    const int kreal = blockIdx.x * 32 + tx;
+    const bool act = kreal < n;
+    const int k = act ? kreal : n - 1;  // idle lanes of the last CTA shadow mode n-1 and store nothing
+    const double lk = lam[k];
+    double rx[NRHS > 0 ? NRHS : 1];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) rx[q] = rxh[(long)q * pitch + k];
+    const int i0 = min(npts, 1 + c * len), i1 = min(npts, i0 + len);
+    double a = 1.0, b = 0.0;
+    if (nch > 1) {
+        sine_chunk<NRHS, false>(b, a, U, G, pitch, k, act, i0, i1, t, lk, rhs_t, rx);
+        sA[c][tx] = a;
+        sB[c][tx] = b;
+        __syncthreads();
+    }
+    double u = zero_start ? 0.0 : U[k];
+    for (int cc = 0; cc < c; ++cc) u = fma(sA[cc][tx], u, sB[cc][tx]);
+    double unused = 1.0;
+    sine_chunk<NRHS, true>(u, unused, U, G, pitch, k, act, i0, i1, t, lk, rhs_t, rx);
+    if (ends != nullptr && act && i1 == npts && (i0 < npts || c == 0)) {
+        // the thread that made the last step (or, on a level of one point, chunk 0) reports the end value ...
         ends[k] = u;
-        ends[pitch + k] = prod;
+        double p = 1.0;  // ... and the product of all step factors
+        if (nch > 1) {
+            for (int cc = 0; cc < nch; ++cc) p *= sA[cc][tx];
+        } else {
+            // single chunk: pass 1 was skipped, redo the product
+            for (int i = i0; i < i1; ++i) p *= __drcp_rn(fma(__dsub_rn(__ldg(t + i), __ldg(t + i - 1)), lk, 1.0));
+        }
+        ends[pitch + k] = p;
     }
 }
 
@@ -353,6 +378,29 @@ int mgb_rows_dst(int32_t m, int32_t n, const double *a_dev, int32_t lda, const d
     return cuda_fail(cudaGetLastError(), "rows_dst");
 }
 
+static int launch_sine_solve(double *U, const double *G, int pitch, int n, int npts, const double *t, const double *lam,
+                             const double *rhs_t, int nrhs, const double *rxh, double *ends, int zero_start, cudaStream_t st) {
+    const int steps = npts - 1;
+    int nch = steps / 8;  // at least 8 steps per chunk
+    if (nch > kMaxChunks) nch = kMaxChunks;
+    if (nch < 1) nch = 1;
+    const int len = steps > 0 ? (steps + nch - 1) / nch : 1;
+    const dim3 grid((n + 31) / 32), block(32, nch);
+#define MGB_RECUR(Q)                                                                                                  \
+    case Q:                                                                                                           \
+        k_sine_solve<Q><<<grid, block, 0, st>>>(U, G, pitch, n, npts, t, lam, rhs_t, rxh, ends, zero_start, len);     \
+        break;
+    switch (nrhs) {
+        MGB_RECUR(0)
+        MGB_RECUR(1)
+        MGB_RECUR(2)
+        MGB_RECUR(3)
+        MGB_RECUR(4)
+    }
+#undef MGB_RECUR
+    return cuda_fail(cudaGetLastError(), "sine_solve");
+}
+
 int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const double *rxhat_dev, double *work_dev,
                               double *ends_dev, int32_t zero_start, void *stream) {
     if (lvl == nullptr || lvl->app != MGB_APP_HEAT1D || lam_dev == nullptr || work_dev == nullptr || lvl->t_dev == nullptr)
@@ -361,28 +409,27 @@ int mgb_heat1d_spectral_recur(const mgb_level *lvl, const double *lam_dev, const
         return heat2d_fail("heat1d_spectral_recur: right-hand side must be separable with at most 4 terms");
     if (device_info() == nullptr) return MGB_ECUDA;
     if (lvl->npts < 2 && ends_dev == nullptr) return MGB_OK;
-    const dim3 grid((lvl->n + 127) / 128);
-    cudaStream_t st = (cudaStream_t)stream;
-#define MGB_RECUR(Q)                                                                                                       \
-    case Q:                                                                                                                \
-        k_spectral_recur<Q><<<grid, 128, 0, st>>>(work_dev, lvl->pitch, lvl->n, lvl->npts, lvl->t_dev, lam_dev, lvl->rhs_t_dev, \
-                                                  rxhat_dev, ends_dev, zero_start);                                        \
-        break;
-    switch (lvl->nrhs) {
-        MGB_RECUR(0)
-        MGB_RECUR(1)
-        MGB_RECUR(2)
-        MGB_RECUR(3)
-        MGB_RECUR(4)
-    }
-#undef MGB_RECUR
-    return cuda_fail(cudaGetLastError(), "heat1d_spectral_recur");
+    return launch_sine_solve(work_dev, work_dev, lvl->pitch, lvl->n, lvl->npts, lvl->t_dev, lam_dev, lvl->rhs_t_dev,
+                             lvl->nrhs, rxhat_dev, ends_dev, zero_start, (cudaStream_t)stream);
+}
+
+int mgb_sine_level_solve(const mgb_level *lvl, const double *lam_dev, const double *rxh_dev, double *ends_dev,
+                         int32_t zero_start, void *stream) {
+    if (lvl == nullptr || lvl->app != MGB_APP_HEAT1D_SINE || lam_dev == nullptr || lvl->u_dev == nullptr ||
+        lvl->t_dev == nullptr)
+        return heat2d_fail("sine_level_solve: needs a HEAT1D_SINE level with its time grid and eigenvalues");
+    if (lvl->rhs_dense_dev != nullptr || lvl->nrhs > kSpectralMaxTerms || (lvl->nrhs > 0 && (rxh_dev == nullptr || lvl->rhs_t_dev == nullptr)))
+        return heat2d_fail("sine_level_solve: right-hand side must be separable with at most 4 terms");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    if (lvl->npts < 2 && ends_dev == nullptr) return MGB_OK;
+    return launch_sine_solve(lvl->u_dev, lvl->g_dev, lvl->pitch, lvl->n, lvl->npts, lvl->t_dev, lam_dev, lvl->rhs_t_dev,
+                             lvl->nrhs, rxh_dev, ends_dev, zero_start, (cudaStream_t)stream);
 }
 
 int mgb_heat1d_spectral_fixup(const mgb_level *lvl, const double *lam_dev, double *work_dev, const double *all_ends_dev,
                               int32_t rank, void *stream) {
-    if (lvl == nullptr || lvl->app != MGB_APP_HEAT1D || lam_dev == nullptr || work_dev == nullptr || lvl->t_dev == nullptr ||
-        all_ends_dev == nullptr || rank < 1)
+    if (lvl == nullptr || (lvl->app != MGB_APP_HEAT1D && lvl->app != MGB_APP_HEAT1D_SINE) || lam_dev == nullptr ||
+        work_dev == nullptr || lvl->t_dev == nullptr || all_ends_dev == nullptr || rank < 1)
         return heat2d_fail("heat1d_spectral_fixup: bad argument");
     if (device_info() == nullptr) return MGB_ECUDA;
     k_spectral_fixup<<<(lvl->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(work_dev, lvl->pitch, lvl->n, lvl->npts, lvl->t_dev,

@@ -16,6 +16,14 @@ __device__ __forceinline__ void vadd(double (&x)[E], const double (&y)[E]) {  //
     for (int j = 0; j < E; ++j) x[j] = y[j] + x[j];
 }
 
+// Registers -> a row slice in HBM with plain stores (used once per sweep, for the injection of point 0: not worth a slot)
+template <int E>
+__device__ __forceinline__ void store_direct(const double (&x)[E], double *dst, int tid, int tile) {
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+        if (tid * E + j < tile) dst[tid * E + j] = x[j];
+}
+
 // first/last point of the interval that starts at C-point k
 __device__ __forceinline__ void interval_of(const LevelDev &L, int k, int &s, int &e) {
     if (L.cpts == nullptr) {  // whole level as one interval (forward solve)
@@ -63,7 +71,7 @@ __device__ __forceinline__ void step_consts(typename Phi::C &c, const LevelDev &
 
 // x <- (g_i +) Phi_i(x): pops the dense right-hand-side row and the g row if the level has them
 template <class Phi, class Pipe, class TeamT>
-__device__ __forceinline__ void advance(double (&x)[Phi::E], typename Phi::C &c, const typename Phi::Item &it,
+__device__ __forceinline__ void advance(double (&x)[Phi::E], typename Phi::C &c, typename Phi::Item &it,
                                         const LevelDev &L, int i, Pipe &pipe, TeamT &team, bool add_g = true) {
     MGB_T0
     step_consts<Phi>(c, L, i, team.tid);
@@ -82,6 +90,54 @@ __device__ __forceinline__ void advance(double (&x)[Phi::E], typename Phi::C &c,
     }
     MGB_T(10)
 }
+
+// advance() with the step's first time factor already in a register (Phi::ct_load issued earlier); functors without
+// that hook ignore it.
+template <class Phi, class Pipe, class TeamT>
+__device__ __forceinline__ void advance_ct(double (&x)[Phi::E], typename Phi::C &c, typename Phi::Item &it,
+                                           const LevelDev &L, int i, Pipe &pipe, TeamT &team, bool add_g, double ct) {
+    if constexpr (Phi::kCtArg) {
+        step_consts<Phi>(c, L, i, team.tid);
+        if (L.rhs_dense) {
+            double b[Phi::E];
+            pipe.pop(b, team);
+            vadd(x, b);
+        }
+        Phi::apply_ct(x, c, it, L, i, team, ct);
+        if (add_g && L.g) {
+            double gg[Phi::E];
+            pipe.pop(gg, team);
+            vadd(x, gg);
+        }
+    } else {
+        advance<Phi>(x, c, it, L, i, pipe, team, add_g);
+    }
+}
+template <class Phi>
+__device__ __forceinline__ double ct_ahead(const LevelDev &L, int i) {
+    if constexpr (Phi::kCtArg) return Phi::ct_load(L, i);
+    return 0.0;
+}
+template <class Phi>
+__device__ __forceinline__ double chain_ahead(const LevelDev &L, int i0, int i1, int lane) {
+    if constexpr (Phi::kTightChain) return Phi::chain_prefetch(L, i0, i1, lane);
+    return 0.0;
+}
+
+// x <- Phi_{i1-1}( ... Phi_{i0}(x)) on a level without g rows and dense right-hand-side rows (nothing to pop, nothing
+// stored in between): the functor's tight loop where it has one (Heat1DSine), else step by step.
+template <class Phi, class Pipe, class TeamT>
+__device__ __forceinline__ void run_chain(double (&x)[Phi::E], typename Phi::C &c, typename Phi::Item &it,
+                                          const LevelDev &L, int i0, int i1, Pipe &pipe, TeamT &team, double first) {
+    if constexpr (Phi::kTightChain) {
+        if (Phi::chain_ok(c, L)) {
+            Phi::chain(x, c, it, L, i0, i1, team, first);  // first = chain_ahead(L, i0, i1, lane)
+            return;
+        }
+    }
+    for (int i = i0; i < i1; ++i) advance<Phi>(x, c, it, L, i, pipe, team, false);
+}
+__device__ __forceinline__ bool plain_steps(const LevelDev &L) { return L.g == nullptr && L.rhs_dense == nullptr; }
 
 // rows `advance` pops for step i, in order: returns false when stage runs past them
 struct StepRows {
@@ -166,15 +222,24 @@ __global__ void __launch_bounds__(Phi::T) k_chain(const LevelDev L, const int nw
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
+    typename Phi::Item it;
+    bool have_item = false;
     for (int w = blockIdx.x; w < nw; w += gridDim.x) {
         const ItemPos ip = item_pos(L, w);
         int s, e;
         interval_of(L, ip.k, s, e);
         if (e - s <= 1) continue;
-        typename Phi::Item it;
-        Phi::begin_item(it, L, ip.sys, pipe, team);
+        if (!Phi::kItemInvariant || !have_item) Phi::begin_item(it, L, ip.sys, pipe, team);
+        have_item = true;
+        const bool tight = last_only && plain_steps(L);
+        const double first = tight ? chain_ahead<Phi>(L, s + 1, e, team.lane) : 0.0;
         double x[Phi::E];
         pipe.pop(x, team);
+        if (tight) {
+            run_chain<Phi>(x, c, it, L, s + 1, e, pipe, team, first);
+            pipe.push(x, L.u + (size_t)(e - 1) * L.pitch + ip.soff, team);
+            continue;
+        }
         for (int i = s + 1; i < e; ++i) {
             advance<Phi>(x, c, it, L, i, pipe, team);
             if (!last_only || i == e - 1) pipe.push(x, L.u + (size_t)i * L.pitch + ip.soff, team);
@@ -455,6 +520,7 @@ __global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const
             for (int q = 0; q < E; ++q) x[q] = (x[q] - y[q]) + y[q];
         }
         pipe.pop(y, team);                                           // v[j-1]
+        if (j == 1) store_direct(y, G.u + ip.soff, team.tid, L.tile);  // point 0 (initial condition / ghost) is injected too
         Phi::retarget_item(it, L, G, team);
         Phi::load_consts(c, G.sconst + (G.ndt > 1 ? (size_t)__ldg(G.dtidx + j) * G.cw : 0), team.tid);
         advance<Phi>(y, c, it, G, j, pipe, team, false);             // Phi_c(v[j-1])
@@ -751,26 +817,34 @@ __global__ void __launch_bounds__(Phi::T) k_down(const LevelDev L, const LevelDe
     Phi::load_consts(cc, G.sconst, team.tid);
     double *const stash = pipe.stash_slot() + team.tid * E;
     const double *const outs = pipe.out_slot() + team.tid * E;
+    typename Phi::Item it;
+    bool have_item = false;
     for (int w = blockIdx.x; w < nw; w += gridDim.x) {
         const ItemPos ip = item_pos(L, w, 1);
         const int j = ip.k;
         const int a = __ldg(L.cpts + j - 1), cp = __ldg(L.cpts + j);
-        typename Phi::Item it;
-        Phi::begin_item(it, L, ip.sys, pipe, team);
+        if (!Phi::kItemInvariant || !have_item) Phi::begin_item(it, L, ip.sys, pipe, team);
+        have_item = true;
+        // the time factors of the item's single steps and of the start of its chain: all in flight before the first row
+        // is waited for
+        const bool tight = plain_steps(L);
+        const double ct_c = ct_ahead<Phi>(L, cp), ct_a = a != 0 ? ct_ahead<Phi>(L, a) : 0.0, ct_j = ct_ahead<Phi>(G, j);
+        const double first = tight ? chain_ahead<Phi>(L, a + 1, cp + 1, team.lane) : 0.0;
         double x[E];
         // C-relaxation of c; the output slot keeps yc until the last push of this item
         pipe.pop(x, team);
-        advance<Phi>(x, cf, it, L, cp, pipe, team);
+        advance_ct<Phi>(x, cf, it, L, cp, pipe, team, true, ct_c);
         pipe.push(x, L.u + (size_t)cp * L.pitch + ip.soff, team);
         pipe.push_again(G.u + (size_t)j * G.pitch + ip.soff);
         // the C-relaxed left end
         pipe.pop(x, team);
-        if (a != 0) advance<Phi>(x, cf, it, L, a, pipe, team);
+        if (a != 0) advance_ct<Phi>(x, cf, it, L, a, pipe, team, true, ct_a);
+        if (j == 1) store_direct(x, G.u + ip.soff, team.tid, L.tile);  // point 0 (initial condition / ghost) is injected too
         // w = Phi_c(x) into the stash, x back
 #pragma unroll
         for (int q = 0; q < E; ++q) stash[q] = x[q];
         Phi::retarget_item(it, L, G, team);
-        advance<Phi>(x, cc, it, G, j, pipe, team, false);
+        advance_ct<Phi>(x, cc, it, G, j, pipe, team, false, ct_j);
         Phi::retarget_item(it, G, L, team);
 #pragma unroll
         for (int q = 0; q < E; ++q) {
@@ -779,8 +853,12 @@ __global__ void __launch_bounds__(Phi::T) k_down(const LevelDev L, const LevelDe
             x[q] = t;
         }
         // F-relaxation chain and the fine step into c
-        for (int i = a + 1; i < cp; ++i) advance<Phi>(x, cf, it, L, i, pipe, team);
-        advance<Phi>(x, cf, it, L, cp, pipe, team, false);
+        if (tight) {
+            run_chain<Phi>(x, cf, it, L, a + 1, cp + 1, pipe, team, first);
+        } else {
+            for (int i = a + 1; i < cp; ++i) advance<Phi>(x, cf, it, L, i, pipe, team);
+            advance<Phi>(x, cf, it, L, cp, pipe, team, false);
+        }
         // FAS right-hand side
         if (L.g) {
             const double *gg = pipe.pop_ptr() + team.tid * E;
@@ -802,7 +880,8 @@ __global__ void __launch_bounds__(Phi::T) k_down(const LevelDev L, const LevelDe
 
 // ------------------------------------------------------------------------------------------------
 // Coarse-grid correction (mgrit.py:722-726) fused with the F-relaxation that follows (mgrit.py:287):
-//   for interval k:  if k >= kfirst: u[c] = u[c] + (G.u[k] - u[c]);   then, if f_relax, the chain from u[c].
+//   for interval k:  if k >= kfirst: u[c] = u[c] + (G.u[k] - u[c]);   then, if f_relax, the chain from u[c]
+//   (frelax == 2: only the last F-point of the interval is stored, see mgb_error_correction).
 // kfirst = 1 on time rank 0 (point 0 is the initial condition).  On the other ranks point 0 is the ghost copy of the
 // previous rank's last C-point and kfirst = 0: the ghost is corrected here with the same arithmetic its owner uses
 // (the coarse ghost row is already current), so the F-relaxation of the first interval starts from the corrected
@@ -874,6 +953,8 @@ __global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const Leve
     pipe.start(team);
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
+    typename Phi::Item it;
+    bool have_item = false;
     for (int w = blockIdx.x; w < nw; w += gridDim.x) {
         const ItemPos ip = item_pos(L, w);
         const int k = ip.k;
@@ -881,8 +962,12 @@ __global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const Leve
         interval_of(L, k, s, e);
         const bool chain = frelax && (e - s > 1);
         if (k < kfirst && !chain) continue;
-        typename Phi::Item it;
-        if (chain) Phi::begin_item(it, L, ip.sys, pipe, team);
+        if (chain && (!Phi::kItemInvariant || !have_item)) {
+            Phi::begin_item(it, L, ip.sys, pipe, team);
+            have_item = true;
+        }
+        const bool tight = chain && frelax == 2 && plain_steps(L);
+        const double first = tight ? chain_ahead<Phi>(L, s + 1, e, team.lane) : 0.0;
         double x[E];
         pipe.pop(x, team);
         if (k >= kfirst) {
@@ -892,10 +977,13 @@ __global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const Leve
             for (int q = 0; q < E; ++q) x[q] = x[q] + (cu[q] - x[q]);
             pipe.push(x, L.u + (size_t)s * L.pitch + ip.soff, team);
         }
-        if (chain) {
+        if (tight) {
+            run_chain<Phi>(x, c, it, L, s + 1, e, pipe, team, first);
+            pipe.push(x, L.u + (size_t)(e - 1) * L.pitch + ip.soff, team);
+        } else if (chain) {
             for (int i = s + 1; i < e; ++i) {
                 advance<Phi>(x, c, it, L, i, pipe, team);
-                pipe.push(x, L.u + (size_t)i * L.pitch + ip.soff, team);
+                if (frelax == 1 || i == e - 1) pipe.push(x, L.u + (size_t)i * L.pitch + ip.soff, team);
             }
         }
     }
@@ -956,14 +1044,17 @@ __global__ void __launch_bounds__(Phi::T) k_residual(const LevelDev L, double *_
     typename Phi::C c;
     Phi::load_consts(c, L.sconst, team.tid);
     if (blockIdx.x == 0 && team.tid == 0) out_sq[0] = 0.0;
+    typename Phi::Item it;
+    bool have_item = false;
     for (int w = blockIdx.x; w < nw; w += gridDim.x) {
         const ItemPos ip = item_pos(L, w, 1);
         const int cp = __ldg(L.cpts + ip.k);
-        typename Phi::Item it;
-        Phi::begin_item(it, L, ip.sys, pipe, team);
+        if (!Phi::kItemInvariant || !have_item) Phi::begin_item(it, L, ip.sys, pipe, team);
+        have_item = true;
+        const double ct_c = ct_ahead<Phi>(L, cp);
         double x[E], y[E];
         pipe.pop(x, team);
-        advance<Phi>(x, c, it, L, cp, pipe, team);
+        advance_ct<Phi>(x, c, it, L, cp, pipe, team, true, ct_c);
         pipe.pop(y, team);
         double acc = 0.0;
         const int nv = Phi::row_n(L) - team.tid * E;

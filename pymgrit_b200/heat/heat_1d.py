@@ -43,10 +43,83 @@ class VectorHeat1D(DeviceVector):
         super().__init__((int(size),), tensor)
 
 
+_PI = np.longdouble('3.14159265358979323846264338327950288')
+SINE_GEMM_MAX = 2048        # largest n transformed with the dense sine matrix when n + 1 is not a power of two
+
+
+def heat1d_eigenvalues(n, fac):
+    """lam_k = fac * 4 sin^2(pi k / (2 (n+1))), k = 1..n, of fac * tridiag(-1, 2, -1) (heat_1d.py:177-196), in extended
+    precision."""
+    k = np.arange(1, n + 1).astype(np.longdouble)
+    return np.longdouble(fac) * 4 * np.sin(k * _PI / (2 * (n + 1))) ** 2
+
+
+class SineTransform:
+    """rows -> rows S on the device, S the orthonormal DST-I matrix (S = S^T = S^-1): a fast sine transform when n + 1
+    is a power of two (mgb_rows_dst), else the product with S (mgb_rows_gemm).  One object per (n, device)."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, n):
+        torch = dl._torch()
+        key = (int(n), torch.cuda.current_device())
+        if key not in cls._cache:
+            if len(cls._cache) > 8:
+                cls._cache.clear()
+            cls._cache[key] = cls(int(n))
+        return cls._cache[key]
+
+    def __init__(self, n):
+        import os
+        torch = dl._torch()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.n = n
+        self.fast = ((n + 1) & n) == 0 and 32 * (n + 1) <= 200 * 1024 and os.environ.get('MGB_SPECTRAL_FFT', '1') != '0'
+        if self.fast:
+            self.smat = None
+            self.twiddles = torch.empty((n + 1, 2), dtype=torch.float64, device=dev)
+            _lib.check(_lib.lib().mgb_dst_twiddles(n, self.twiddles.data_ptr(), _lib.current_stream_ptr()), 'dst_twiddles')
+        else:
+            self.smat = torch.empty((n, n), dtype=torch.float64, device=dev)
+            _lib.check(_lib.lib().mgb_sine_matrix(n, self.smat.data_ptr(), n, _lib.current_stream_ptr()), 'sine_matrix')
+
+    def apply(self, src, src_pitch, dst, dst_pitch, rows, row0=None):
+        """dst[:rows, :n] = src[:rows, :n] S (row 0 of src taken from row0 if given); src != dst."""
+        if rows <= 0:
+            return
+        n = self.n
+        if self.fast:
+            _lib.check(_lib.lib().mgb_rows_dst(rows, n, src.data_ptr(), src_pitch,
+                                               None if row0 is None else row0.data_ptr(), self.twiddles.data_ptr(),
+                                               dst.data_ptr(), dst_pitch, _lib.current_stream_ptr()), 'rows_dst')
+            return
+        _lib.check(_lib.lib().mgb_rows_gemm(rows, n, n, src.data_ptr(), src_pitch,
+                                            None if row0 is None else row0.data_ptr(), self.smat.data_ptr(), n,
+                                            dst.data_ptr(), dst_pitch, _lib.current_stream_ptr()), 'rows_gemm')
+
+    def rows(self, values):
+        """[count, n] contiguous device tensor -> its transform (new tensor)."""
+        torch = dl._torch()
+        values = values.contiguous()
+        out = torch.empty_like(values)
+        self.apply(values, values.shape[1], out, out.shape[1], values.shape[0])
+        return out
+
+
 class Heat1D(DeviceApplication):
+    """Same constructor as the reference (heat_1d.py:131-175).  Two device representations of the level rows:
+
+      kind = APP_HEAT1D        the node values; Phi = the Toeplitz tridiagonal solve of csrc/phi.cuh (Heat1D)
+      kind = APP_HEAT1D_SINE   the sine coefficients u S; Phi = one FMA + one multiplication per unknown (Heat1DSine)
+
+    Mgrit picks the sine representation for a hierarchy of Heat1D levels connected by GridTransferCopy whose
+    right-hand side is zero or separable (`as_sine()` returns the twin application it then runs); `sine_space=False`
+    (or the environment variable MGB_HEAT1D_SINE=0) keeps the node representation, `sine_space=True` insists.
+    User-visible values (vector_t_start, Mgrit.u[l][i].get_values(), step()) are node values either way."""
     kind = _lib.APP_HEAT1D
 
-    def __init__(self, x_start, x_end, nx, a, init_cond=lambda x: x * 0, rhs=lambda x, t: x * 0, *args, **kwargs):
+    def __init__(self, x_start, x_end, nx, a, init_cond=lambda x: x * 0, rhs=lambda x, t: x * 0, *args,
+                 sine_space=None, **kwargs):
         super().__init__(*args, **kwargs)
         self.x_start = x_start
         self.x_end = x_end
@@ -56,6 +129,7 @@ class Heat1D(DeviceApplication):
         self.dx = self.x[1] - self.x[0]
         self.a = a
         self.rhs = rhs
+        self.sine_space = sine_space
         self.vector_template = VectorHeat1D(self.nx)
         self.init_cond = init_cond
         self.vector_t_start = VectorHeat1D(self.nx)
@@ -65,7 +139,94 @@ class Heat1D(DeviceApplication):
         # one table of spatial factors on the device
         self._rhs_split = _shared_split(self.rhs, self.x, self.t)
 
+    # ---- representation -------------------------------------------------------------------------------------------
+    def can_sine(self):
+        import os
+        if self.sine_space is False or (self.sine_space is None and os.environ.get('MGB_HEAT1D_SINE', '1') == '0'):
+            return False
+        n = self.nx
+        return self._rhs_split.kind != 'dense' and n >= 1 and (((n + 1) & n) == 0 and n <= 4095 or n <= SINE_GEMM_MAX)
+
+    def as_sine(self):
+        """The same problem with its level rows in sine space (a shallow copy: the user's object is left alone)."""
+        import copy
+        twin = copy.copy(self)
+        twin.kind = _lib.APP_HEAT1D_SINE
+        return twin
+
+    @property
+    def _in_sine(self):
+        return self.kind == _lib.APP_HEAT1D_SINE
+
+    def rows_to_values(self, rows):
+        if not self._in_sine:
+            return super().rows_to_values(rows)
+        torch = dl._torch()
+        out = torch.empty((rows.shape[0], self.nx), dtype=torch.float64, device=rows.device)
+        SineTransform.get(self.nx).apply(rows, rows.stride(0), out, self.nx, rows.shape[0])
+        return out
+
+    def values_to_rows(self, values, rows) -> None:
+        if not self._in_sine:
+            return super().values_to_rows(values, rows)
+        vals = values.reshape(rows.shape[0], self.nx).contiguous()
+        if rows.stride(0) > self.nx:
+            rows[:, self.nx:] = 0.0
+        SineTransform.get(self.nx).apply(vals, self.nx, rows, rows.stride(0), rows.shape[0])
+
+    def _sine_device_tables(self, team_threads, chunk):
+        """Device tables every sine-space level of this problem shares: eigenvalues in natural order and the transformed
+        spatial right-hand-side factors (natural order [q][pitch] and thread-transposed [q][chunk][team_threads])."""
+        torch = dl._torch()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        split = self._rhs_split
+        key = (dev.index, team_threads, chunk, None if split.basis is None else split.basis.shape[0],
+               None if split.basis is None else hash(split.basis.tobytes()), float(self.a), float(self.dx))
+        hit = getattr(split, '_sine_dev', None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        n, pitch = self.nx, self.nx + (self.nx & 1)
+        lam = np.asarray(heat1d_eigenvalues(n, np.longdouble(self.a) / np.longdouble(self.dx) ** 2), dtype=np.float64)
+        tabs = dict(lam=torch.as_tensor(lam).to(dev), h2d=8 * n, rxh=None, rhs_x=None, nrhs=0)
+        if split.kind == 'separable':
+            q = split.basis.shape[0]
+            basis = torch.as_tensor(np.ascontiguousarray(split.basis)).to(dev)
+            tabs['h2d'] += split.basis.nbytes
+            rxh = torch.zeros((q, pitch), dtype=torch.float64, device=dev)
+            SineTransform.get(n).apply(basis, n, rxh, pitch, q)
+            full = torch.zeros((q, team_threads * chunk), dtype=torch.float64, device=dev)
+            full[:, :n] = rxh[:, :n]
+            tabs['rxh'] = rxh
+            tabs['rhs_x'] = full.reshape(q, team_threads, chunk).transpose(1, 2).contiguous()   # [q][chunk][team_threads]
+            tabs['nrhs'] = q
+        split._sine_dev = (key, tabs)
+        return tabs
+
+    def sine_host_tables(self, t, team_threads, chunk):
+        """Host part of a sine-space level's Phi data (include/mgrit_b200.h, MGB_APP_HEAT1D_SINE): dt classes, the
+        step-constant rows [dt, use_reciprocals], diag = [eigenvalues; 1 / (1 + dt lam)] thread-transposed, and dt per
+        point."""
+        t = np.asarray(t, dtype=float)
+        dt_full = np.empty(len(t))
+        dt_full[0] = 0.0
+        np.subtract(t[1:], t[:-1], out=dt_full[1:])
+        dts, dtidx = dl.dt_classes(t, dt_full[1:])
+        uniform = len(dts) == 1
+        sconst = np.zeros((len(dts), 8))
+        sconst[:, 0] = dts
+        sconst[:, 1] = 1.0 if uniform else 0.0
+        n = self.nx
+        lam_l = heat1d_eigenvalues(n, np.longdouble(self.a) / np.longdouble(self.dx) ** 2)      # heat_1d.py:185
+        flat = np.zeros((2, team_threads * chunk))
+        flat[0, :n] = np.asarray(lam_l, dtype=np.float64)
+        if uniform:       # 1 / (1 + dt lam_k) in extended precision, rounded once; the padding acts on zeros
+            flat[1, :n] = np.asarray(1 / (1 + np.longdouble(dts[0]) * lam_l), dtype=np.float64)
+        diag = np.ascontiguousarray(flat.reshape(2, team_threads, chunk).transpose(0, 2, 1))   # [2][chunk][team_threads]
+        return dict(ndt=len(dts), dtidx=dtidx, sconst=sconst, cw=8, diag=diag), dt_full
+
     def level_tables(self, t, team_threads, chunk):
+        if self._in_sine:
+            return self._level_tables_sine(t, team_threads, chunk)
         fac = self.a / self.dx ** 2                                   # heat_1d.py:185
         t = np.asarray(t, dtype=float)
         dt_full = np.empty(len(t))
@@ -87,15 +248,31 @@ class Heat1D(DeviceApplication):
             tab['rhs_dense'] = split.dense(t) * dt_full[:, None]
         return tab
 
+    def _level_tables_sine(self, t, team_threads, chunk):
+        tab, dt_full = self.sine_host_tables(t, team_threads, chunk)
+        shared = self._sine_device_tables(team_threads, chunk)
+        split = self._rhs_split
+        if split.kind == 'separable':
+            tab['nrhs'] = shared['nrhs']
+            tab['rhs_x_dev'] = shared['rhs_x']
+            out = dl.pinned_array((len(t), tab['nrhs'])) if len(t) >= (1 << 15) else None
+            tab['rhs_t'] = split.coefficients(t, scale=dt_full, out=out)
+        return tab
+
     # ---- coarsest-level solve in sine space (csrc/spectral.cu) ---------------------------------------------------
     SPECTRAL_MIN_POINTS = 24     # below this the sequential Phi chain (mgb_forward_solve) is as fast
 
     def spectral_solver(self, level):
         """A SpectralSolve for `level` (the coarsest DeviceLevel of a hierarchy), or None when the chain of Phi
         applications is used: short levels, or a right-hand side that is not separable."""
+        if self._in_sine:
+            return SineLevelSolve(self, level) if level.npts >= 2 else None
         if level.npts < self.SPECTRAL_MIN_POINTS or self._rhs_split.kind == 'dense':
             return None
         return SpectralSolve(self, level)
+
+    def spectral_min_points(self):
+        return 2 if self._in_sine else self.SPECTRAL_MIN_POINTS
 
 
 class SpectralSolve:
@@ -109,20 +286,8 @@ class SpectralSolve:
         self.n, self.pitch, self.level = n, pitch, level
         self.h2d_bytes = 0
         level.ensure_t_dev()                     # the scalar recurrences read dt_i = t[i] - t[i-1]
-        import os
-        # n + 1 a power of two (nx = 2^k + 1): fast sine transform, one CTA per row; otherwise the product with S
-        self.fast = ((n + 1) & n) == 0 and 32 * (n + 1) <= 200 * 1024 and os.environ.get('MGB_SPECTRAL_FFT', '1') != '0'
-        if self.fast:
-            self.smat = None
-            self.twiddles = torch.empty((n + 1, 2), dtype=torch.float64, device=dev)
-            _lib.check(_lib.lib().mgb_dst_twiddles(n, self.twiddles.data_ptr(), _lib.current_stream_ptr()), 'dst_twiddles')
-        else:
-            self.smat = torch.empty((n, n), dtype=torch.float64, device=dev)
-            _lib.check(_lib.lib().mgb_sine_matrix(n, self.smat.data_ptr(), n, _lib.current_stream_ptr()), 'sine_matrix')
-        k = np.arange(1, n + 1).astype(np.longdouble)
-        pi = np.longdouble('3.14159265358979323846264338327950288')
-        fac = np.longdouble(app.a) / np.longdouble(app.dx) ** 2                       # heat_1d.py:185
-        lam = np.asarray(fac * 4 * np.sin(k * pi / (2 * (n + 1))) ** 2, dtype=np.float64)
+        self.xform = SineTransform.get(n)          # fast sine transform for n + 1 a power of two, else the product with S
+        lam = np.asarray(heat1d_eigenvalues(n, np.longdouble(app.a) / np.longdouble(app.dx) ** 2), dtype=np.float64)
         self.lam = torch.as_tensor(lam).to(dev)
         self.h2d_bytes += lam.nbytes
         self.work = torch.zeros((level.npts, pitch), dtype=torch.float64, device=dev)
@@ -138,14 +303,7 @@ class SpectralSolve:
 
     def _gemm(self, src, dst, rows, row0=None):
         """dst[:rows, :n] = src[:rows, :n] S (row 0 of src taken from row0 if given)."""
-        if self.fast:
-            _lib.check(_lib.lib().mgb_rows_dst(rows, self.n, src.data_ptr(), self.pitch,
-                                               None if row0 is None else row0.data_ptr(), self.twiddles.data_ptr(),
-                                               dst.data_ptr(), self.pitch, _lib.current_stream_ptr()), 'rows_dst')
-            return
-        _lib.check(_lib.lib().mgb_rows_gemm(rows, self.n, self.n, src.data_ptr(), self.pitch,
-                                            None if row0 is None else row0.data_ptr(), self.smat.data_ptr(), self.n,
-                                            dst.data_ptr(), self.pitch, _lib.current_stream_ptr()), 'rows_gemm')
+        self.xform.apply(src, self.pitch, dst, self.pitch, rows, row0=row0)
 
     def transform_in(self):
         """work[0] = u[0] S, work[i] = g[i] S: one product."""
@@ -186,3 +344,57 @@ class SpectralSolve:
         lv = self.level
         if lv.npts > first_row:
             self._gemm(self.work[first_row:], lv.u[first_row:], lv.npts - first_row)
+
+    def solve(self, comm):
+        """The whole level; returns the number of kernel launches."""
+        rank, size = comm.Get_rank(), comm.Get_size()
+        self.transform_in()
+        if size > 1:
+            self.recur_time_parallel(comm)
+        else:
+            self.recur()
+        self.transform_out(first_row=0 if rank > 0 else 1)
+        return 3 + (1 if size > 1 and rank > 0 else 0)
+
+
+class SineLevelSolve:
+    """The sequential solve (mgrit.py:459-486) of a level whose rows are already in sine space: no transforms, the n
+    scalar recurrences run time-parallel in one launch (mgb_sine_level_solve).  Between time ranks: every rank runs from
+    zero, the (last value, factor product) rows travel once, one fix-up pass -- no rank-to-rank chain
+    (mgrit.py:467-484)."""
+
+    def __init__(self, app, level):
+        shared = app._sine_device_tables(level.team_threads, level.chunk)
+        self.level, self.pitch = level, level.pitch
+        self.lam, self.rxh = shared['lam'], shared['rxh']
+        self.h2d_bytes = 0
+        level.ensure_t_dev()                     # the scalar recurrences read dt_i = t[i] - t[i-1]
+        self._ends = None
+
+    def _recur(self, ends=None, zero_start=False):
+        _lib.check(_lib.lib().mgb_sine_level_solve(self.level.ref, self.lam.data_ptr(),
+                                                   None if self.rxh is None else self.rxh.data_ptr(),
+                                                   None if ends is None else ends.data_ptr(), 1 if zero_start else 0,
+                                                   _lib.current_stream_ptr()), 'sine_level_solve')
+
+    def solve(self, comm):
+        rank, size = comm.Get_rank(), comm.Get_size()
+        if size == 1:
+            self._recur()
+            return 1
+        torch = dl._torch()
+        if self._ends is None:
+            dev = self.level.u.device
+            self._ends = torch.zeros((2, self.pitch), dtype=torch.float64, device=dev)
+            self._all_ends = torch.zeros((size, 2, self.pitch), dtype=torch.float64, device=dev)
+        self._recur(ends=self._ends, zero_start=rank > 0)
+        box = getattr(comm, 'mailbox', None)
+        if box and box.gather and box.pitch == self.pitch:
+            all_ends = box.share_rows(self._ends)            # peer-memory stores instead of a collective
+        else:
+            comm.all_gather_rows(self._all_ends, self._ends)
+            all_ends = self._all_ends.data_ptr()
+        if rank > 0:
+            _lib.check(_lib.lib().mgb_heat1d_spectral_fixup(self.level.ref, self.lam.data_ptr(), self.level.u.data_ptr(),
+                                                            all_ends, rank, _lib.current_stream_ptr()), 'spectral_fixup')
+        return 1 + (1 if rank > 0 else 0)

@@ -23,7 +23,7 @@ if world > 1:                       # python -m torch.distributed.run --nproc-pe
     if rank != 0:
         sys.stdout = open(os.devnull, 'w')
 wl = sys.argv[1] if len(sys.argv) > 1 else 'cfg5'
-nt, co = bench.WORKLOADS[wl]
+nt, co = bench.workload_grid(wl)
 
 
 def run():
@@ -43,9 +43,10 @@ def run():
     return [1e3 * (b - a) for a, b in zip(t, t[1:])], s
 
 
-for k in range(4):
+for k in range(8):
     ms, s = run()
     print('hierarchy %.1f ms | Mgrit() %.1f ms | solve() %.1f ms | readback %.1f ms | total %.1f ms' % (*ms, sum(ms)))
+    print('    ' + ' | '.join('%s %.2f' % ph for ph in s.setup_phases))
     del s
 pr = cProfile.Profile()
 pr.enable()

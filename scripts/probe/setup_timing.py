@@ -36,7 +36,7 @@ timed(M.Mgrit, 'nested_iteration', 'nested_iteration (host side)')
 timed(M.Mgrit, '_init_levels', '_init_levels')
 timed(torch.cuda, 'synchronize', 'cuda.synchronize')
 timed(torch, 'zeros', 'torch.zeros')
-nt, co = bench.WORKLOADS['cfg5']
+nt, co = bench.workload_grid('cfg5')
 for k in range(5):
     acc.clear()
     torch.cuda.synchronize()

@@ -27,7 +27,7 @@ show = int(os.environ.get('SHOW_RANK', world - 1))
 if rank != show:
     sys.stdout = open(os.devnull, 'w')
 wl = sys.argv[1] if len(sys.argv) > 1 else 'cfg5'
-nt, co = bench.WORKLOADS[wl]
+nt, co = bench.workload_grid(wl)
 if len(sys.argv) > 2:
     co = tuple(int(x) for x in sys.argv[2].split(','))
 
@@ -46,7 +46,7 @@ info = solver.solve()
 e1.record()
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) * 1e3
-print(f'{bench.describe(wl, nt, co)}: {len(info["conv"])} iterations, device {e0.elapsed_time(e1):.2f} ms, wall {wall:.2f} ms')
+print(f'{bench.describe(wl, co)}: {len(info["conv"])} iterations, device {e0.elapsed_time(e1):.2f} ms, wall {wall:.2f} ms')
 
 records = []
 

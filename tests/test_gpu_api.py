@@ -253,7 +253,7 @@ def test_spectral_coarse_solve_matches_phi_chain(P, variant):
     replaces (mgrit.py:459-486), on the same u[0] and FAS right-hand side g: 1e-12 relative."""
     import logging
     import torch
-    kw = dict(x_start=0, x_end=1, nx=1025, a=1, init_cond=C.heat_init, rhs=C.heat_rhs)
+    kw = dict(x_start=0, x_end=1, nx=1025, a=1, init_cond=C.heat_init, rhs=C.heat_rhs, sine_space=False)
     if variant == 'zero_rhs':
         kw.pop('rhs')
     if variant == 'rank2_rhs':
@@ -267,7 +267,7 @@ def test_spectral_coarse_solve_matches_phi_chain(P, variant):
     coarse = P.Heat1D(t_interval=t[::2], **kw)
     solver = P.Mgrit(problem=[fine, coarse], nested_iteration=False, logging_lvl=logging.WARNING)
     assert 1 in solver._spectral
-    assert solver._spectral[1].fast == (variant != 'nx1001_product')
+    assert solver._spectral[1].xform.fast == (variant != 'nx1001_product')
     lv = solver._lv[1]
     gen = torch.Generator(device='cuda').manual_seed(7)
     lv.g[:, :lv.n] = torch.randn((lv.npts, lv.n), generator=gen, device='cuda', dtype=torch.float64) * 1e-2
@@ -281,6 +281,89 @@ def test_spectral_coarse_solve_matches_phi_chain(P, variant):
     assert float(chain[1:].abs().max()) > 1e-3
     assert float((spectral - chain).abs().max()) <= 1e-12 * float(chain.abs().max())
     assert float(spectral[:, lv.n:].abs().max()) == 0.0           # the row padding stays zero
+
+
+@pytest.mark.parametrize('variant', ['uniform', 'nonuniform_t', 'zero_rhs', 'rank2_rhs', 'nx1001_product', 'short'])
+def test_sine_level_solve_matches_phi_chain(P, variant):
+    """A level kept in sine space: the time-parallel scalar recurrences of mgb_sine_level_solve against (a) the chain of
+    diagonal Phi applications through the generic sweep kernel and (b) the chain of tridiagonal solves on the same data in
+    node space (mgrit.py:459-486): 1e-12 relative."""
+    import logging
+    import torch
+    kw = dict(x_start=0, x_end=1, nx=1025, a=1, init_cond=C.heat_init, rhs=C.heat_rhs)
+    if variant == 'zero_rhs':
+        kw.pop('rhs')
+    if variant == 'rank2_rhs':
+        kw['rhs'] = C.heat_rhs_rank2
+    if variant == 'nx1001_product':
+        kw['nx'] = 1001
+    nt = 37 if variant == 'short' else 513
+    t = np.linspace(0, 2, nt)
+    if variant == 'nonuniform_t':
+        t = 2 * np.linspace(0, 1, nt) ** 1.3
+    out = {}
+    g_nodes = None
+    for space in ('sine', 'node'):
+        fine = P.Heat1D(t_interval=t, sine_space=space == 'sine', **kw)
+        coarse = P.Heat1D(t_interval=t[::2], sine_space=space == 'sine', **kw)
+        solver = P.Mgrit(problem=[fine, coarse], nested_iteration=False, logging_lvl=logging.WARNING)
+        assert solver.problem[1].kind == (P._lib.APP_HEAT1D_SINE if space == 'sine' else P._lib.APP_HEAT1D)
+        lv = solver._lv[1]
+        if g_nodes is None:
+            gen = torch.Generator(device='cuda').manual_seed(7)
+            g_nodes = torch.randn((lv.npts, lv.n), generator=gen, device='cuda', dtype=torch.float64) * 1e-2
+        lv.app.values_to_rows(g_nodes, lv.g)                       # the same FAS right-hand side in either representation
+        sp = solver._spectral.pop(1, None)
+        solver.forward_solve(1)                                    # chain of Phi applications (mgb_forward_solve)
+        out[space, 'chain'] = lv.app.rows_to_values(lv.u).clone()
+        if space == 'sine':
+            assert type(sp).__name__ == 'SineLevelSolve'
+            lv.u[1:].zero_()
+            solver._spectral[1] = sp
+            solver.forward_solve(1)
+            out[space, 'solve'] = lv.app.rows_to_values(lv.u).clone()
+            assert float(lv.u[:, lv.n:].abs().max()) == 0.0        # the row padding stays zero
+    ref = out['node', 'chain']
+    scale = float(ref.abs().max())
+    assert scale > 1e-3
+    assert float((out['sine', 'chain'] - ref).abs().max()) <= 1e-12 * scale
+    assert float((out['sine', 'solve'] - ref).abs().max()) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize('name', ['heat1d_cfg2_nt1025', 'heat1d_nonuniform_t', 'heat1d_varying', 'heat1d_small_f_cf2',
+                                  'heat1d_rhs_rank2', 'heat1d_example'])
+def test_sine_space_solve_matches_node_space_solve(P, name, monkeypatch):
+    """The whole MGRIT solve with the level rows in sine space against the tridiagonal kernels: same iteration count,
+    residual history to 1e-12 of the run's scale, solution to 1e-12 relative."""
+    from b200_util import run_b200, solution_rows
+    if name not in C.CASES:
+        pytest.skip('case not defined')
+    monkeypatch.setenv('MGB_HEAT1D_SINE', '1')
+    sine, info_s = run_b200(name)
+    assert sine.problem[0].kind == P._lib.APP_HEAT1D_SINE
+    monkeypatch.setenv('MGB_HEAT1D_SINE', '0')
+    node, info_n = run_b200(name)
+    assert node.problem[0].kind == P._lib.APP_HEAT1D
+    us, un = solution_rows(sine)[0], solution_rows(node)[0]
+    scale = np.max(np.abs(un))
+    assert len(info_s['conv']) == len(info_n['conv'])
+    assert np.max(np.abs(info_s['conv'] - info_n['conv'])) <= 1e-12 * scale * np.sqrt(len(un))
+    assert np.max(np.abs(us - un)) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize('name', ['heat1d_cfg2_nt1025', 'heat1d_rhs_nonsep', 'heat1d_trailing_f', 'advection_cfg4_small',
+                                  'heat2d_cfg3_small', 'heat1d_bdf2_example', 'heat1d_weighted'])
+def test_lazy_f_points_are_bit_identical(P, name, monkeypatch):
+    """Level 0 stores only the last F-point of every interval while the solver iterates and computes the others once at
+    the end (MGB_CORRECT_LAST_ONLY + one F-relaxation): same residual history and solution, bit for bit, as storing
+    every F-point in every iteration."""
+    from b200_util import run_b200, solution_rows
+    monkeypatch.setenv('MGB_LAZY_F', '1')
+    lazy, info_l = run_b200(name)
+    monkeypatch.setenv('MGB_LAZY_F', '0')
+    eager, info_e = run_b200(name)
+    assert np.array_equal(info_l['conv'], info_e['conv'])
+    assert np.array_equal(solution_rows(lazy)[0], solution_rows(eager)[0])
 
 
 @pytest.mark.parametrize('name', ['heat1d_cfg2_nt1025', 'heat1d_nonuniform_t', 'heat1d_rhs_nonsep', 'heat1d_small_f_cf2',

@@ -63,7 +63,7 @@ def test_cfg5_heat1d_full_size(P):
     """configs[4] on one GPU: heat_1d nx=1025, nt=2^20+1, FCF V-cycles, the hierarchy bench.py uses."""
     import bench
     from oracle import mgrit_oracle as O
-    nt, coarsening = bench.WORKLOADS['cfg5']
+    nt, coarsening = bench.workload_grid('cfg5')
     solver = P.Mgrit(problem=bench.hierarchy(P.Heat1D, nt, coarsening), logging_lvl=logging.WARNING, **bench.SOLVER_KW)
     info = solver.solve()
     conv = info['conv']

@@ -29,9 +29,19 @@ def _check_against_golden(name):
     return solver, info
 
 
+@pytest.mark.parametrize('space', ['sine', 'node'])
 @pytest.mark.parametrize('name', [k for k in _cases(('heat1d',)) if C.CASES[k]['app'] == 'heat1d' and 'at_k' not in C.CASES[k]])
-def test_heat1d_against_reference_fixture(name):
-    _check_against_golden(name)
+def test_heat1d_against_reference_fixture(name, space, monkeypatch):
+    """Every Heat1D fixture of the unmodified reference in both device representations of the level rows: sine
+    coefficients (Phi diagonal, csrc/phi.cuh Heat1DSine; what Mgrit picks when it can) and node values (Toeplitz
+    tridiagonal solve).  Spatial coarsening and non-separable right-hand sides stay in node space either way."""
+    import pymgrit_b200 as P
+    monkeypatch.setenv('MGB_HEAT1D_SINE', '1' if space == 'sine' else '0')
+    solver, _ = _check_against_golden(name)
+    case = C.CASES[name]
+    sine_possible = 'transfer' not in case and solver.problem[0]._rhs_split.kind != 'dense'
+    want = P._lib.APP_HEAT1D_SINE if (space == 'sine' and sine_possible) else P._lib.APP_HEAT1D
+    assert all(p.kind == want for p in solver.problem)
 
 
 @pytest.mark.parametrize('name', [k for k in C.CASES if C.CASES[k]['app'] == 'heat1d2pts'])

@@ -188,3 +188,41 @@ def test_applications_build_and_deepcopy_without_a_device():
     tr.check(P.Heat1D(nx=17, t_start=0, t_stop=1, nt=9, **C.HEAT), P.Heat1D(nx=9, t_start=0, t_stop=1, nt=5, **C.HEAT))
     with pytest.raises(Exception):
         tr.check(P.Heat1D(nx=17, t_start=0, t_stop=1, nt=9, **C.HEAT), P.Heat1D(nx=10, t_start=0, t_stop=1, nt=5, **C.HEAT))
+
+
+@pytest.mark.parametrize('nx', [65, 50])
+def test_sine_space_tables_restate_the_heat1d_step(nx):
+    """Heat1D with its rows in sine space (csrc/phi.cuh Heat1DSine): the host tables (eigenvalues, reciprocals, their
+    thread-transposed layout) pushed through a NumPy restatement of the kernel's arithmetic give the reference's step
+    (heat_1d.py:198-217, here the oracle's sparse solve)."""
+    import pymgrit_b200 as P
+    from oracle import mgrit_oracle as O
+    from scipy.fft import dst
+    kw = dict(x_start=0, x_end=1, nx=nx, a=0.7, init_cond=C.heat_init, rhs=C.heat_rhs_rank2)
+    t = np.linspace(0, 1, 17)
+    app = P.Heat1D(t_interval=t, **kw)
+    assert app.can_sine() and app.as_sine().kind == 7 and app.kind == 1
+    orc = O.Heat1DOracle(t_interval=t, **kw)
+    n = nx - 2
+    threads, chunk = 32, 3 if n > 32 else 1
+    for grid in (t, t ** 1.5):                                   # uniform: reciprocals; non-uniform: division per step
+        tab, dt = app.sine_host_tables(grid, threads, chunk)
+        lam = tab['diag'][0].T.reshape(-1)[:n]
+        inv = tab['diag'][1].T.reshape(-1)[:n]
+        assert np.all(tab['diag'][:, :, :].transpose(0, 2, 1).reshape(2, -1)[:, n:] == 0.0)
+        uniform = tab['ndt'] == 1
+        assert tab['sconst'][0, 1] == (1.0 if uniform else 0.0)
+        u = np.asarray(orc.u0, dtype=float)
+        for i in (1, 7, 16):
+            xh = dst(u, type=1, norm='ortho')
+            bh = dst(np.asarray(kw['rhs'](app.x, grid[i])) * dt[i], type=1, norm='ortho')
+            if uniform:
+                new = (xh + bh) * inv
+            else:
+                row = tab['sconst'][tab['dtidx'][i]]
+                assert row[0] == dt[i]
+                new = (xh + bh) / (1 + row[0] * lam)
+            got = dst(new, type=1, norm='ortho')
+            ref = orc.phi(u, grid[i - 1], grid[i])
+            assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))
+            u = ref
