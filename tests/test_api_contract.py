@@ -145,7 +145,12 @@ def test_product_never_touches_the_oracle_or_the_reference():
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
     bench = open(os.path.join(root, 'bench.py')).read()
-    assert '/root/reference' not in bench            # nothing run on the GPU box reads the reference tree
+    # nothing run on the GPU box reads the reference tree: the CPU arm drives the unmodified reference only where the tree
+    # exists (the build container), behind reference_src(); the GPU arm never mentions it
+    import inspect
+    import bench as B
+    assert '/root/reference' not in inspect.getsource(B.gpu_arm) + inspect.getsource(B.parity_check)
+    assert 'os.path.isdir' in inspect.getsource(B.reference_src)
     entry = open(os.path.join(root, '__graft_entry__.py')).read()
     assert '/root/reference' not in entry
 
