@@ -234,6 +234,22 @@ int mgb_jump_norms(const mgb_level *lvl, double *last_dev, double *out_sq_dev, v
  * (TWO: sum of squares, ONE: sum of roots, INF: max of roots) to out_dev[0]. */
 int mgb_temporal_norm(const double *sq_dev, int32_t count, int32_t t_norm, double *out_dev, void *stream);
 
+/* Stopping test without a host round trip per iteration (mgrit.py:626: `if self.conv[iteration + 1] < self.tol: break`).
+ * The reference decides on the host after every iteration; a GPU solver that does so idles while the host reads one double
+ * and queues the next cycle.  Instead the host queues one iteration ahead:
+ *   mgb_convergence_flag  after the residual norm of an iteration has been reduced to norm_dev[0] (the 2-norm's sum of
+ *                         squares, or the 1-/inf-norm), stores it in hist_dev[0] and raises flag_dev[0] if the norm
+ *                         (its square root for MGB_TNORM_TWO) is below tol;
+ *   mgb_set_stop_flag     makes every sweep launched from now on return at once while that flag is up, so the cycle
+ *                         that was queued before the host learned of convergence changes nothing (NULL: off);
+ *   mgb_write_flag        sets the flag from the stream (cleared before the next solve).
+ * The values the host reads one iteration late are the same numbers; the iteration count and the iterates are
+ * unchanged.  Ghost-row exchanges between time ranks are not skipped (their sequence numbers stay in step). */
+int mgb_set_stop_flag(const int32_t *flag_dev);
+int mgb_write_flag(int32_t *flag_dev, int32_t value, void *stream);
+int mgb_convergence_flag(const double *norm_dev, int32_t t_norm, double tol, double *hist_dev, int32_t *flag_dev,
+                         void *stream);
+
 /* Nested iteration, mgrit.py:559-563: fine.u[c_j] = coarse.u[j] for j >= 1. */
 int mgb_inject_up(const mgb_level *fine, const mgb_level *coarse, void *stream);
 
@@ -303,6 +319,32 @@ int mgb_heat1d_spectral_fixup(const mgb_level *lvl, const double *lam_dev, doubl
  * mgb_heat1d_spectral_recur (time ranks > 0 start from zero and are fixed up by mgb_heat1d_spectral_fixup on u). */
 int mgb_sine_level_solve(const mgb_level *lvl, const double *lam_dev, const double *rxh_dev, double *ends_dev,
                          int32_t zero_start, void *stream);
+
+/* ---- The batched path: applications without fused team kernels (csrc/generic.cu) ---------------------------------- */
+/* The reference's plug-in is Application.step (core/application.py:99).  An application that brings its own batched device
+ * Phi (pymgrit_b200.BatchedApplication.step_rows: many (row, step) pairs per call) runs the same sweeps: the host walks
+ * the positions inside a coarse interval, every position is one batched Phi over all intervals of the level, and the
+ * row-wise parts of mgrit.py:312-327, 354-368, 497-547, 722-726 are these two entry points.  Index arrays are int32 device
+ * arrays of `count` row numbers (NULL: row k).
+ *   mgb_rows_lincomb  out[oi[k]] = (a x[xi[k]] + b y[yi[k]]) + c z[zi[k]]  on n doubles per row (y, z may be NULL; every
+ *                     product and sum rounded on its own, like the reference's NumPy expressions)
+ *   mgb_rows_sumsq    out_sq[k] = sum_q x[xi[k]][q]^2   (Vector.norm squared; fixed summation order) */
+int mgb_rows_lincomb(int32_t count, int32_t n, double *out_dev, int32_t out_pitch, const int32_t *out_idx_dev, double a,
+                     const double *x_dev, int32_t x_pitch, const int32_t *x_idx_dev, double b, const double *y_dev,
+                     int32_t y_pitch, const int32_t *y_idx_dev, double c, const double *z_dev, int32_t z_pitch,
+                     const int32_t *z_idx_dev, void *stream);
+int mgb_rows_sumsq(int32_t count, int32_t n, const double *x_dev, int32_t pitch, const int32_t *x_idx_dev,
+                   double *out_sq_dev, void *stream);
+
+/* Allen-Cahn, IMEX branch of allen_cahn/allen_cahn.py:191-197, batched: for k < count
+ *   rhs = u + dt[k] (1/eps^2) u (1 - u^nu),  dst[di[k]] = (I - dt[k] L)^-1 rhs,   u = src[si[k]] (nx x nx nodes, row-major)
+ * with the periodic 5-point Laplacian L = L1 (x) I + I (x) L1, L1 = -Q diag(mu) Q^T: q_dev [nx*nx] the real orthonormal
+ * Fourier basis (columns), qt_dev its transpose, mu_dev [nx] = (4/dx^2) sin^2(pi m / nx) per column; work1/2_dev
+ * [count][nx*nx] scratch.  Four batched FP64 products per call (spsolve in the reference: the same linear system). */
+int mgb_allen_cahn_imex_rows(int32_t nx, int32_t count, const double *src_dev, int32_t src_pitch,
+                             const int32_t *src_idx_dev, double *dst_dev, int32_t dst_pitch, const int32_t *dst_idx_dev,
+                             const double *dt_dev, double inv_eps2, int32_t nu, const double *q_dev, const double *qt_dev,
+                             const double *mu_dev, double *work1_dev, double *work2_dev, void *stream);
 
 /* ---- Ghost rows between time ranks over peer memory (csrc/peer.cu) ----------------------------------------- */
 /* Replaces the reference's kind-0/4 messages (mgrit.py:305-310, 510-517, 693-713: pickled vector, isend/recv) by direct

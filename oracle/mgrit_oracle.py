@@ -255,6 +255,36 @@ class Heat2DOracle(OracleProblem):
         return new.reshape(self.nx, self.ny)
 
 
+class AllenCahnOracle(OracleProblem):
+    """allen_cahn/allen_cahn.py:136-270, IMEX branch (allen_cahn.py:191-197): reaction explicit, periodic 5-point
+    Laplacian implicit through a sparse direct solve."""
+
+    def __init__(self, nx=128, nu=2, eps=0.04, radius=0.25, method='IMEX', **kw):
+        super().__init__(**kw)
+        if method != 'IMEX':
+            raise Exception('the oracle restates the IMEX branch only')
+        self.nx = self.ny = nx
+        self.nu, self.eps, self.radius = nu, eps, radius
+        self.dx = 1.0 / nx                                           # allen_cahn.py:167
+        self.x = np.linspace(start=-0.5, stop=0.5, num=nx)           # allen_cahn.py:170
+        one = sp.lil_matrix((nx, nx))                                # circulant second difference (allen_cahn.py:175-189)
+        for i in range(nx):
+            one[i, i] += -2.0
+            one[i, (i + 1) % nx] += 1.0
+            one[i, (i - 1) % nx] += 1.0
+        one = one.tocsc()
+        self.space_disc = (sp.kron(one, sp.eye(nx)) + sp.kron(sp.eye(nx), one)) * (1.0 / self.dx ** 2)
+        self.id = sp.eye(nx * nx)
+        r = np.sqrt(self.x[:, None] ** 2 + self.x[None, :] ** 2)     # allen_cahn.py:238-243
+        self.u0 = np.tanh((radius - r) / (np.sqrt(2) * eps))
+
+    def phi(self, u, t_start, t_stop):
+        new = np.asarray(u, dtype=float).flatten()
+        rhs = new + (t_stop - t_start) * (1 / self.eps ** 2 * new * (1.0 - new ** self.nu))      # allen_cahn.py:194
+        new = spsolve((self.id - (t_stop - t_start) * self.space_disc).tocsc(), rhs)             # allen_cahn.py:195
+        return new.reshape(self.nx, self.ny)
+
+
 class Advection1DOracle(OracleProblem):
     """advection/advection_1d.py:68-143: implicit Euler + first-order upwind, periodic."""
 

@@ -21,5 +21,7 @@ from pymgrit_b200.heat.heat_1d_2pts_bdf2 import Heat1DBDF2
 from pymgrit_b200.advection.advection_1d import Advection1D, VectorAdvection1D
 from pymgrit_b200.dahlquist.dahlquist import Dahlquist, VectorDahlquist
 from pymgrit_b200.brusselator.brusselator import Brusselator, VectorBrusselator
+from pymgrit_b200.allen_cahn.allen_cahn import AllenCahn, VectorAllenCahn2D
+from pymgrit_b200.core.batched import BatchedApplication
 
 __version__ = '0.1.0'

@@ -10,6 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libmgrit_b200.so')
 
+APP_BATCHED = 0            # no fused team kernels: the batched path (core/batched.py, csrc/generic.cu)
 APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D, APP_HEAT1D_2PTS, APP_HEAT1D_SINE = 1, 2, 3, 4, 5, 6, 7
 TNORM_ONE, TNORM_TWO, TNORM_INF = 1, 2, 3
 ABI_VERSION = 8
@@ -64,6 +65,9 @@ SYMBOLS = {
     'mgb_heat1d_interp_rows': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_temporal_norm': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    'mgb_set_stop_flag': (C.c_int, [C.c_void_p]),
+    'mgb_write_flag': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    'mgb_convergence_flag': (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_inject_up': (C.c_int, [_LP, _LP, C.c_void_p]),
     'mgb_step': (C.c_int, [_LP, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_heat2d_layout': (C.c_int, [C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
@@ -80,6 +84,13 @@ SYMBOLS = {
     'mgb_heat1d_spectral_recur': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_sine_level_solve': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_heat1d_spectral_fixup': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    'mgb_rows_lincomb': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_void_p]),
+    'mgb_rows_sumsq': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mgb_allen_cahn_imex_rows': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_peer_put_row': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     'mgb_peer_wait_row': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     'mgb_peer_put_rows': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),

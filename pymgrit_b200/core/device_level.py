@@ -57,6 +57,21 @@ def pinned_array(shape):
     return arr
 
 
+def _stage_small(host):
+    """Copy of a small host array in page-locked memory (pooled), typed like the array."""
+    nbytes = host.nbytes
+    bucket = 64
+    while bucket < nbytes:                 # few pool sizes: powers of two
+        bucket *= 2
+    buf = pinned_array((bucket // 8,))
+    raw = buf._owner.view(_torch().uint8)[:nbytes]
+    view = raw.view({np.dtype(np.float64): _torch().float64, np.dtype(np.int32): _torch().int32}[host.dtype]).view(host.shape)
+    arr = view.numpy().view(_PinnedArray)
+    arr[...] = host
+    arr._owner, arr._slot, arr._base_tensor = view, buf._slot, buf._base_tensor
+    return arr
+
+
 def team_shape(kind, n):
     import os
     forced = os.environ.get('MGB_SHAPE_%d' % kind)            # experiments: "threads,chunk" for application kind `kind`
@@ -96,7 +111,8 @@ class DeviceLevel:
         self.n = int(app.ndof)                            # doubles of a row that carry values
         tiny = app.kind in (_lib.APP_DAHLQUIST, _lib.APP_BRUSSELATOR)
         self.pitch = int(app.row_pitch()) if hasattr(app, 'row_pitch') else (self.n if tiny else self.n + (self.n & 1))
-        self.team_threads, self.chunk = team_shape(app.kind, self.n)
+        self.batched = app.kind == _lib.APP_BATCHED          # no fused kernels, no struct mgb_level (core/batched.py)
+        self.team_threads, self.chunk = (0, 0) if self.batched else team_shape(app.kind, self.n)
         # the (asynchronous) zero fill of the level arrays runs on the device while the host builds the tables
         if u_init is not None:
             self.u = u_init
@@ -114,7 +130,7 @@ class DeviceLevel:
             self.finish_tables()
 
     def finish_tables(self):
-        if self.c is not None:
+        if self.c is not None or self.batched:
             return
         torch = _torch()
         app, dev = self.app, self.u.device
@@ -125,6 +141,11 @@ class DeviceLevel:
             if a is None:
                 return None
             owner = getattr(a, '_owner', None)
+            if owner is None and 0 < a.size * np.dtype(dtype).itemsize <= (1 << 20):
+                # small table: through page-locked memory as well -- a pageable cudaMemcpy waits for everything queued on
+                # the stream (the coarse sweeps of nested iteration) before it returns
+                a = _stage_small(np.ascontiguousarray(a, dtype=dtype))
+                owner = a._owner
             if owner is not None and a.dtype == dtype:        # page-locked already: asynchronous copy, no staging
                 ten = owner.to(dev, non_blocking=True)
                 slot = getattr(a, '_slot', None)
@@ -232,15 +253,49 @@ class DeviceLevel:
         return out
 
 
-def dt_classes(t, dt=None):
+_PAR_MIN = 1 << 17          # arrays at least this long are worked on in pieces by the table threads
+
+
+def parallel_pieces(n, fn):
+    """fn(a, b) over pieces [a, b) of range(n) on the table threads (core/rhs_tables.py; NumPy releases the GIL), in
+    this thread for short ranges.  Returns the list of results in order."""
+    if n < _PAR_MIN:
+        return [fn(0, n)]
+    from pymgrit_b200.core.rhs_tables import _pool
+    pool, nthr = _pool()
+    edges = np.linspace(0, n, nthr + 1).astype(int)
+    return list(pool.map(lambda ab: fn(int(ab[0]), int(ab[1])), zip(edges[:-1], edges[1:])))
+
+
+def time_steps(t):
+    """dt[i] = t[i] - t[i-1] (dt[0] = 0), its smallest and largest value: one pass over t in pieces (at nt = 2^20 the
+    separate NumPy passes of diff / min / max are a millisecond each)."""
+    t = np.asarray(t, dtype=float)
+    dt = np.empty(len(t))
+    if len(t) == 0:
+        return dt, 0.0, 0.0
+    dt[0] = 0.0
+    if len(t) == 1:
+        return dt, 0.0, 0.0
+
+    def piece(a, b):                       # steps into points a+1 .. b
+        np.subtract(t[a + 1:b + 1], t[a:b], out=dt[a + 1:b + 1])
+        return float(dt[a + 1:b + 1].min()), float(dt[a + 1:b + 1].max())
+    parts = parallel_pieces(len(t) - 1, piece)
+    return dt, min(p[0] for p in parts), max(p[1] for p in parts)
+
+
+def dt_classes(t, dt=None, lo_hi=None):
     """dt_i = t[i] - t[i-1] grouped by exact value: (distinct values, index per point or None).  dt: t[1:] - t[:-1] if the
-    caller has it already."""
+    caller has it already (lo_hi: its minimum and maximum, from time_steps)."""
     t = np.asarray(t, dtype=float)
     if len(t) < 2:
         return np.array([1.0]), None
     if dt is None:
         dt = t[1:] - t[:-1]
-    if dt[0] == dt[-1] and dt[0] == dt[len(dt) // 2] and dt.min() == dt.max():      # uniform grid: one pass each
+    if lo_hi is None:
+        lo_hi = (dt.min(), dt.max()) if dt[0] == dt[-1] == dt[len(dt) // 2] else (0.0, 1.0)
+    if lo_hi[0] == lo_hi[1]:                                    # uniform grid
         return dt[:1].copy(), None
     uniq, inv = np.unique(dt, return_inverse=True)
     idx = np.zeros(len(t), dtype=np.int32)

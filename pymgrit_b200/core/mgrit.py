@@ -80,7 +80,6 @@ class Mgrit:
             now = time.perf_counter()
             self.setup_phases.append((name, 1e3 * (now - _t_phase[0])))
             _t_phase[0] = now
-        self._phase = phase
 
         if transfer is None:
             transfer = [GridTransferCopy() for _ in range(len(problem) - 1)]
@@ -127,6 +126,10 @@ class Mgrit:
         # grid transfers: the identity is fused into the sweeps; a DeviceGridTransfer (spatial coarsening as row-wise
         # kernels) splits the FAS restriction and the correction around it; a transfer written in Python cannot run
         # inside a sweep
+        batched = [p.kind == _lib.APP_BATCHED for p in problem]
+        if any(batched) and not (all(batched) and all(type(tr) is GridTransferCopy for tr in transfer)):
+            raise Exception('applications on the batched path (BatchedApplication) need every level to be one and the '
+                            'identity transfer GridTransferCopy between the levels')
         for lvl, tr in enumerate(transfer):
             if type(tr) is GridTransferCopy:
                 if (problem[lvl].kind, problem[lvl].ndof) != (problem[lvl + 1].kind, problem[lvl + 1].ndof):
@@ -152,6 +155,8 @@ class Mgrit:
         self.comm_space_rank = -99
         self.comm_space_size = 1
 
+        if any(batched) and self.comm_time_size > 1:
+            raise Exception('the batched path (BatchedApplication) runs on one time rank')
         if conv_crit in (2, 3) and self.comm_time_size > 1:
             raise Exception('local convergence criteria (conv_crit 2, 3) are available on one time rank only; '
                             'use conv_crit 0 or 1 with several ranks')
@@ -225,7 +230,7 @@ class Mgrit:
         flags = []
         for lvl in range(self.lvl_max - 1):
             cp = self._lv[lvl].cpts
-            ok = (weight_c == 1.0 and self._xfer[lvl] is None
+            ok = (weight_c == 1.0 and self._xfer[lvl] is None and not batched[lvl]
                   and problem[lvl].kind in (_lib.APP_HEAT1D, _lib.APP_ADVECTION1D, _lib.APP_HEAT2D, _lib.APP_HEAT1D_2PTS,
                                             _lib.APP_HEAT1D_SINE)
                   and (cp is None or len(cp) < 2 or int(np.min(np.diff(cp))) >= 2)
@@ -244,7 +249,14 @@ class Mgrit:
             if sp is not None:
                 self._spectral[self.lvl_max - 1] = sp
         self.comm_time.setup_peer_exchange(self)         # ghost rows over peer memory where the ranks can (core/comm.py)
-        self.u = [_LevelVectors(lv, 'u', self._materialise_f_points if k == 0 else None) for k, lv in enumerate(self._lv)]
+        import weakref
+        me = weakref.ref(self)               # no reference cycle: a dropped solver frees its 8.6 GB level at once
+
+        def before_read():
+            solver = me()
+            if solver is not None:
+                solver._materialise_f_points()
+        self.u = [_LevelVectors(lv, 'u', before_read if k == 0 else None) for k, lv in enumerate(self._lv)]
         self.g = [None] + [_LevelVectors(lv, 'g') for lv in self._lv[1:]]
         self.v = [None] * self.lvl_max       # never materialised: identical to the fine level's C-point rows ...
         self._rres = [None] * self.lvl_max   # ... except below a spatial transfer: v, fine residual rows, their restriction
@@ -258,6 +270,10 @@ class Mgrit:
                 self.v[lvl + 1] = _LevelVectors(coarse, 'v')
                 self._rres[lvl] = torch.zeros((ncp, fine.pitch), dtype=torch.float64, device=fine.u.device)
                 self._rresc[lvl] = torch.zeros((ncp, coarse.pitch), dtype=torch.float64, device=fine.u.device)
+        self._batched = None
+        if any(batched):
+            from pymgrit_b200.core.batched import BatchedSweeps
+            self._batched = BatchedSweeps(self)
         phase('path flags, coarsest solver, peer exchange')
         self._init_levels()
         phase('initial condition')
@@ -472,7 +488,7 @@ class Mgrit:
         self.iteration(lvl=lvl + 1, cycle_type=cycle_type, iteration=iteration, first_f=True)
         # correction + the F-relaxation of mgrit.py:287, one launch; on level 0 only the last F-point of every interval
         # is stored while the solver iterates (_materialise_f_points)
-        lazy = lvl == 0 and self._lazy_f and self.lvl_max > 1
+        lazy = lvl == 0 and self._lazy_f and self.lvl_max > 1 and self._batched is None
         self.error_correction(lvl=lvl, f_relax=True, last_only=lazy)
         if lazy:
             self._f_stale = True
@@ -482,16 +498,22 @@ class Mgrit:
     def f_relax(self, lvl: int, last_only: bool = False) -> None:
         """F-relaxation (mgrit.py:292-333): one launch over all coarse intervals.  last_only: store only the last
         F-point of every interval (down-sweep of a cycle, where the other F-points are never read)."""
+        if self._batched is not None:
+            return self._batched.f_relax(lvl, last_only)
         flags = _lib.F_RELAX_LAST_ONLY if last_only else 0
         _lib.check(_lib.lib().mgb_f_relax(self._lv[lvl].ref, flags, self._stream()), 'f_relax')
 
     def c_relax(self, lvl: int) -> None:
         """C-relaxation (mgrit.py:335-370)."""
+        if self._batched is not None:
+            return self._batched.c_relax(lvl)
         _lib.check(_lib.lib().mgb_c_relax(self._lv[lvl].ref, float(self.weight_c), self._stream()), 'c_relax')
         self._exchange_ghost(lvl)
 
     def fas_residual(self, lvl: int) -> None:
         """Injection + FAS right-hand side of the next coarser level (mgrit.py:488-549)."""
+        if self._batched is not None:
+            return self._batched.fas_residual(lvl)
         fine, coarse = self._lv[lvl], self._lv[lvl + 1]
         xfer = self._xfer[lvl]
         if xfer is not None:
@@ -526,6 +548,8 @@ class Mgrit:
     def error_correction(self, lvl: int, f_relax: bool = False, last_only: bool = False) -> None:
         """Coarse-grid correction of the C-points (mgrit.py:715-726), optionally fused with the next F-relaxation
         (last_only: of which only the last point of every interval is stored)."""
+        if self._batched is not None:
+            return self._batched.error_correction(lvl, f_relax, last_only)
         xfer = self._xfer[lvl]
         if xfer is not None:
             fine, coarse = self._lv[lvl], self._lv[lvl + 1]
@@ -546,6 +570,8 @@ class Mgrit:
         in sine space (csrc/spectral.cu): two transforms and n independent scalar recurrences instead of a chain of
         tridiagonal solves; the time ranks exchange one all-gather of two rows each instead of the rank-to-rank
         chain (mgrit.py:467-484)."""
+        if self._batched is not None:
+            return self._batched.forward_solve(lvl)
         lv = self._lv[lvl]
         sp = self._spectral.get(lvl) if lv.npts > 0 else None
         if sp is None:
@@ -566,6 +592,8 @@ class Mgrit:
                 self._xfer[lvl].interpolate_rows(len(fine.cpts), 1, coarse.u, None, fine.u, fine.cpts_dev, False,
                                                  coarse.app)
                 self.launches += 1
+            elif self._batched is not None:
+                self._batched.inject_up(lvl)
             else:
                 _lib.check(_lib.lib().mgb_inject_up(self._lv[lvl].ref, self._lv[lvl + 1].ref, self._stream()),
                            'inject_up')
@@ -580,11 +608,17 @@ class Mgrit:
     # ------------------------------------------------------------------------------------------
     def compute_residual(self):
         """Squared residual norms at the local C-points of level 0 (mgrit.py:387-413), left on the device."""
+        if self._batched is not None:
+            self._batched.residual_norms(self._sq)
+            return self._sq
         _lib.check(_lib.lib().mgb_residual_norms(self._lv[0].ref, self._sq.data_ptr(), self._stream()), 'residual_norms')
         return self._sq
 
     def compute_jump(self):
         """Squared jump norms at the local C-points (mgrit.py:372-385)."""
+        if self._batched is not None:
+            self._batched.jump_norms(self.save_values_last_iter, self._sq)
+            return self._sq
         _lib.check(_lib.lib().mgb_jump_norms(self._lv[0].ref, self.save_values_last_iter.data_ptr(), self._sq.data_ptr(),
                                              self._stream()), 'jump_norms')
         return self._sq
@@ -632,12 +666,88 @@ class Mgrit:
             return '{0: <32}'.format(f" | conv: {self.conv[iteration + 1]}")
         return '{0: <32}'.format(f" | conv on process {self.comm_time_size - 1}: {self.conv[iteration + 1]}")
 
+    def _can_queue_ahead(self) -> bool:
+        """The stopping test can run on the device, one iteration behind the host (include/mgrit_b200.h,
+        mgb_convergence_flag), when nobody needs the residual of an iteration before the next one is queued: no
+        per-iteration log line (logging level above INFO), no per-iteration output function, the global residual
+        criterion, and only sweeps that honour the stop flag (no spatial grid transfer)."""
+        import os
+        return (os.environ.get('MGB_QUEUE_AHEAD', '1') != '0' and self._log_lvl > logging.INFO
+                and not (self.output_fcn is not None and self.output_lvl == 2)
+                and self.conv_crit == 0 and all(x is None for x in self._xfer) and self.lvl_max > 1
+                and self._batched is None)
+
+    def _solve_queued_ahead(self) -> None:
+        """solve()'s loop with the host one iteration ahead of the device.  Iteration k+1 is queued before the residual of
+        iteration k is known; if that residual meets the tolerance the device raises the stop flag and every sweep of
+        iteration k+1 returns at once, so the iterates, the iteration count and the residual history are those of the
+        plain loop -- without the device idling while the host reads one double and queues the next cycle."""
+        torch = _lib_torch()
+        lib = _lib.lib()
+        dev = self._lv[0].u.device
+        nslot = self.iter_max + 1
+        if getattr(self, '_hist_dev', None) is None or len(self._hist_dev) < nslot:
+            self._hist_dev = torch.zeros(nslot, dtype=torch.float64, device=dev)
+            self._hist_host = torch.zeros(nslot, dtype=torch.float64).pin_memory()
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        flag_ptr = self._flag.data_ptr()
+        _lib.check(lib.mgb_write_flag(flag_ptr, 0, self._stream()), 'write_flag')
+        _lib.check(lib.mgb_set_stop_flag(flag_ptr), 'set_stop_flag')
+        events = {}
+        try:
+            def read(k):
+                """Residual of iteration k (1-based) once its copy has arrived; True if it stops the iteration."""
+                events.pop(k).synchronize()
+                val = float(self._hist_host[k])
+                self.conv[k] = np.sqrt(val) if self._t_norm_id == 2 else val
+                self.solve_iter = k
+                return self.conv[k] < self.tol
+
+            done = False
+            queued = 0
+            for iteration in range(self.iter_max):
+                self.iteration(lvl=0, cycle_type=self.cycle_type, iteration=iteration, first_f=True)
+                self._queue_convergence(iteration + 1)
+                ev = torch.cuda.Event()
+                self._hist_host[iteration + 1:iteration + 2].copy_(self._hist_dev[iteration + 1:iteration + 2], non_blocking=True)
+                ev.record()
+                events[iteration + 1] = ev
+                queued = iteration + 1
+                if iteration >= 1 and read(iteration):
+                    done = True                      # iteration `iteration + 1` is queued but will not run
+                    break
+            if not done:
+                read(queued)
+        finally:
+            _lib.check(lib.mgb_write_flag(flag_ptr, 0, self._stream()), 'write_flag')
+            _lib.check(lib.mgb_set_stop_flag(None), 'set_stop_flag')
+
+    def _queue_convergence(self, slot: int) -> None:
+        """Residual norms, temporal norm, reduction over the time ranks, and the device-side stopping test."""
+        lv0 = self._lv[0]
+        ncp = 0 if lv0.cpts is None else len(lv0.cpts)
+        if ncp > 0:
+            sq = self.compute_residual()
+            _lib.check(_lib.lib().mgb_temporal_norm(sq.data_ptr(), ncp, self._t_norm_id, self._norm_out.data_ptr(),
+                                                    self._stream()), 'temporal_norm')
+        else:
+            self._norm_out.zero_()
+        part = self.comm_time.reduce_norm(self._norm_out, self._t_norm_id)
+        _lib.check(_lib.lib().mgb_convergence_flag(part.data_ptr(), self._t_norm_id, float(self.tol),
+                                                   self._hist_dev[slot:].data_ptr(), self._flag.data_ptr(),
+                                                   self._stream()), 'convergence_flag')
+
     def solve(self) -> dict:
         """Iterate until the stopping criterion is met (mgrit.py:590-646)."""
         torch = _lib_torch()
         self.log_info("Start solve")
         runtime_solve_start = time.time()
-        for iteration in range(self.iter_max):
+        if self._can_queue_ahead():
+            self._solve_queued_ahead()
+            iterations = ()
+        else:
+            iterations = range(self.iter_max)
+        for iteration in iterations:
             self.solve_iter = iteration + 1
             time_it_start = time.time()
             self.iteration(lvl=0, cycle_type=self.cycle_type, iteration=iteration, first_f=True)

@@ -41,6 +41,14 @@ def _strided(mask, stride):
     return out
 
 
+def _increasing(t):
+    """t[i] < t[i+1] for all i (in pieces on the table threads for long grids)."""
+    if len(t) < 2:
+        return True
+    from pymgrit_b200.core.device_level import parallel_pieces
+    return all(parallel_pieces(len(t) - 1, lambda a, b: bool(np.all(t[a + 1:b + 1] > t[a:b]))))
+
+
 def c_point_masks(global_t):
     """is_c[l][i]: point i of level l is also a point of level l+1 (mgrit.py:212, 768-770); all True on the coarsest."""
     masks = []
@@ -51,7 +59,7 @@ def c_point_masks(global_t):
         tc = global_t[l + 1]
         mask = np.zeros(len(t), dtype=bool)
         stride = (len(t) - 1) // (len(tc) - 1) if len(tc) > 1 and (len(t) - 1) % (len(tc) - 1) == 0 else 0
-        increasing = bool(np.all(t[1:] > t[:-1]))
+        increasing = _increasing(t)
         if increasing and stride > 0 and np.array_equal(t[::stride], tc):
             mask[::stride] = True                        # the usual case t_coarse = t[::m]: no search needed
             mask = _strided(mask, stride)

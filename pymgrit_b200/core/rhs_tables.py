@@ -263,11 +263,15 @@ class RhsSplit:
         scale = None if scale is None else np.asarray(scale, dtype=float)
         cached = self._valid.get(self._key(t))
         if cached is not None and cached.shape == (q, len(t)):   # found while validating this grid
-            for k in range(q):
-                if scale is not None:
-                    np.multiply(cached[k], scale, out=out[:, k])
-                else:
-                    out[:, k] = cached[k]
+            from pymgrit_b200.core.device_level import parallel_pieces
+
+            def piece(a, b):
+                for k in range(q):
+                    if scale is not None:
+                        np.multiply(cached[k, a:b], scale[a:b], out=out[a:b, k])
+                    else:
+                        out[a:b, k] = cached[k, a:b]
+            parallel_pieces(len(t), piece)
             return out
         invT = np.ascontiguousarray(np.linalg.inv(self.basis[:, self.sel]).T)   # q x q system, q <= MAX_TERMS
 

@@ -27,6 +27,9 @@ int cuda_fail(cudaError_t e, const char *what) {
     return MGB_ECUDA;
 }
 
+static const int *g_stop = nullptr;
+const int *stop_flag() { return g_stop; }
+
 const DeviceInfo *device_info() {
     static DeviceInfo info;
     static int state = 0;  // 0 unknown, 1 ok, 2 failed
@@ -146,6 +149,7 @@ static int check_level(const mgb_level *l, const SweepTable **tab, LevelDev *out
     out->nrow = (l->app == MGB_APP_HEAT1D_2PTS) ? l->pitch : l->n;  // doubles of a row the row-wise helpers touch
     out->sig = multi ? l->sig_dev : nullptr;
     out->diag = (l->app == MGB_APP_HEAT1D_SINE) ? l->diag_dev : nullptr;
+    out->stop = g_stop;
     if (multi) out->n = out->tile;
     if (tiny && l->t_dev == nullptr) return fail(MGB_EINVAL, "ODE applications need the time grid t_dev%s");
     return MGB_OK;
@@ -217,7 +221,9 @@ __global__ void k_copy_rows(const double *__restrict__ src, double *__restrict__
 __device__ __forceinline__ double tn_map(double v, int mode) { return mode == MGB_TNORM_TWO ? v : sqrt(v); }
 __device__ __forceinline__ double tn_comb(double a, double b, int mode) { return mode == MGB_TNORM_INF ? fmax(a, b) : a + b; }
 
-__global__ void k_temporal_norm(const double *__restrict__ sq, int count, int mode, double *__restrict__ out) {
+__global__ void k_temporal_norm(const double *__restrict__ sq, int count, int mode, double *__restrict__ out,
+                                const int *__restrict__ stop) {
+    if (stop != nullptr && *stop != 0) return;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     const int T = blockDim.x;
     int q = threadIdx.x;
@@ -256,6 +262,18 @@ __global__ void k_sumsq(int n, const double *__restrict__ x, double *__restrict_
     acc = block_sum(acc);
     if (threadIdx.x == 0) out[0] = acc;
 }
+
+// hist[0] = the (rank-reduced) temporal norm; the flag goes up if the stopping test of mgrit.py:626 holds
+__global__ void k_convergence_flag(const double *__restrict__ partial, int mode, double tol, double *__restrict__ hist,
+                                   int *__restrict__ flag) {
+    if (*flag != 0) return;  // queued after the criterion was met: leave the history alone
+    const double v = partial[0];
+    hist[0] = v;
+    const double conv = (mode == MGB_TNORM_TWO) ? sqrt(v) : v;
+    if (conv < tol) *flag = 1;
+}
+
+__global__ void k_set_flag(int *flag, int value) { *flag = value; }
 
 // ---- host-side step constants -------------------------------------------------------------------------
 static long double lpow(long double b, long e) { return e <= 0 ? 1.0L : powl(b, (long double)e); }
@@ -489,8 +507,29 @@ int mgb_temporal_norm(const double *sq_dev, int32_t count, int32_t t_norm, doubl
     if (sq_dev == nullptr || out_dev == nullptr || count < 0 || t_norm < 1 || t_norm > 3)
         return fail(MGB_EINVAL, "bad argument%s");
     if (device_info() == nullptr) return MGB_ECUDA;
-    k_temporal_norm<<<1, 1024, 0, (cudaStream_t)stream>>>(sq_dev, count, t_norm, out_dev);
+    k_temporal_norm<<<1, 1024, 0, (cudaStream_t)stream>>>(sq_dev, count, t_norm, out_dev, g_stop);
     return cuda_fail(cudaGetLastError(), "temporal_norm");
+}
+
+int mgb_set_stop_flag(const int32_t *flag_dev) {
+    g_stop = flag_dev;
+    return MGB_OK;
+}
+
+int mgb_write_flag(int32_t *flag_dev, int32_t value, void *stream) {
+    if (flag_dev == nullptr) return fail(MGB_EINVAL, "bad argument%s");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    k_set_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, value);
+    return cuda_fail(cudaGetLastError(), "write_flag");
+}
+
+int mgb_convergence_flag(const double *norm_dev, int32_t t_norm, double tol, double *hist_dev, int32_t *flag_dev,
+                         void *stream) {
+    if (norm_dev == nullptr || hist_dev == nullptr || flag_dev == nullptr || t_norm < 1 || t_norm > 3)
+        return fail(MGB_EINVAL, "bad argument%s");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    k_convergence_flag<<<1, 1, 0, (cudaStream_t)stream>>>(norm_dev, t_norm, tol, hist_dev, flag_dev);
+    return cuda_fail(cudaGetLastError(), "convergence_flag");
 }
 
 int mgb_inject_up(const mgb_level *fine, const mgb_level *coarse, void *stream) {

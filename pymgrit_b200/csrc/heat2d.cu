@@ -106,7 +106,7 @@ __global__ void k_heat2d_boundary(int nx, int ny, int nint, int nint_pad, int pi
     }
 }
 
-static int launch_gemm(int M, int N, int K, const double *A, int lda, long sA, const double *B, int ldb, long sB, double *C,
+int launch_gemm(int M, int N, int K, const double *A, int lda, long sA, const double *B, int ldb, long sB, double *C,
                        int ldc, long sC, int count, cudaStream_t st) {
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, count);
     k_dgemm<<<grid, 256, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC);

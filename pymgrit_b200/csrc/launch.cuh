@@ -61,12 +61,16 @@ struct Launch {
     }
 
     static int rows_extra(const LevelDev &L) { return (L.g ? 1 : 0) + (L.rhs_dense ? 1 : 0); }
+    // Input slots of a sweep that pops `base` rows per item plus a row per step on levels with g / dense right-hand-side
+    // rows.  (Measured: three more slots for those per-step rows do not help -- level 1 of the headline workload got 20 %
+    // slower, profiles/r02i_timeline.txt: the chains there wait for the dependent loads of Phi, not for the bulk copies.)
+    static int slots(const LevelDev &L, int base) { return base + rows_extra(L); }
     static int nsys(const LevelDev &L) { return L.nsys > 1 ? L.nsys : 1; }
 
     // flags & 1: store only the last point of every interval (the other F-points are dead in a down-sweep)
     static int f_relax(const LevelDev &L, int flags, cudaStream_t st) {
         if (L.ncpts < 1) return 0;
-        const int nin = 2 + rows_extra(L);
+        const int nin = slots(L, 2);
         const int nw = L.ncpts * nsys(L);
         int grid;
         if (int rc = grid_for(k_chain<Phi>, nw, nin, &grid)) return rc;
@@ -109,7 +113,7 @@ struct Launch {
     // C-relaxation + F-relaxation + FAS restriction in one pass (k_down); one more slot: the stash
     static int down(const LevelDev &L, const LevelDev &G, cudaStream_t st) {
         if (L.ncpts < 2) return 0;
-        const int nin = 1 + rows_extra(L), nw = (L.ncpts - 1) * nsys(L);
+        const int nin = slots(L, 1), nw = (L.ncpts - 1) * nsys(L);
         int grid;
         if (int rc = grid_for(k_down<Phi>, nw, nin + 1, &grid)) return rc;
         k_down<Phi><<<grid, Phi::T, smem_bytes(nin + 1), st>>>(L, G, nw, nin);
@@ -120,7 +124,7 @@ struct Launch {
         if (L.ncpts < 1) return 0;
         // every F-point stored: the sweep is a stream of rows, three input slots keep the loads ahead; last point only: two
         // rows in per interval, fewer slots leave room for more resident teams
-        const int nin = (frelax == 2 ? 2 : 3) + rows_extra(L), nw = L.ncpts * nsys(L);
+        const int nin = slots(L, frelax == 2 ? 2 : 3), nw = L.ncpts * nsys(L);
         int grid;
         if (int rc = grid_for(k_correct<Phi>, nw, nin, &grid)) return rc;
         k_correct<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, G, frelax, kfirst, nw, nin);
@@ -173,7 +177,7 @@ struct Launch {
         L.cpts = nullptr;
         L.ncpts = 0;
         if (L.npts < 2) return 0;
-        const int nin = 2 + rows_extra(L), nw = (L.npts - 1) * nsys(L);
+        const int nin = slots(L, 2), nw = (L.npts - 1) * nsys(L);
         int grid;
         if (int rc = grid_for(k_window<Phi>, nw, nin, &grid)) return rc;
         k_window<Phi><<<grid, Phi::T, smem_bytes(nin), st>>>(L, old, k, nw, nin);

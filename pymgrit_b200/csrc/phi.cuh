@@ -46,7 +46,13 @@ struct LevelDev {
     int nrow;
     const double *sig;  // [pitch] per-element symbol of the spatial operator (Heat2D), row layout; NULL otherwise
     const double *diag; // Heat1DSine: [2][E][T] thread-transposed eigenvalues lam_k and reciprocals 1/(1 + dt lam_k)
+    const int *stop;    // device flag set by mgb_convergence_flag once the stopping criterion is met: sweeps that were
+                        // queued ahead of that knowledge return at once (mgb_set_stop_flag); nullptr = not in use
 };
+
+// First statement of every sweep kernel.
+#define MGB_RETURN_IF_STOPPED(L) \
+    if ((L).stop != nullptr && *(L).stop != 0) return;
 
 // Applications without per-element item data
 struct NoItem {};
@@ -460,7 +466,7 @@ constexpr int kHeat2DMaxTerms = 3;
 template <int T_, int E_>
 struct Heat2D {
     using SH = Shape<T_, E_>;
-    static constexpr bool kTightChain = false;
+    static constexpr bool kTightChain = true;   // chain() below
     static constexpr bool kCtArg = false;
     static constexpr bool kItemInvariant = false;  // begin_item depends on the level only, not on the work item
     static constexpr int T = T_, E = E_;
@@ -471,8 +477,11 @@ struct Heat2D {
         double ex;   // (1 - theta) * dt: the explicit part, ... = (1 - ex sig) x + rhs   (0 for backward Euler)
     };
     struct Item {
-        double sig[E];
+        double sig[E];       // symbol of the spatial operator (boundary tiles: the Dirichlet values)
         double rx[QMAX][E];
+        double inv[E];       // 1 / (1 + theta dt sig) for the dt in dtc ...
+        double fac[E];       // ... and 1 - (1 - theta) dt sig (Crank-Nicolson / forward Euler)
+        double dtc, exc;     // the step the two arrays were made for (NaN: none yet)
         bool boundary;
     };
     __device__ static __forceinline__ int row_n(const LevelDev &L) { return L.n; }
@@ -489,10 +498,67 @@ struct Heat2D {
         for (int k = 0; k < QMAX; ++k)
             if (k < L.nrhs) pipe.pop(it.rx[k], team);
         it.boundary = sys >= L.ip[0];
+        it.dtc = it.exc = nan("");
     }
     // all levels share the symbol and the right-hand-side factors (checked by the C ABI)
     template <class TeamT>
     __device__ static __forceinline__ void retarget_item(Item &, const LevelDev &, const LevelDev &, TeamT &) {}
+
+    __device__ static __forceinline__ void factors(Item &it, const C &c) {
+        // The two per-element factors depend on the step size only: they are made once per (item, dt) -- one division per
+        // element -- and every step of that size is then a multiplication (a division per element and step used to be
+        // most of the arithmetic of a sweep).
+        if (c.dt != it.dtc || c.ex != it.exc) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                it.inv[j] = __ddiv_rn(1.0, fma(c.dt, it.sig[j], 1.0));
+                it.fac[j] = fma(-c.ex, it.sig[j], 1.0);
+            }
+            it.dtc = c.dt;
+            it.exc = c.ex;
+        }
+    }
+
+    // Steps i0 .. i1-1 without g / dense rows and nothing stored in between, backward Euler on a uniform level with at
+    // most one right-hand-side term: as Heat1DSine::chain (one coalesced load of 32 time factors per warp, a step is a
+    // shuffle, E FMAs and E multiplications).
+    __device__ static __forceinline__ bool chain_ok(const C &c, const LevelDev &L) {
+        return c.ex == 0.0 && c.dt != 0.0 && L.ndt == 1 && L.nrhs <= 1;
+    }
+    __device__ static __forceinline__ double chain_prefetch(const LevelDev &L, int i0, int i1, int lane) {
+        return (L.nrhs == 1 && i0 + lane < i1) ? __ldg(L.rhs_t + i0 + lane) : 0.0;
+    }
+    template <class TeamT>
+    __device__ static __forceinline__ void chain(double (&x)[E], const C &c, Item &it, const LevelDev &L, int i0, int i1,
+                                                 TeamT &team, double first) {
+        if (i1 <= i0) return;
+        if (it.boundary) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) x[j] = it.sig[j];
+            return;
+        }
+        factors(it, c);
+        if (L.nrhs == 0) {
+            for (int i = i0; i < i1; ++i) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) x[j] = x[j] * it.inv[j];
+            }
+            return;
+        }
+        double nxt = first;
+        for (int base = i0; base < i1; base += 32) {
+            const double cur = nxt;
+            const int nb = base + 32 + team.lane;
+            nxt = (nb < i1) ? __ldg(L.rhs_t + nb) : 0.0;
+            const int cnt = min(32, i1 - base);
+#pragma unroll 1
+            for (int s = 0; s < cnt; ++s) {
+                const double ct = __shfl_sync(0xffffffffu, cur, s);
+#pragma unroll
+                for (int j = 0; j < E; ++j) x[j] = fma(ct, it.rx[0][j], x[j]) * it.inv[j];
+            }
+        }
+    }
 
     template <class TeamT>
     __device__ static __forceinline__ void apply(double (&x)[E], const C &c, Item &it, const LevelDev &L, int i,
@@ -502,9 +568,10 @@ struct Heat2D {
             for (int j = 0; j < E; ++j) x[j] = it.sig[j];
             return;
         }
+        factors(it, c);
         if (c.ex != 0.0) {  // Crank-Nicolson / forward Euler: (I - (1 - theta) dt L) u first (heat_2d.py:306, 352)
 #pragma unroll
-            for (int j = 0; j < E; ++j) x[j] = x[j] * fma(-c.ex, it.sig[j], 1.0);
+            for (int j = 0; j < E; ++j) x[j] = x[j] * it.fac[j];
         }
 #pragma unroll
         for (int k = 0; k < QMAX; ++k) {
@@ -516,7 +583,7 @@ struct Heat2D {
         }
         if (c.dt != 0.0) {
 #pragma unroll
-            for (int j = 0; j < E; ++j) x[j] = __ddiv_rn(x[j], fma(c.dt, it.sig[j], 1.0));
+            for (int j = 0; j < E; ++j) x[j] = x[j] * it.inv[j];
         }
     }
 };

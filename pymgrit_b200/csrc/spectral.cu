@@ -47,7 +47,8 @@ constexpr int GN = 64, GK = 16;
 template <int TM>
 __global__ void __launch_bounds__(256) k_rows_gemm(int M, int N, int K, const double *__restrict__ A, int lda,
                                                    const double *__restrict__ a_row0, const double *__restrict__ B, int ldb,
-                                                   double *__restrict__ Cm, int ldc) {
+                                                   double *__restrict__ Cm, int ldc, const int *__restrict__ stop) {
+    if (stop != nullptr && *stop != 0) return;
     constexpr int RM = TM / 16;                 // output rows per thread
     constexpr int LA = (TM * GK + 255) / 256;   // A elements staged per thread and slab
     __shared__ double As[GK][TM + 4];
@@ -136,7 +137,8 @@ __global__ void k_dst_twiddles(int N, double2 *__restrict__ w) {
 __global__ void __launch_bounds__(256) k_rows_dst(const int nrows, const int n, const int log2n2,
                                                   const double *__restrict__ A, const int lda,
                                                   const double *__restrict__ a_row0, const double2 *__restrict__ tw,
-                                                  double *__restrict__ Cm, const int ldc) {
+                                                  double *__restrict__ Cm, const int ldc, const int *__restrict__ stop) {
+    if (stop != nullptr && *stop != 0) return;
     extern __shared__ double2 z[];  // 2N complex
     const int N = n + 1, N2 = 2 * N;
     const double scale = -0.5 * sqrt(2.0 / N);
@@ -244,7 +246,8 @@ __global__ void __launch_bounds__(1024) k_sine_solve(double *__restrict__ U, con
                                                      const int npts, const double *__restrict__ t,
                                                      const double *__restrict__ lam, const double *__restrict__ rhs_t,
                                                      const double *__restrict__ rxh, double *__restrict__ ends,
-                                                     const int zero_start, const int len) {
+                                                     const int zero_start, const int len, const int *__restrict__ stop) {
+    if (stop != nullptr && *stop != 0) return;
     __shared__ double sA[kMaxChunks][32], sB[kMaxChunks][32];
     const int tx = threadIdx.x, c = threadIdx.y, nch = blockDim.y;
     const int kreal = blockIdx.x * 32 + tx;
@@ -285,7 +288,9 @@ __global__ void __launch_bounds__(1024) k_sine_solve(double *__restrict__ U, con
 // then W[0] = s and W[i] += (prod_{j <= i} 1 / (1 + dt_j lam)) s.
 __global__ void __launch_bounds__(128) k_spectral_fixup(double *__restrict__ W, int pitch, int n, int npts,
                                                         const double *__restrict__ t, const double *__restrict__ lam,
-                                                        const double *__restrict__ all, int rank) {
+                                                        const double *__restrict__ all, int rank,
+                                                        const int *__restrict__ stop) {
+    if (stop != nullptr && *stop != 0) return;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const double lk = lam[k];
@@ -337,11 +342,11 @@ int mgb_rows_gemm(int32_t m, int32_t n, int32_t k, const double *a_dev, int32_t 
     const int nb = (n + GN - 1) / GN;
     // the tallest tile whose grid still covers the SMs
     if ((long)((m + 63) / 64) * nb >= di->sms || m > 2048)
-        k_rows_gemm<64><<<dim3(nb, (m + 63) / 64), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc);
+        k_rows_gemm<64><<<dim3(nb, (m + 63) / 64), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc, stop_flag());
     else if ((long)((m + 31) / 32) * nb >= di->sms || m > 256)
-        k_rows_gemm<32><<<dim3(nb, (m + 31) / 32), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc);
+        k_rows_gemm<32><<<dim3(nb, (m + 31) / 32), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc, stop_flag());
     else
-        k_rows_gemm<16><<<dim3(nb, (m + 15) / 16), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc);
+        k_rows_gemm<16><<<dim3(nb, (m + 15) / 16), 256, 0, st>>>(m, n, k, a_dev, lda, a_row0_dev, b_dev, ldb, c_dev, ldc, stop_flag());
     return cuda_fail(cudaGetLastError(), "rows_gemm");
 }
 
@@ -374,7 +379,7 @@ int mgb_rows_dst(int32_t m, int32_t n, const double *a_dev, int32_t lda, const d
     while ((1 << log2n2) < 2 * N) ++log2n2;
     const int grid = m < 8 * di->sms ? m : 8 * di->sms;
     k_rows_dst<<<grid, 256, smem, (cudaStream_t)stream>>>(m, n, log2n2, a_dev, lda, a_row0_dev, (const double2 *)tw_dev,
-                                                          c_dev, ldc);
+                                                          c_dev, ldc, stop_flag());
     return cuda_fail(cudaGetLastError(), "rows_dst");
 }
 
@@ -388,7 +393,8 @@ static int launch_sine_solve(double *U, const double *G, int pitch, int n, int n
     const dim3 grid((n + 31) / 32), block(32, nch);
 #define MGB_RECUR(Q)                                                                                                  \
     case Q:                                                                                                           \
-        k_sine_solve<Q><<<grid, block, 0, st>>>(U, G, pitch, n, npts, t, lam, rhs_t, rxh, ends, zero_start, len);     \
+        k_sine_solve<Q><<<grid, block, 0, st>>>(U, G, pitch, n, npts, t, lam, rhs_t, rxh, ends, zero_start, len,      \
+                                                stop_flag());                                                        \
         break;
     switch (nrhs) {
         MGB_RECUR(0)
@@ -433,7 +439,7 @@ int mgb_heat1d_spectral_fixup(const mgb_level *lvl, const double *lam_dev, doubl
         return heat2d_fail("heat1d_spectral_fixup: bad argument");
     if (device_info() == nullptr) return MGB_ECUDA;
     k_spectral_fixup<<<(lvl->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(work_dev, lvl->pitch, lvl->n, lvl->npts, lvl->t_dev,
-                                                                            lam_dev, all_ends_dev, rank);
+                                                                            lam_dev, all_ends_dev, rank, stop_flag());
     return cuda_fail(cudaGetLastError(), "heat1d_spectral_fixup");
 }
 

@@ -216,6 +216,7 @@ struct GenChain {
 // limiter, and the smaller L1 and the spills cost what the extra warps gain; profiles/r01c_last_only_occupancy.txt.)
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_chain(const LevelDev L, const int nw, const int last_only, const int nin) {
+    MGB_RETURN_IF_STOPPED(L)
     using SH = typename Phi::SH;
     Team<Phi::T> team(g_smem);
     RowPipe<SH, GenChain> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenChain(L, blockIdx.x, nw, gridDim.x));
@@ -299,6 +300,7 @@ struct GenWindow {
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_window(const LevelDev L, const double *__restrict__ old, const int k,
                                                    const int nw, const int nin) {
+    MGB_RETURN_IF_STOPPED(L)
     using SH = typename Phi::SH;
     Team<Phi::T> team(g_smem);
     RowPipe<SH, GenWindow> pipe(g_smem, nin, L.tile, Phi::row_n(L), GenWindow(L, old, k, blockIdx.x, nw, gridDim.x));
@@ -391,6 +393,7 @@ struct GenCRelax {
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_c_relax(const LevelDev L, const double wgt, const int nw, const int nin,
                                                     const int kbase) {
+    MGB_RETURN_IF_STOPPED(L)
     using SH = typename Phi::SH;
     const bool weighted = (wgt != 1.0);
     Team<Phi::T> team(g_smem);
@@ -492,6 +495,7 @@ struct GenFas {
 
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_fas_residual(const LevelDev L, const LevelDev G, const int nw, const int nin) {
+    MGB_RETURN_IF_STOPPED(L)
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
@@ -595,6 +599,7 @@ struct GenResRows {
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_residual_rows(const LevelDev L, double *__restrict__ out, const int nw,
                                                           const int nin) {
+    MGB_RETURN_IF_STOPPED(L)
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
@@ -679,6 +684,7 @@ struct GenFasRhs {
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_fas_rhs(const LevelDev G, const double *__restrict__ V,
                                                     const double *__restrict__ RR, const int nw, const int nin) {
+    MGB_RETURN_IF_STOPPED(G)
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
@@ -807,6 +813,7 @@ struct GenDown {
 
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_down(const LevelDev L, const LevelDev G, const int nw, const int nin) {
+    MGB_RETURN_IF_STOPPED(L)
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
@@ -946,6 +953,7 @@ struct GenCorrect {
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_correct(const LevelDev L, const LevelDev G, const int frelax, const int kfirst,
                                                     const int nw, const int nin) {
+    MGB_RETURN_IF_STOPPED(L)
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);
@@ -1036,6 +1044,7 @@ struct GenResidual {
 template <class Phi>
 __global__ void __launch_bounds__(Phi::T) k_residual(const LevelDev L, double *__restrict__ out_sq, const int nw,
                                                      const int nin) {
+    MGB_RETURN_IF_STOPPED(L)
     using SH = typename Phi::SH;
     constexpr int E = Phi::E;
     Team<Phi::T> team(g_smem);

@@ -12,6 +12,7 @@ struct DeviceInfo {
 };
 const DeviceInfo *device_info();                 // api.cu; nullptr (and an error message) without a CUDA device
 int cuda_fail(cudaError_t e, const char *what);  // api.cu: records the message, returns MGB_ECUDA or 0
+const int *stop_flag();                          // api.cu: the device flag of mgb_set_stop_flag, or nullptr
 
 struct SweepTable {
     int team_threads;

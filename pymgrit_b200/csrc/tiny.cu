@@ -92,6 +92,7 @@ __device__ __forceinline__ void tiny_interval(const LevelDev &L, int k, int &s, 
 
 template <class P>
 __global__ void kt_chain(const LevelDev L, int nitems) {
+    MGB_RETURN_IF_STOPPED(L)
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nitems; k += gridDim.x * blockDim.x) {
         int s, e;
         tiny_interval(L, k, s, e);
@@ -107,6 +108,7 @@ __global__ void kt_chain(const LevelDev L, int nitems) {
 
 template <class P>
 __global__ void kt_c_relax(const LevelDev L, double w) {
+    MGB_RETURN_IF_STOPPED(L)
     for (int k = 1 + blockIdx.x * blockDim.x + threadIdx.x; k < L.ncpts; k += gridDim.x * blockDim.x) {
         // a run of adjacent C-points (non-uniform coarsening) is walked by the thread of its first point, in
         // ascending order like the reference's loop (mgrit.py:356)
@@ -128,6 +130,7 @@ __global__ void kt_c_relax(const LevelDev L, double w) {
 
 template <class P>
 __global__ void kt_fas(const LevelDev L, const LevelDev G) {
+    MGB_RETURN_IF_STOPPED(L)
     for (int j = 1 + blockIdx.x * blockDim.x + threadIdx.x; j < L.ncpts; j += gridDim.x * blockDim.x) {
         const int c = L.cpts[j];
         double x[P::N], y[P::N], v[P::N];
@@ -143,6 +146,7 @@ __global__ void kt_fas(const LevelDev L, const LevelDev G) {
                 x[q] = ADD(SUB(x[q], y[q]), y[q]);
         }
         ld<P>(v, L.u, L.cpts[j - 1], L.pitch);
+        if (j == 1) st<P>(v, G.u, 0, G.pitch);  // point 0 (initial condition / ghost) is injected like any other C-point
         advance_tiny<P>(v, G, j, false);
 #pragma unroll
         for (int q = 0; q < P::N; ++q) x[q] = SUB(x[q], v[q]);
@@ -152,6 +156,7 @@ __global__ void kt_fas(const LevelDev L, const LevelDev G) {
 
 template <class P>
 __global__ void kt_correct(const LevelDev L, const LevelDev G, int frelax, int kfirst) {
+    MGB_RETURN_IF_STOPPED(L)
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.ncpts; k += gridDim.x * blockDim.x) {
         int s, e;
         tiny_interval(L, k, s, e);
@@ -172,6 +177,7 @@ __global__ void kt_correct(const LevelDev L, const LevelDev G, int frelax, int k
 
 template <class P>
 __global__ void kt_residual(const LevelDev L, double *out_sq) {
+    MGB_RETURN_IF_STOPPED(L)
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.ncpts; k += gridDim.x * blockDim.x) {
         if (k == 0) {
             out_sq[0] = 0.0;

@@ -207,10 +207,8 @@ class Heat1D(DeviceApplication):
         step-constant rows [dt, use_reciprocals], diag = [eigenvalues; 1 / (1 + dt lam)] thread-transposed, and dt per
         point."""
         t = np.asarray(t, dtype=float)
-        dt_full = np.empty(len(t))
-        dt_full[0] = 0.0
-        np.subtract(t[1:], t[:-1], out=dt_full[1:])
-        dts, dtidx = dl.dt_classes(t, dt_full[1:])
+        dt_full, dt_lo, dt_hi = dl.time_steps(t)
+        dts, dtidx = dl.dt_classes(t, dt_full[1:], (dt_lo, dt_hi))
         uniform = len(dts) == 1
         sconst = np.zeros((len(dts), 8))
         sconst[:, 0] = dts
@@ -229,10 +227,8 @@ class Heat1D(DeviceApplication):
             return self._level_tables_sine(t, team_threads, chunk)
         fac = self.a / self.dx ** 2                                   # heat_1d.py:185
         t = np.asarray(t, dtype=float)
-        dt_full = np.empty(len(t))
-        dt_full[0] = 0.0
-        np.subtract(t[1:], t[:-1], out=dt_full[1:])
-        dts, dtidx = dl.dt_classes(t, dt_full[1:])
+        dt_full, dt_lo, dt_hi = dl.time_steps(t)
+        dts, dtidx = dl.dt_classes(t, dt_full[1:], (dt_lo, dt_hi))
         tab = dict(ndt=len(dts), dtidx=dtidx,
                    sconst=dl.step_const_table(self.kind, dts * fac, self.nx, team_threads, chunk))
         tab['cw'] = tab['sconst'].shape[1]

@@ -11,6 +11,8 @@ def b200_apps():
     apps = {'heat1d': P.Heat1D, 'advection1d': P.Advection1D, 'dahlquist': P.Dahlquist, 'brusselator': P.Brusselator}
     if hasattr(P, 'Heat2D'):
         apps['heat2d'] = P.Heat2D
+    if hasattr(P, 'AllenCahn'):
+        apps['allencahn'] = P.AllenCahn
     if hasattr(P, 'Heat1DBDF2'):
         apps['heat1d2pts'] = lambda method, **kw: {'BDF1': P.Heat1DBDF1, 'BDF2': P.Heat1DBDF2}[method](**kw)
     return apps

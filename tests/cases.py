@@ -149,6 +149,13 @@ CASES = {
     # examples/example_brusselator.py -> tests/mpi/results/brusselator
     'brusselator_example': dict(app='brusselator', app_kw=dict(), t=(0, 12, 641),
                                 grids=('index', [slice(None, None, 20)]), solver=dict(cf_iter=1)),
+    # examples/example_allen_cahn.py:36-37 (IMEX, two levels) at nx = 32; F-cycle / three levels / jump criterion variants
+    'allencahn_example': dict(app='allencahn', app_kw=dict(nx=32, method='IMEX'), t=(0, 0.032, 33),
+                              grids=_simple(2, 2), solver=dict(tol=1e-9)),
+    'allencahn_3lvl_f': dict(app='allencahn', app_kw=dict(nx=24, method='IMEX', nu=2, eps=0.05), t=(0, 0.032, 65),
+                             grids=_simple(3, 4), solver=dict(tol=1e-9, cycle_type='F', cf_iter=2, nested_iteration=False)),
+    'allencahn_jump': dict(app='allencahn', app_kw=dict(nx=15, method='IMEX', nu=2, eps=0.06), t=(0, 0.02, 41),
+                           grids=_simple(2, 4), solver=dict(tol=1e-8, conv_crit=1)),
     # examples/example_advection.py
     'advection_example': dict(app='advection1d', app_kw=dict(c=1, x_start=-1, x_end=1, nx=129), t=(0, 2, 129),
                               grids=('nt', [129, 65]), solver=dict(cf_iter=1, nested_iteration=False)),

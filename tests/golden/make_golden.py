@@ -33,10 +33,11 @@ from pymgrit.heat.heat_1d_2pts_bdf2 import Heat1DBDF2     # noqa: E402
 from pymgrit.advection.advection_1d import Advection1D    # noqa: E402
 from pymgrit.dahlquist.dahlquist import Dahlquist         # noqa: E402
 from pymgrit.brusselator.brusselator import Brusselator   # noqa: E402
+from pymgrit.allen_cahn.allen_cahn import AllenCahn       # noqa: E402
 import cases as C                                         # noqa: E402
 
 APPS = {'heat1d': Heat1D, 'heat2d': Heat2D, 'advection1d': Advection1D, 'dahlquist': Dahlquist,
-        'brusselator': Brusselator}
+        'brusselator': Brusselator, 'allencahn': AllenCahn}
 
 
 def heat1d2pts(method, **kw):

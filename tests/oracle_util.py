@@ -9,7 +9,8 @@ from oracle import mgrit_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 ORACLE_APPS = {'heat1d': O.Heat1DOracle, 'heat2d': O.Heat2DOracle, 'advection1d': O.Advection1DOracle,
-               'dahlquist': O.DahlquistOracle, 'brusselator': O.BrusselatorOracle, 'heat1d2pts': O.Heat1D2PtsOracle}
+               'dahlquist': O.DahlquistOracle, 'brusselator': O.BrusselatorOracle, 'heat1d2pts': O.Heat1D2PtsOracle,
+               'allencahn': O.AllenCahnOracle}
 
 
 def oracle_problem(case, solver=None):

@@ -400,3 +400,73 @@ def test_heat2d_theta_method_step_against_oracle(P, method):
     if method == 'FE':
         with pytest.raises(Exception):
             P.Heat2D(t_start=0, t_stop=1, nt=11, bc_left=1.0, **kw)
+
+
+def test_allen_cahn_known_answers_and_contract(P):
+    """tests/allen_cahn/test_allen_cahn.py: constructor, the initial condition, the IMEX step (test_heat_2d_step_imex),
+    the Vector arithmetic; the Newton branches raise (not built)."""
+    kw = dict(nx=3, eps=3, newton_tol=5, newton_maxiter=4, lin_tol=5, lin_maxiter=1, radius=0.25, nu=1, t_start=0, t_stop=1,
+              nt=11)
+    app = P.AllenCahn(method='IMEX', **kw)
+    assert (app.nx, app.nu, app.eps, app.newton_maxiter, app.newton_tol, app.lin_tol, app.lin_maxiter, app.radius,
+            app.method) == (3, 1, 3, 4, 5, 5, 1, 0.25, 'IMEX')
+    assert isinstance(app.vector_template, P.VectorAllenCahn2D) and isinstance(app.vector_t_start, P.VectorAllenCahn2D)
+    np.testing.assert_almost_equal(app.vector_t_start.get_values(), np.array([[-0.10732614, -0.05885746, -0.10732614],
+                                                                              [-0.05885746, 0.05885746, -0.05885746],
+                                                                              [-0.10732614, -0.05885746, -0.10732614]]))
+    res = app.step(u_start=app.vector_t_start, t_start=0, t_stop=0.1)
+    np.testing.assert_almost_equal(res.get_values(), np.array([[-0.07997795, -0.0640509, -0.07997795],
+                                                               [-0.0640509, -0.03719789, -0.0640509],
+                                                               [-0.07997795, -0.0640509, -0.07997795]]))
+    with pytest.raises(Exception):
+        P.AllenCahn(method='DE', **kw)
+    with pytest.raises(Exception):
+        P.AllenCahn(method='IMPL', **kw)                          # Newton branches: no device kernels
+    v1, v2 = P.VectorAllenCahn2D(3, 3), P.VectorAllenCahn2D(3, 3)
+    v1.set_values(np.ones((3, 3)))
+    v2.set_values(2 * np.ones((3, 3)))
+    np.testing.assert_equal((v1 + v2).get_values(), 3 * np.ones((3, 3)))
+    np.testing.assert_equal((v2 - v1).get_values(), np.ones((3, 3)))
+    np.testing.assert_equal((v1 * 5).get_values(), 5 * np.ones((3, 3)))
+    v1.set_values(np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9.]]))
+    assert abs(v1.norm() - np.linalg.norm(np.arange(1, 10.))) < 1e-14
+
+
+def test_allen_cahn_step_against_oracle_at_example_size(P):
+    """One IMEX step at the example's size (128 x 128 periodic nodes) against the oracle's sparse direct solve."""
+    from oracle import mgrit_oracle as O
+    app = P.AllenCahn(t_start=0, t_stop=0.032, nt=33, method='IMEX')
+    orc = O.AllenCahnOracle(t_start=0, t_stop=0.032, nt=33, method='IMEX')
+    got = app.step(u_start=app.vector_t_start, t_start=0.0, t_stop=0.001).get_values()
+    ref = orc.phi(orc.u0, 0.0, 0.001)
+    assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_user_defined_batched_application(P):
+    """The extension point (core/batched.py): a user application that only implements step_rows
+    with its own device code -- here torch operations for the Dahlquist test equation -- runs through Mgrit and gives the
+    reference's residual history (README.rst:102-122)."""
+    import torch
+
+    class MyVector(P.DeviceVector):
+        def __init__(self, tensor=None):
+            super().__init__((1,), tensor)
+
+    class MyDahlquist(P.BatchedApplication):
+        def __init__(self, *args, **kwargs):
+            super().__init__(*args, **kwargs)
+            self.ndof = 1
+            self.vector_template = MyVector()
+            self.vector_t_start = MyVector()
+            self.vector_t_start.set_values(np.array([1.0]))
+
+        def step_rows(self, src, src_idx, dst, dst_idx, t_start, t_stop):
+            dt = torch.as_tensor(t_stop - t_start, device=src.device)
+            vals = src[src_idx.long(), 0] / (1 + dt)                       # backward Euler, lambda = -1
+            dst[dst_idx.long(), 0] = vals
+
+    prob = P.simple_setup_problem(MyDahlquist(t_start=0, t_stop=5, nt=101), level=2, coarsening=2)
+    import logging
+    info = P.Mgrit(problem=prob, tol=1e-10, logging_lvl=logging.WARNING).solve()
+    ref = [7.186185937025427e-05, 1.246106707585954e-06, 2.1015566149418615e-08, 3.1441273895579124e-10, 3.975216519949153e-12]
+    assert len(info['conv']) == 5 and np.max(np.abs(np.array(info['conv']) - ref)) <= 1e-14

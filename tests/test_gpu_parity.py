@@ -62,6 +62,14 @@ def test_at_mgrit_against_reference_fixture(name):
         P.AtMgrit(problem=solver.problem, k=2, conv_crit=2)
 
 
+@pytest.mark.parametrize('name', [k for k in C.CASES if C.CASES[k]['app'] == 'allencahn'])
+def test_allen_cahn_imex_against_reference_fixture(name):
+    """allen_cahn/allen_cahn.py (IMEX branch) on the batched path (core/batched.py, csrc/generic.cu): fixtures of the
+    unmodified reference (examples/example_allen_cahn.py at nx = 32, an F-cycle on three levels, the jump criterion)."""
+    solver, _ = _check_against_golden(name)
+    assert solver._batched is not None and not any(solver._fused_down)
+
+
 def test_spatial_coarsening_matches_reference_result_file():
     """examples/example_spatial_coarsening.py -> tests/mpi/results/spatial_coarsening (4 decimals there, tests/mpi/mpi.py:49)."""
     _, info = run_b200('heat1d_spatial_example')

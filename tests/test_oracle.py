@@ -47,6 +47,17 @@ def test_brusselator_step_known_answer():  # tests/brusselator/test_brusselator.
     np.testing.assert_almost_equal(p.phi(np.zeros(2), 0, 0.1), np.array([0.08240173, 0.01319825]))
 
 
+def test_allen_cahn_imex_step_known_answer():   # tests/allen_cahn/test_allen_cahn.py:123-146 (test_heat_2d_step_imex)
+    prob = O.AllenCahnOracle(nx=3, eps=3, radius=0.25, method='IMEX', nu=1, t_start=0, t_stop=1, nt=11)
+    np.testing.assert_almost_equal(prob.u0, np.array([[-0.10732614, -0.05885746, -0.10732614],
+                                                       [-0.05885746, 0.05885746, -0.05885746],
+                                                       [-0.10732614, -0.05885746, -0.10732614]]))
+    np.testing.assert_almost_equal(prob.phi(prob.u0, 0, 0.1), np.array([[-0.07997795, -0.0640509, -0.07997795],
+                                                                         [-0.0640509, -0.03719789, -0.0640509],
+                                                                         [-0.07997795, -0.0640509, -0.07997795]]))
+    np.testing.assert_equal(prob.space_disc.toarray()[0], [-36., 9., 9., 9., 0., 0., 9., 0., 0.])   # :41-49
+
+
 def test_heat1d_2pts_step_known_answers():
     # tests/heat/test_heat_1d_2pts_bdf1.py:35-54
     p = O.Heat1D2PtsOracle(a=1, init_cond=lambda x: 2 * x, x_start=0, x_end=1, nx=11, dtau=0.1, method='BDF1', t_start=0,
