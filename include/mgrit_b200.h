@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 8
+#define MGB_ABI_VERSION 9
 
 /* application kinds (which Phi) */
 #define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
@@ -110,6 +110,10 @@ typedef struct mgb_level {
     const double *diag_dev; /* HEAT1D_SINE: [2][chunk][team_threads] thread-transposed: the       */
                             /* eigenvalues lam_k of (a/dx^2) tridiag(-1,2,-1), then 1/(1+dt lam_k)*/
                             /* for the level's dt (used when ndt == 1); else NULL                 */
+    const double *nat_dev;  /* HEAT1D_SINE, optional: [2 + nrhs][pitch] in natural mode order: lam_k,     */
+                            /* 1/(1+dt lam_k), X_q S.  With it mgb_f_relax, mgb_down_sweep,               */
+                            /* mgb_error_correction and mgb_residual_norms run as one thread per mode     */
+                            /* (csrc/sine_modes.cu: no shared-memory staging, coalesced rows, same values)*/
 } mgb_level;
 
 int mgb_abi_version(void);
@@ -356,6 +360,16 @@ int mgb_allen_cahn_imex_rows(int32_t nx, int32_t count, const double *src_dev, i
  *   receiver: mgb_peer_wait_row(my slot, my ghost row, count, my flag, PREDECESSOR's ack word, seq)
  *             waits (on the device) for seq, copies the row, acknowledges.
  * Both are ordinary asynchronous launches on `stream`; neither touches the host. */
+/* Every device-side wait on a peer gives up after a timeout (30 s unless mgb_peer_set_timeout changes it): the kernel
+ * records which wait it was and goes on, so a rank that died or took another code path cannot hang the other GPUs.
+ * mgb_peer_status copies the word to the host (synchronising; the solver calls it when a solve is over): 0 = every wait
+ * was answered, else one of MGB_PEER_WAIT_*; reset != 0 clears it. */
+#define MGB_PEER_WAIT_ROW 1        /* a ghost row did not arrive                              */
+#define MGB_PEER_WAIT_ACK 2        /* the successor never consumed the previous ghost row      */
+#define MGB_PEER_WAIT_GATHER 3     /* rows of the coarsest-level gather did not arrive         */
+#define MGB_PEER_WAIT_GATHER_ACK 4 /* a rank never consumed the previous gather                */
+int mgb_peer_status(int32_t *error_out, int32_t reset);
+int mgb_peer_set_timeout(double seconds);
 int mgb_peer_put_row(const double *src_dev, double *peer_slot_dev, int32_t count, void *peer_flag_dev, const void *my_ack_dev,
                      uint64_t seq, void *stream);
 int mgb_peer_wait_row(const double *my_slot_dev, double *dst_dev, int32_t count, const void *my_flag_dev, void *peer_ack_dev,

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libmgrit_b200.so')
 APP_BATCHED = 0            # no fused team kernels: the batched path (core/batched.py, csrc/generic.cu)
 APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D, APP_HEAT1D_2PTS, APP_HEAT1D_SINE = 1, 2, 3, 4, 5, 6, 7
 TNORM_ONE, TNORM_TWO, TNORM_INF = 1, 2, 3
-ABI_VERSION = 8
+ABI_VERSION = 9
 F_RELAX_LAST_ONLY = 1
 CORRECT_F_RELAX, CORRECT_GHOST, CORRECT_LAST_ONLY = 1, 2, 4
 DAHLQUIST_METHODS = {'BE': 0, 'FE': 1, 'TR': 2, 'MR': 3}
@@ -34,7 +34,7 @@ class MgbLevel(C.Structure):
         ('rhs_x_dev', C.c_void_p), ('rhs_t_dev', C.c_void_p), ('rhs_dense_dev', C.c_void_p),
         ('t_dev', C.c_void_p),
         ('p', C.c_double * 8), ('ip', C.c_int32 * 4),
-        ('sig_dev', C.c_void_p), ('diag_dev', C.c_void_p),
+        ('sig_dev', C.c_void_p), ('diag_dev', C.c_void_p), ('nat_dev', C.c_void_p),
     ]
 
 
@@ -91,6 +91,8 @@ SYMBOLS = {
     'mgb_allen_cahn_imex_rows': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mgb_peer_status': (C.c_int, [c_int32_p, C.c_int32]),
+    'mgb_peer_set_timeout': (C.c_int, [C.c_double]),
     'mgb_peer_put_row': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     'mgb_peer_wait_row': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     'mgb_peer_put_rows': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),

@@ -45,6 +45,9 @@ class SerialComm:
     def reduce_norm(self, partial, t_norm):
         return partial
 
+    def check_peers(self):
+        return None
+
 
 class PeerMailbox:
     """Symmetric memory every time rank's neighbours can address directly (torch.distributed._symmetric_memory: the
@@ -181,7 +184,9 @@ class TorchDistComm:
         if not self.all_true([ok])[0]:
             return
         levels, pitch = len(solver._lv), max(lv.pitch for lv in solver._lv)
-        key = (id(self.group), levels, pitch, solver._lv[0].u.device.index)
+        # a stable key: the ranks of the group, not id(group) (which Python may hand to a later group object)
+        ranks = tuple(self.dist.get_process_group_ranks(self.group)) if self.group is not None else ('world', self.size)
+        key = (ranks, levels, pitch, solver._lv[0].u.device.index)
         hit = _MAILBOXES.get(key)
         if hit is None:                       # every rank creates (or fails to create) its mailbox at the same call
             try:
@@ -193,6 +198,20 @@ class TorchDistComm:
         box, agreed = hit
         if agreed:
             self.mailbox = box
+
+    def check_peers(self):
+        """After a solve: did every device-side wait on a neighbour get its answer (csrc/peer.cu)?"""
+        if not getattr(self, 'mailbox', None):
+            return
+        import ctypes as C
+        from pymgrit_b200 import _lib
+        err = C.c_int32(0)
+        _lib.check(_lib.lib().mgb_peer_status(C.byref(err), 1), 'peer_status')
+        if err.value:
+            what = {1: 'a ghost row did not arrive', 2: 'the next rank never consumed a ghost row',
+                    3: 'rows of the coarsest-level gather did not arrive', 4: 'a rank never consumed a gather'}
+            raise Exception(f'time rank {self.rank}: {what.get(err.value, "a peer wait")} within the timeout -- another time '
+                            'rank died or took a different code path; the results of this solve are invalid')
 
     def exchange_ghost(self, solver, lvl):
         lv = solver._lv[lvl]

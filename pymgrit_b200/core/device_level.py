@@ -114,6 +114,7 @@ class DeviceLevel:
         self.batched = app.kind == _lib.APP_BATCHED          # no fused kernels, no struct mgb_level (core/batched.py)
         self.team_threads, self.chunk = (0, 0) if self.batched else team_shape(app.kind, self.n)
         # the (asynchronous) zero fill of the level arrays runs on the device while the host builds the tables
+        self.zero_filled = bool(zero_u) and u_init is None
         if u_init is not None:
             self.u = u_init
         elif zero_u:
@@ -208,6 +209,10 @@ class DeviceLevel:
         c.nsys = int(tab.get('nsys', 1))
         c.sig_dev = ptr(sig)
         diag = up(tab.get('diag'), np.float64)
+        nat = tab.get('nat_dev')
+        if nat is not None:
+            self._keep.append(nat)
+        c.nat_dev = ptr(nat)
         c.diag_dev = ptr(diag)
         self.nsys = c.nsys
         c.rhs_x_dev, c.rhs_t_dev, c.rhs_dense_dev = ptr(rhs_x), ptr(rhs_t), ptr(rhs_dense)

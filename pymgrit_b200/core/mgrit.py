@@ -97,6 +97,8 @@ class Mgrit:
             raise Exception("Unknown output level. Choose 0, 1 or 2.")
         masks = partition.c_point_masks([p.t for p in problem])
         for lvl in range(1, len(problem)):
+            if getattr(masks[lvl - 1], 'stride', 0) > 0:
+                continue           # t_coarse == t_fine[::m] on an increasing grid (partition.c_point_masks): nothing to count
             if int(np.count_nonzero(masks[lvl - 1])) != len(np.unique(problem[lvl].t)):
                 raise Exception('Some points from level ' + str(lvl - 1) + ' are not points of level ' + str(lvl))
         if t_norm not in [1, 2, 3]:
@@ -169,6 +171,7 @@ class Mgrit:
 
         self.launches = 0
         self._f_stale = False
+        self._f_uninit = False
         import os as _os
         self._lazy_f = _os.environ.get('MGB_LAZY_F', '1') != '0'
         self.problem = problem
@@ -222,6 +225,7 @@ class Mgrit:
             self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0, defer_tables=defer,
                                         zero_u=not (defer and max_iter > 0 and not (callable(output_fcn) and
                                                                                     output_lvl == 2))))
+        self._f_uninit = self.lvl_max > 1 and not self._lv[0].zero_filled
         phase('level arrays + coarse-level tables')
         # levels whose down-sweep runs as one fused launch (mgb_down_sweep): unweighted C-relaxation, at least one
         # F-point in every interval (on every time rank), team kernels
@@ -329,6 +333,16 @@ class Mgrit:
         residual and the next C-relaxation read, mgb_error_correction MGB_CORRECT_LAST_ONLY).  Before anybody looks at
         the level -- the end of solve(), an output function, Mgrit.u[0][i] -- one F-relaxation computes the others: the
         values the reference holds at that moment (its F-points are the Phi chains from the C-points, mgrit.py:287)."""
+        if self._f_uninit:
+            # level 0 was allocated without a fill (nested iteration and the first cycle write every row before a sweep
+            # reads it); somebody looks at it before that first cycle: the F-points hold the reference's zero initial guess
+            self._f_uninit = False
+            lv = self._lv[0]
+            if lv.cpts is not None and lv.npts > 0:
+                torch = _lib_torch()
+                is_f = torch.ones(lv.npts, dtype=torch.bool, device=lv.u.device)
+                is_f[torch.as_tensor(np.asarray(lv.cpts, dtype=np.int64), device=lv.u.device)] = False
+                lv.u[is_f] = 0.0
         if self._f_stale:
             self._f_stale = False
             self.f_relax(lvl=0)
@@ -473,6 +487,8 @@ class Mgrit:
         # Down-sweep: C-relaxation and the FAS restriction read only the last F-point of an interval, and the
         # F-relaxation fused into error_correction() below rewrites every F-point, so the F-relaxations here keep
         # only those last points (same values, the dead stores are skipped).
+        if lvl == 0:
+            self._f_uninit = False           # from here on the F-points are the cycle's business (_f_stale)
         if (lvl > 0 or (iteration == 0 and lvl == 0)) and first_f:
             self.f_relax(lvl=lvl, last_only=True)
         fused = False
@@ -775,6 +791,7 @@ class Mgrit:
                 break
         self._materialise_f_points()
         torch.cuda.synchronize()
+        self.comm_time.check_peers()             # a bounded device-side wait that gave up (csrc/peer.cu) raises here
         self.comm_time.barrier()
         self.runtime_solve = time.time() - runtime_solve_start
         self.log_info(f"Solve took {self.runtime_solve} s")

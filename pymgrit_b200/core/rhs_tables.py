@@ -117,7 +117,8 @@ class RhsSplit:
         self.max_terms = max_terms
         self.kind, self.basis, self.sel = None, None, None
         self._sample_t = np.zeros(0)
-        self._valid = {}              # time-grid key -> cached [nt, q] coefficients (None for 'zero')
+        self._valid = {}              # time-grid key -> cached [q, nt] coefficients (None for 'zero')
+        self._grids = {}              # time-grid key -> the validated grid itself (slabs of it are valid too)
         n = self.sampler.size
         rng = np.random.RandomState(12345)
         spread = np.unique(np.round(np.linspace(0, n - 1, min(n, self.N_CHECK - 2) + 2)[1:-1]).astype(int))
@@ -134,10 +135,27 @@ class RhsSplit:
         step = max(1, len(t) // 61)
         return (len(t), float(t[0]), float(t[-1]), hash(t[::step].tobytes())) if len(t) else (0,)
 
+    def _slab_of(self, t):
+        """(key, offset) if t is a contiguous piece of a grid this split has been validated on (the slab of a time rank),
+        else None.  Checked on the end points and a strided sample of the piece."""
+        if len(t) == 0:
+            return None
+        for key, grid in self._grids.items():
+            if len(grid) < len(t):
+                continue
+            off = int(np.searchsorted(grid, t[0]))
+            if off + len(t) > len(grid) or grid[off] != t[0] or grid[off + len(t) - 1] != t[-1]:
+                continue
+            step = max(1, len(t) // 257)
+            if np.array_equal(grid[off:off + len(t):step], t[::step]):
+                return key, off
+        return None
+
     def _build(self, sample_t):
         """Candidate split from the rows b(., t), t in sample_t."""
         self._sample_t = np.unique(np.asarray(sample_t, dtype=float))
         self._valid = {}
+        self._grids = {}
         R = self._rows(self._sample_t)
         self._scale = float(np.max(np.abs(R))) if R.size else 0.0
         if self._scale == 0.0:
@@ -204,7 +222,7 @@ class RhsSplit:
         key = self._key(t)
         n = self.sampler.size
         for _ in range(retries + 1):
-            if self.kind == 'dense' or key in self._valid:
+            if self.kind == 'dense' or key in self._valid or self._slab_of(t) is not None:
                 return self.kind
             full = len(t) * n <= self.FULL_CHECK
             pts = np.arange(n) if full else (self._check_pts if self.sel is None else
@@ -242,7 +260,9 @@ class RhsSplit:
             if not bad:
                 if len(self._valid) > 8:
                     self._valid.clear()
+                    self._grids.clear()
                 self._valid[key] = coef
+                self._grids[key] = t
                 return self.kind
             # the times that fit worst join the samples (largest defects, plus the first and last offender)
             bad.sort()
@@ -251,6 +271,7 @@ class RhsSplit:
             self._build(np.concatenate([self._sample_t, extra]))
         self.kind, self.basis, self.sel = 'dense', None, None
         self._valid = {}
+        self._grids = {}
         return self.kind
 
     def coefficients(self, t, scale=None, out=None):
@@ -262,6 +283,10 @@ class RhsSplit:
             out = np.empty((len(t), q))
         scale = None if scale is None else np.asarray(scale, dtype=float)
         cached = self._valid.get(self._key(t))
+        if cached is None and self.kind == 'separable':
+            hit = self._slab_of(t)                               # a time rank's slab of a grid validated as a whole
+            if hit is not None:
+                cached = self._valid[hit[0]][:, hit[1]:hit[1] + len(t)]
         if cached is not None and cached.shape == (q, len(t)):   # found while validating this grid
             from pymgrit_b200.core.device_level import parallel_pieces
 

@@ -149,6 +149,7 @@ static int check_level(const mgb_level *l, const SweepTable **tab, LevelDev *out
     out->nrow = (l->app == MGB_APP_HEAT1D_2PTS) ? l->pitch : l->n;  // doubles of a row the row-wise helpers touch
     out->sig = multi ? l->sig_dev : nullptr;
     out->diag = (l->app == MGB_APP_HEAT1D_SINE) ? l->diag_dev : nullptr;
+    out->nat = (l->app == MGB_APP_HEAT1D_SINE) ? l->nat_dev : nullptr;
     out->stop = g_stop;
     if (multi) out->n = out->tile;
     if (tiny && l->t_dev == nullptr) return fail(MGB_EINVAL, "ODE applications need the time grid t_dev%s");
@@ -411,6 +412,7 @@ int mgb_advection1d_step_consts(double nu_, int32_t n, int32_t T, int32_t E, dou
 int mgb_f_relax(const mgb_level *lvl, int32_t flags, void *stream) {
     MGB_PROLOGUE(lvl)
     if (L.cpts == nullptr) return fail(MGB_EINVAL, "f_relax needs the C-point table%s");
+    if (sine_modes_ok(L)) return sine_modes_f_relax(L, flags, st);
     return tab->f_relax(L, flags, st);
 }
 
@@ -442,6 +444,7 @@ int mgb_down_sweep(const mgb_level *fine, const mgb_level *coarse, void *stream)
     if (int rc = check_level(coarse, &tab2, &G)) return rc;
     if (int rc = check_pair(fine, coarse)) return rc;
     if (tab->down == nullptr) return fail(MGB_ENOSHAPE, "no fused down-sweep for this application%s");
+    if (sine_modes_ok(L) && sine_modes_ok(G) && G.nrhs == L.nrhs) return sine_modes_down(L, G, st);
     return tab->down(L, G, st);
 }
 
@@ -452,6 +455,7 @@ int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t
     if (int rc = check_level(coarse, &tab2, &G)) return rc;
     if (int rc = check_pair(fine, coarse)) return rc;
     const int frelax = (flags & MGB_CORRECT_F_RELAX) ? ((flags & MGB_CORRECT_LAST_ONLY) ? 2 : 1) : 0;
+    if (sine_modes_ok(L)) return sine_modes_correct(L, G, frelax, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
     return tab->correct(L, G, frelax, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
 }
 
@@ -470,6 +474,7 @@ int mgb_local_coarse_solve(const mgb_level *lvl, const double *old_dev, int32_t 
 int mgb_residual_norms(const mgb_level *lvl, double *out_sq_dev, void *stream) {
     MGB_PROLOGUE(lvl)
     if (L.cpts == nullptr || out_sq_dev == nullptr) return fail(MGB_EINVAL, "residual_norms needs C-points and an output%s");
+    if (sine_modes_ok(L)) return sine_modes_residual(L, out_sq_dev, st);
     return tab->residual(L, out_sq_dev, st);
 }
 

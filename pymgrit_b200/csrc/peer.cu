@@ -24,6 +24,30 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Every wait on a peer is bounded: a rank that died or took another code path must not hang the other GPUs for ever.
+// After g_peer_timeout_ns the waiting kernel records which wait gave up in g_peer_error and goes on (its data is then
+// meaningless); the host reads the word with mgb_peer_status() when the solve is over and raises.
+__device__ unsigned long long g_peer_timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ int g_peer_error = 0;
+
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p >= want (acquire, system scope); false after the timeout
+__device__ __forceinline__ bool wait_ge(const unsigned long long *p, unsigned long long want, int kind) {
+    if (ld_acquire_sys(p) >= want) return true;
+    const unsigned long long t0 = now_ns();
+    while (ld_acquire_sys(p) < want) {
+        if (now_ns() - t0 > g_peer_timeout_ns) {
+            atomicExch(&g_peer_error, kind);
+            return false;
+        }
+    }
+    return true;
+}
+
 // CTA-wide row copy: 16-byte accesses when both rows are 16-byte aligned (the PDE applications), 8-byte otherwise (the
 // one- and two-component ODE rows)
 __device__ __forceinline__ void copy_row(const double *__restrict__ src, double *__restrict__ dst, int count) {
@@ -42,9 +66,7 @@ __device__ __forceinline__ void copy_row(const double *__restrict__ src, double 
 __global__ void __launch_bounds__(256) k_put_row(const double *__restrict__ src, double *__restrict__ dst, int count,
                                                  unsigned long long *flag, const unsigned long long *ack,
                                                  unsigned long long seq) {
-    if (threadIdx.x == 0 && seq > 2)
-        while (ld_acquire_sys(ack) + 2 < seq) {
-        }
+    if (threadIdx.x == 0 && seq > 2) wait_ge(ack, seq - 2, MGB_PEER_WAIT_ACK);
     __syncthreads();
     copy_row(src, dst, count);
     __threadfence_system();
@@ -56,9 +78,7 @@ __global__ void __launch_bounds__(256) k_put_row(const double *__restrict__ src,
 __global__ void __launch_bounds__(256) k_wait_row(const double *__restrict__ slot, double *__restrict__ dst, int count,
                                                   const unsigned long long *flag, unsigned long long *ack,
                                                   unsigned long long seq) {
-    if (threadIdx.x == 0)
-        while (ld_acquire_sys(flag) < seq) {
-        }
+    if (threadIdx.x == 0) wait_ge(flag, seq, MGB_PEER_WAIT_ROW);
     __syncthreads();
     copy_row(slot, dst, count);
     __syncthreads();
@@ -80,8 +100,7 @@ __global__ void __launch_bounds__(256) k_put_rows(const double *__restrict__ src
                                                   unsigned long long seq) {
     const int p = blockIdx.x;
     if (threadIdx.x == 0 && seq > 2)
-        while (ld_acquire_sys(reinterpret_cast<const unsigned long long *>(pl.c[p])) + 2 < seq) {
-        }
+        wait_ge(reinterpret_cast<const unsigned long long *>(pl.c[p]), seq - 2, MGB_PEER_WAIT_GATHER_ACK);
     __syncthreads();
     copy_row(src, reinterpret_cast<double *>(pl.a[p]), count);
     __threadfence_system();
@@ -92,8 +111,7 @@ __global__ void __launch_bounds__(256) k_put_rows(const double *__restrict__ src
 __global__ void __launch_bounds__(32) k_wait_flags(const PeerList pl, unsigned long long seq) {
     const int p = blockIdx.x;
     if (threadIdx.x == 0) {
-        while (ld_acquire_sys(reinterpret_cast<const unsigned long long *>(pl.a[p])) < seq) {
-        }
+        wait_ge(reinterpret_cast<const unsigned long long *>(pl.a[p]), seq, MGB_PEER_WAIT_GATHER);
         st_release_sys(reinterpret_cast<unsigned long long *>(pl.b[p]), seq - 1);
     }
 }
@@ -115,6 +133,26 @@ static int fill(PeerList &pl, int n, const uint64_t *a, const uint64_t *b, const
 using namespace mgb;
 
 extern "C" {
+
+int mgb_peer_status(int32_t *error_out, int32_t reset) {
+    if (error_out == nullptr) return heat2d_fail("peer_status: bad argument");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    int err = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&err, g_peer_error, sizeof(int));
+    if (e == cudaSuccess && reset && err != 0) {
+        const int zero = 0;
+        e = cudaMemcpyToSymbol(g_peer_error, &zero, sizeof(int));
+    }
+    *error_out = err;
+    return cuda_fail(e, "peer_status");
+}
+
+int mgb_peer_set_timeout(double seconds) {
+    if (!(seconds > 0.0)) return heat2d_fail("peer_set_timeout: bad argument");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    const unsigned long long ns = (unsigned long long)(seconds * 1e9);
+    return cuda_fail(cudaMemcpyToSymbol(g_peer_timeout_ns, &ns, sizeof(ns)), "peer_set_timeout");
+}
 
 int mgb_peer_put_row(const double *src_dev, double *peer_slot_dev, int32_t count, void *peer_flag_dev, const void *my_ack_dev,
                      uint64_t seq, void *stream) {

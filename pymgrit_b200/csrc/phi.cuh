@@ -46,6 +46,7 @@ struct LevelDev {
     int nrow;
     const double *sig;  // [pitch] per-element symbol of the spatial operator (Heat2D), row layout; NULL otherwise
     const double *diag; // Heat1DSine: [2][E][T] thread-transposed eigenvalues lam_k and reciprocals 1/(1 + dt lam_k)
+    const double *nat;  // Heat1DSine: [2 + nrhs][pitch] the same tables in natural mode order (sine_modes.cu), or nullptr
     const int *stop;    // device flag set by mgb_convergence_flag once the stopping criterion is met: sweeps that were
                         // queued ahead of that knowledge return at once (mgb_set_stop_flag); nullptr = not in use
 };

@@ -14,6 +14,13 @@ const DeviceInfo *device_info();                 // api.cu; nullptr (and an erro
 int cuda_fail(cudaError_t e, const char *what);  // api.cu: records the message, returns MGB_ECUDA or 0
 const int *stop_flag();                          // api.cu: the device flag of mgb_set_stop_flag, or nullptr
 
+// sine_modes.cu: the hot sweeps of a HEAT1D_SINE level with one thread per mode
+bool sine_modes_ok(const LevelDev &L);
+int sine_modes_f_relax(const LevelDev &L, int flags, cudaStream_t st);
+int sine_modes_down(const LevelDev &L, const LevelDev &G, cudaStream_t st);
+int sine_modes_correct(const LevelDev &L, const LevelDev &G, int frelax, int kfirst, cudaStream_t st);
+int sine_modes_residual(const LevelDev &L, double *out_sq, cudaStream_t st);
+
 struct SweepTable {
     int team_threads;
     int chunk;

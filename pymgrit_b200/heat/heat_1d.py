@@ -220,7 +220,8 @@ class Heat1D(DeviceApplication):
         if uniform:       # 1 / (1 + dt lam_k) in extended precision, rounded once; the padding acts on zeros
             flat[1, :n] = np.asarray(1 / (1 + np.longdouble(dts[0]) * lam_l), dtype=np.float64)
         diag = np.ascontiguousarray(flat.reshape(2, team_threads, chunk).transpose(0, 2, 1))   # [2][chunk][team_threads]
-        return dict(ndt=len(dts), dtidx=dtidx, sconst=sconst, cw=8, diag=diag), dt_full
+        pitch = n + (n & 1)
+        return dict(ndt=len(dts), dtidx=dtidx, sconst=sconst, cw=8, diag=diag, nat=flat[:, :pitch].copy()), dt_full
 
     def level_tables(self, t, team_threads, chunk):
         if self._in_sine:
@@ -245,9 +246,18 @@ class Heat1D(DeviceApplication):
         return tab
 
     def _level_tables_sine(self, t, team_threads, chunk):
+        torch = dl._torch()
         tab, dt_full = self.sine_host_tables(t, team_threads, chunk)
         shared = self._sine_device_tables(team_threads, chunk)
         split = self._rhs_split
+        # the same tables in natural mode order for the one-thread-per-mode sweeps (csrc/sine_modes.cu)
+        nat_host = tab.pop('nat')
+        q = shared['nrhs']
+        nat = torch.empty((2 + q, nat_host.shape[1]), dtype=torch.float64, device=shared['lam'].device)
+        nat[:2].copy_(dl._stage_small(nat_host)._owner, non_blocking=True)
+        if q:
+            nat[2:].copy_(shared['rxh'])
+        tab['nat_dev'] = nat
         if split.kind == 'separable':
             tab['nrhs'] = shared['nrhs']
             tab['rhs_x_dev'] = shared['rhs_x']

@@ -1,0 +1,12 @@
+#!/bin/bash
+tag=${1:-r02j}
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${tag}_pytest_gpu.log
+timeout 300 python scripts/e2e_breakdown.py cfg5 > gpurun_out/${tag}_e2e_breakdown_n1.txt 2>&1
+head -16 gpurun_out/${tag}_e2e_breakdown_n1.txt
+timeout 600 python bench.py --no-cpu > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+python - <<PY
+import json
+d=json.load(open('gpurun_out/${tag}_bench.json'))
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'], d['parity']['ok'], d['config']['conv'])
+PY

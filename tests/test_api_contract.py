@@ -177,7 +177,8 @@ def test_every_case_reaches_the_device_boundary():
 
 
 @pytest.mark.parametrize('name', ['example_dahlquist', 'example_heat_1d', 'example_heat_1d_bdf2',
-                                  'example_spatial_coarsening', 'example_heat_2d', 'example_at_mgrit'])
+                                  'example_spatial_coarsening', 'example_heat_2d', 'example_at_mgrit',
+                                  'example_allen_cahn'])
 def test_examples_reach_the_device_boundary(name):
     """examples/*.py (the reference's examples with the import swapped): the host-side setup of each runs on the CPU and
     the solver constructor then stops for the one reason that there is no CUDA device."""

@@ -470,3 +470,40 @@ def test_user_defined_batched_application(P):
     info = P.Mgrit(problem=prob, tol=1e-10, logging_lvl=logging.WARNING).solve()
     ref = [7.186185937025427e-05, 1.246106707585954e-06, 2.1015566149418615e-08, 3.1441273895579124e-10, 3.975216519949153e-12]
     assert len(info['conv']) == 5 and np.max(np.abs(np.array(info['conv']) - ref)) <= 1e-14
+
+
+@pytest.mark.parametrize('name', ['example_dahlquist', 'example_heat_1d', 'example_heat_1d_bdf2', 'example_spatial_coarsening',
+                                  'example_heat_2d', 'example_at_mgrit', 'example_allen_cahn'])
+def test_examples_run(name):
+    """examples/*.py -- the reference's examples with the import swapped -- run to the end on the device and report a
+    residual history that went down."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    r = subprocess.run([sys.executable, os.path.join(root, 'examples', name + '.py')], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600, env=env, cwd=os.path.join(root, 'examples'))
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert 'conv' in r.stdout or re.search(r'\[[0-9.e+\- \n]+\]', r.stdout), r.stdout[-2000:]
+
+
+@pytest.mark.parametrize('name', ['heat1d_cfg2_nt1025', 'heat1d_nonuniform_t', 'heat1d_rhs_rank2', 'heat1d_trailing_f',
+                                  'heat1d_small_f_cf2', 'heat1d_example', 'heat1d_zero_rhs', 'heat1d_nx4097'])
+def test_one_thread_per_mode_sweeps_are_bit_identical_to_the_team_kernels(P, name, monkeypatch):
+    """csrc/sine_modes.cu (one thread per mode, no shared-memory staging) against the team kernels of csrc/sweeps.cuh on
+    sine-space levels: the same operations per element in the same order, so the same bits -- residual history (whose
+    per-row sums of squares are added in another order: 1e-15 relative) and solution."""
+    from b200_util import run_b200, solution_rows
+    if name not in C.CASES:
+        pytest.skip('case not defined')
+    monkeypatch.setenv('MGB_HEAT1D_SINE', '1')
+    monkeypatch.setenv('MGB_SINE_MODES', '1')
+    modes, info_m = run_b200(name)
+    assert modes.problem[0].kind == P._lib.APP_HEAT1D_SINE
+    monkeypatch.setenv('MGB_SINE_MODES', '0')
+    team, info_t = run_b200(name)
+    assert len(info_m['conv']) == len(info_t['conv'])
+    assert np.allclose(info_m['conv'], info_t['conv'], rtol=1e-12, atol=0)
+    assert np.array_equal(solution_rows(modes)[0], solution_rows(team)[0])
