@@ -45,6 +45,9 @@ def _increasing(t):
     """t[i] < t[i+1] for all i (in pieces on the table threads for long grids)."""
     if len(t) < 2:
         return True
+    from pymgrit_b200.core.application import known_increasing
+    if known_increasing(t):
+        return True
     from pymgrit_b200.core.device_level import parallel_pieces
     return all(parallel_pieces(len(t) - 1, lambda a, b: bool(np.all(t[a + 1:b + 1] > t[a:b]))))
 

@@ -43,13 +43,22 @@ struct DiagPhi {
             for (int q = 0; q < Q; ++q) rx[q][r] = ok ? __ldg(L.nat + (size_t)(2 + q) * L.pitch + m) : 0.0;
         }
     }
+    // the time factors of step i (issued early: the load is a dependent access that a step would otherwise wait for)
+    __device__ static __forceinline__ void factors(double (&ct)[Q > 0 ? Q : 1], const LevelDev &L, int i) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) ct[q] = __ldg(L.rhs_t + (size_t)i * Q + q);
+    }
     // x <- Phi_i(x)   (same operations, in the same order, as Heat1DSine::apply)
     __device__ __forceinline__ void step(double (&x)[R], const LevelDev &L, int i) const {
+        double ct[Q > 0 ? Q : 1];
+        factors(ct, L, i);
+        step(x, L, i, ct);
+    }
+    __device__ __forceinline__ void step(double (&x)[R], const LevelDev &L, int i, const double (&ct)[Q > 0 ? Q : 1]) const {
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            const double ct = __ldg(L.rhs_t + (size_t)i * Q + q);
 #pragma unroll
-            for (int r = 0; r < R; ++r) x[r] = fma(ct, rx[q][r], x[r]);
+            for (int r = 0; r < R; ++r) x[r] = fma(ct[q], rx[q][r], x[r]);
         }
         if (recip) {
 #pragma unroll
@@ -94,7 +103,48 @@ __device__ __forceinline__ void advance(double (&x)[R], const DiagPhi<Q> &phi, c
     }
 }
 
-// F-relaxation (mgrit.py:312-327); last_only: only the last F-point of an interval is stored.  One CTA per interval.
+// Steps i0 .. i1-1 in a row: x <- (g[i] +) Phi_i(x), stored after every step (STORE) or not at all.  The time factors of 32
+// steps come with one coalesced load per warp (lane l holds step base + l; the next 32 are in flight meanwhile) and reach
+// the steps by shuffle: a plain load per step is a dependent access that half of all issue slots waited for (ncu, long
+// scoreboard 52 %: profiles/r02n_modes_full.txt).
+template <int Q, bool STORE>
+__device__ __forceinline__ void run_steps(double (&x)[R], const DiagPhi<Q> &phi, const LevelDev &L, int i0, int i1, int m0) {
+    const int lane = threadIdx.x & 31;
+    double nxt[Q > 0 ? Q : 1];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) nxt[q] = (i0 + lane < i1) ? __ldg(L.rhs_t + (size_t)(i0 + lane) * Q + q) : 0.0;
+    for (int base = i0; base < i1; base += 32) {
+        double cur[Q > 0 ? Q : 1];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            cur[q] = nxt[q];
+            const int nb = base + 32 + lane;
+            nxt[q] = (nb < i1) ? __ldg(L.rhs_t + (size_t)nb * Q + q) : 0.0;
+        }
+        const int cnt = min(32, i1 - base);
+#pragma unroll 2
+        for (int s = 0; s < cnt; ++s) {
+            const int i = base + s;
+            double ct[Q > 0 ? Q : 1];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) ct[q] = __shfl_sync(0xffffffffu, cur[q], s);
+            phi.step(x, L, i, ct);
+            if (L.g) {
+                double g[R];
+                ldrow(g, L.g, i, L.pitch, m0, L.n);
+#pragma unroll
+                for (int r = 0; r < R; ++r) x[r] = g[r] + x[r];
+            }
+            if (STORE) strow(x, L.u, i, L.pitch, m0, L.n);
+        }
+    }
+}
+
+// One CTA per item: the hardware scheduler keeps every SM full of CTAs in different phases (row loads, arithmetic, stores).
+// (Measured: a persistent grid whose CTAs prefetch the first rows of their next item is slower -- 5.3 instead of 4.75 ms per
+// solve, profiles/r02m_modes_variants.txt: fewer, longer-lived CTAs overlap less than many short ones.)
+
+// F-relaxation (mgrit.py:312-327); last_only: only the last F-point of an interval is stored.
 template <int Q>
 __global__ void __launch_bounds__(TB, MINB) k_chain(const LevelDev L, const int last_only) {
     MGB_RETURN_IF_STOPPED(L)
@@ -108,23 +158,18 @@ __global__ void __launch_bounds__(TB, MINB) k_chain(const LevelDev L, const int 
             double x[R];
             ldrow(x, L.u, s, L.pitch, m0, L.n);
             if (last_only) {
-#pragma unroll 4
-                for (int i = s + 1; i < e; ++i) advance<Q>(x, phi, L, i, m0, true);
+                run_steps<Q, false>(x, phi, L, s + 1, e, m0);
                 strow(x, L.u, e - 1, L.pitch, m0, L.n);
             } else {
-#pragma unroll 2
-                for (int i = s + 1; i < e; ++i) {
-                    advance<Q>(x, phi, L, i, m0, true);
-                    strow(x, L.u, i, L.pitch, m0, L.n);
-                }
+                run_steps<Q, true>(x, phi, L, s + 1, e, m0);
             }
         }
     }
 }
 
-// C-relaxation + F-relaxation + FAS restriction in one pass (sweeps.cuh k_down, same formulas).  One CTA per C-point j >= 1.
+// C-relaxation + F-relaxation + FAS restriction in one pass (sweeps.cuh k_down, same formulas); items = C-points j >= 1.
 template <int Q>
-__global__ void __launch_bounds__(TB, MINB) k_down(const LevelDev L, const LevelDev G) {
+__global__ void __launch_bounds__(TB, 3) k_down(const LevelDev L, const LevelDev G) {
     MGB_RETURN_IF_STOPPED(L)
     for (int j = 1 + blockIdx.x; j < L.ncpts; j += gridDim.x) {
         const int a = __ldg(L.cpts + j - 1), c = __ldg(L.cpts + j);
@@ -132,14 +177,33 @@ __global__ void __launch_bounds__(TB, MINB) k_down(const LevelDev L, const Level
             DiagPhi<Q> phi;
             phi.load(L, m0);
             double x[R], yc[R], w[R];
+            // time factors of the item's single steps, all in flight before the first row is waited for
+            double ct_c[Q > 0 ? Q : 1], ct_a[Q > 0 ? Q : 1], ct_j[Q > 0 ? Q : 1];
+            DiagPhi<Q>::factors(ct_c, L, c);
+            DiagPhi<Q>::factors(ct_a, L, a == 0 ? c : a);
+            DiagPhi<Q>::factors(ct_j, G, j);
             // C-relaxation of c
             ldrow(yc, L.u, c - 1, L.pitch, m0, L.n);
-            advance<Q>(yc, phi, L, c, m0, true);
+            ldrow(x, L.u, a == 0 ? 0 : a - 1, L.pitch, m0, L.n);
+            phi.step(yc, L, c, ct_c);
+            if (L.g) {
+                double g[R];
+                ldrow(g, L.g, c, L.pitch, m0, L.n);
+#pragma unroll
+                for (int r = 0; r < R; ++r) yc[r] = g[r] + yc[r];
+            }
             strow(yc, L.u, c, L.pitch, m0, L.n);
             strow(yc, G.u, j, G.pitch, m0, L.n);  // injection
             // the C-relaxed left end
-            ldrow(x, L.u, a == 0 ? 0 : a - 1, L.pitch, m0, L.n);
-            if (a != 0) advance<Q>(x, phi, L, a, m0, true);
+            if (a != 0) {
+                phi.step(x, L, a, ct_a);
+                if (L.g) {
+                    double g[R];
+                    ldrow(g, L.g, a, L.pitch, m0, L.n);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) x[r] = g[r] + x[r];
+                }
+            }
             if (j == 1) strow(x, G.u, 0, G.pitch, m0, L.n);  // point 0 (initial condition / ghost) is injected too
             // w = Phi_c(x) with the coarse level's factors
             {
@@ -147,12 +211,11 @@ __global__ void __launch_bounds__(TB, MINB) k_down(const LevelDev L, const Level
                 cphi.load(G, m0);
 #pragma unroll
                 for (int r = 0; r < R; ++r) w[r] = x[r];
-                cphi.step(w, G, j);
+                cphi.step(w, G, j, ct_j);
             }
             // F-relaxation chain and the fine step into c
-#pragma unroll 4
-            for (int i = a + 1; i < c; ++i) advance<Q>(x, phi, L, i, m0, true);
-            advance<Q>(x, phi, L, c, m0, false);
+            run_steps<Q, false>(x, phi, L, a + 1, c, m0);
+            phi.step(x, L, c, ct_c);
             // FAS right-hand side
             if (L.g) {
                 double gc[R];
@@ -175,8 +238,8 @@ __global__ void __launch_bounds__(TB, MINB) k_correct(const LevelDev L, const Le
     for (int k = blockIdx.x; k < L.ncpts; k += gridDim.x) {
         int s, e;
         interval(L, k, s, e);
-        const bool chain = frelax && (e - s > 1);
-        if (k < kfirst && !chain) continue;
+        const bool relax = frelax && (e - s > 1);
+        if (k < kfirst && !relax) continue;
         for (int m0 = 0; m0 < L.n; m0 += TB * R) {
             double x[R];
             ldrow(x, L.u, s, L.pitch, m0, L.n);
@@ -187,19 +250,14 @@ __global__ void __launch_bounds__(TB, MINB) k_correct(const LevelDev L, const Le
                 for (int r = 0; r < R; ++r) x[r] = x[r] + (cu[r] - x[r]);
                 strow(x, L.u, s, L.pitch, m0, L.n);
             }
-            if (!chain) continue;
+            if (!relax) continue;
             DiagPhi<Q> phi;
             phi.load(L, m0);
             if (frelax == 2) {
-#pragma unroll 4
-                for (int i = s + 1; i < e; ++i) advance<Q>(x, phi, L, i, m0, true);
+                run_steps<Q, false>(x, phi, L, s + 1, e, m0);
                 strow(x, L.u, e - 1, L.pitch, m0, L.n);
             } else {
-#pragma unroll 2
-                for (int i = s + 1; i < e; ++i) {
-                    advance<Q>(x, phi, L, i, m0, true);
-                    strow(x, L.u, i, L.pitch, m0, L.n);
-                }
+                run_steps<Q, true>(x, phi, L, s + 1, e, m0);
             }
         }
     }
