@@ -322,6 +322,11 @@ bool sine_modes_ok(const LevelDev &L) {
            (L.ndt == 1 || L.dtidx != nullptr);
 }
 
+// the coarse level of a pair only lends its tables (the coarsest level has no C-point list)
+bool sine_modes_coarse_ok(const LevelDev &G, const LevelDev &L) {
+    return G.nat != nullptr && G.nrhs == L.nrhs && G.rhs_dense == nullptr && (G.ndt == 1 || G.dtidx != nullptr);
+}
+
 int sine_modes_f_relax(const LevelDev &L, int flags, cudaStream_t st) {
     using namespace modes;
     if (L.ncpts < 1) return 0;
