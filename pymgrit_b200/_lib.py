@@ -130,6 +130,17 @@ def check(rc, what=''):
         raise Exception(f'libmgrit_b200 {what} failed (code {rc}): {msg}')
 
 
+_raw_stream = None
+
+
 def current_stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (as the void* the C ABI takes).  Through torch's raw
+    accessor: `torch.cuda.current_stream().cuda_stream` builds a Python Stream object per call, ~15 us -- a millisecond per
+    solve at 60 launches."""
+    global _raw_stream
     import torch
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', False)
+    if _raw_stream:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)

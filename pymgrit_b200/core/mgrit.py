@@ -148,6 +148,11 @@ class Mgrit:
 
         phase('argument checks, C-point masks, representation')
         self.comm_time = as_time_comm(comm_time)
+        if comm_space is not None and hasattr(comm_space, 'Get_size') and comm_space.Get_size() > 1:
+            # the reference hands comm_space to applications that are parallel in space (PETSc, mgrit.py:129-140); every
+            # application of this package lives on one GPU
+            raise Exception('comm_space with more than one process is not supported: the applications of pymgrit_b200 are '
+                            'not parallel in space (one GPU per time rank)')
         self.comm_space = comm_space
         self.comm_time_rank = self.comm_time.Get_rank()
         self.comm_time_size = self.comm_time.Get_size()

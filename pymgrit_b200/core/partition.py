@@ -249,9 +249,13 @@ class Partition:
             # slab ends must be points of the coarsest grid: spread its intervals over the ranks
             # (level-0 indices of the coarsest points by composing the C-point masks: level l+1 is the C-points of
             # level l in order, so no search or sort over the 2^20 fine points is needed)
-            coarse_idx = np.flatnonzero(masks[0]) if L > 1 else np.arange(n0)
-            for l in range(1, L - 1):
-                coarse_idx = coarse_idx[masks[l]]
+            strides = [getattr(masks[l], 'stride', 0) for l in range(L - 1)]
+            if L > 1 and all(st > 0 for st in strides):       # regular coarsening on every level: plain arithmetic
+                coarse_idx = np.arange(0, n0, int(np.prod(strides)))
+            else:
+                coarse_idx = np.flatnonzero(masks[0]) if L > 1 else np.arange(n0)
+                for l in range(1, L - 1):
+                    coarse_idx = coarse_idx[masks[l]]
             if len(coarse_idx) != len(global_t[-1]) or not np.array_equal(t0[coarse_idx], global_t[-1]):
                 coarse_idx = np.flatnonzero(np.isin(t0, global_t[-1]))      # grids with repeated or unsorted points
             nc = len(coarse_idx)

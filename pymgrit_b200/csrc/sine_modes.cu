@@ -107,8 +107,8 @@ __device__ __forceinline__ void advance(double (&x)[R], const DiagPhi<Q> &phi, c
 // steps come with one coalesced load per warp (lane l holds step base + l; the next 32 are in flight meanwhile) and reach
 // the steps by shuffle: a plain load per step is a dependent access that half of all issue slots waited for (ncu, long
 // scoreboard 52 %: profiles/r02n_modes_full.txt).
-template <int Q, bool STORE>
-__device__ __forceinline__ void run_steps(double (&x)[R], const DiagPhi<Q> &phi, const LevelDev &L, int i0, int i1, int m0) {
+template <int Q, bool STORE, bool HASG>
+__device__ __forceinline__ void run_steps_g(double (&x)[R], const DiagPhi<Q> &phi, const LevelDev &L, int i0, int i1, int m0) {
     const int lane = threadIdx.x & 31;
     double nxt[Q > 0 ? Q : 1];
 #pragma unroll
@@ -122,14 +122,14 @@ __device__ __forceinline__ void run_steps(double (&x)[R], const DiagPhi<Q> &phi,
             nxt[q] = (nb < i1) ? __ldg(L.rhs_t + (size_t)nb * Q + q) : 0.0;
         }
         const int cnt = min(32, i1 - base);
-#pragma unroll 2
+#pragma unroll 4
         for (int s = 0; s < cnt; ++s) {
             const int i = base + s;
             double ct[Q > 0 ? Q : 1];
 #pragma unroll
             for (int q = 0; q < Q; ++q) ct[q] = __shfl_sync(0xffffffffu, cur[q], s);
             phi.step(x, L, i, ct);
-            if (L.g) {
+            if (HASG) {
                 double g[R];
                 ldrow(g, L.g, i, L.pitch, m0, L.n);
 #pragma unroll
@@ -138,6 +138,14 @@ __device__ __forceinline__ void run_steps(double (&x)[R], const DiagPhi<Q> &phi,
             if (STORE) strow(x, L.u, i, L.pitch, m0, L.n);
         }
     }
+}
+// (the test for g rows is taken out of the step loop: the loop of a level-0 chain is shuffles, FMAs and multiplications only)
+template <int Q, bool STORE>
+__device__ __forceinline__ void run_steps(double (&x)[R], const DiagPhi<Q> &phi, const LevelDev &L, int i0, int i1, int m0) {
+    if (L.g)
+        run_steps_g<Q, STORE, true>(x, phi, L, i0, i1, m0);
+    else
+        run_steps_g<Q, STORE, false>(x, phi, L, i0, i1, m0);
 }
 
 // One CTA per item: the hardware scheduler keeps every SM full of CTAs in different phases (row loads, arithmetic, stores).
