@@ -303,7 +303,10 @@ class Mgrit:
         if self.iter_max == 0:
             self.comm_time.barrier()
         phase('norm buffers')
-        torch.cuda.synchronize()
+        if self._log_lvl <= logging.INFO or self.iter_max == 0 or (self.output_fcn is not None and self.output_lvl == 2):
+            torch.cuda.synchronize()         # "Setup took ..." is printed: make it the time the setup really took
+        # otherwise the sweeps queued by the setup (nested iteration) are still running when the constructor returns and
+        # solve() queues behind them: time_setup + time_solve is unchanged, the host does not idle in between
         phase('wait for the device')
         self.runtime_setup = time.time() - runtime_setup_start
 

@@ -27,6 +27,10 @@ int cuda_fail(cudaError_t e, const char *what) {
     return MGB_ECUDA;
 }
 
+// levels with at least this many points are streams of rows when every F-point is stored: the team kernels' bulk stores
+// write them best; shorter levels are latency-bound and run as one thread per mode (sine_modes.cu)
+constexpr int kStreamPoints = 1 << 17;
+
 static const int *g_stop = nullptr;
 const int *stop_flag() { return g_stop; }
 
@@ -414,7 +418,7 @@ int mgb_f_relax(const mgb_level *lvl, int32_t flags, void *stream) {
     if (L.cpts == nullptr) return fail(MGB_EINVAL, "f_relax needs the C-point table%s");
     // one thread per mode for the chains that store one point; with every F-point stored the sweep is a stream of rows and
     // the team kernel's bulk stores are the better writer (88 % against 85 % of the HBM peak, profiles/r02p_*)
-    if (sine_modes_ok(L) && (flags & MGB_F_RELAX_LAST_ONLY)) return sine_modes_f_relax(L, flags, st);
+    if (sine_modes_ok(L) && ((flags & MGB_F_RELAX_LAST_ONLY) || L.npts < kStreamPoints)) return sine_modes_f_relax(L, flags, st);
     return tab->f_relax(L, flags, st);
 }
 
@@ -457,7 +461,7 @@ int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t
     if (int rc = check_level(coarse, &tab2, &G)) return rc;
     if (int rc = check_pair(fine, coarse)) return rc;
     const int frelax = (flags & MGB_CORRECT_F_RELAX) ? ((flags & MGB_CORRECT_LAST_ONLY) ? 2 : 1) : 0;
-    if (sine_modes_ok(L) && frelax != 1) return sine_modes_correct(L, G, frelax, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
+    if (sine_modes_ok(L) && (frelax != 1 || L.npts < kStreamPoints)) return sine_modes_correct(L, G, frelax, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
     return tab->correct(L, G, frelax, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
 }
 
