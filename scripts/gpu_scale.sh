@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8 GPUs: bench at N = 8, 4, 2 (parity block in every line), timeline and e2e phases at N = 8
-tag=${1:-r02s}
+tag=${1:-r02y}
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
 for n in 8 4 2; do

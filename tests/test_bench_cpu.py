@@ -69,10 +69,10 @@ def test_helpers():
     assert [len(p.t) for p in levels] == [4097, 65, 5]
     assert np.array_equal(levels[1].t, levels[0].t[::64])
     assert 'coarsening 64x16' in bench.describe('cfg5', co)
-    full = bench.ncu_traffic('error_correction+f_relax', 16384, 64)
-    assert full is not None and abs(full / (66 * 16384 * 8184) - 1) < 0.01          # DRAM bytes = algorithmic bytes
-    assert bench.ncu_traffic('error_correction+f_relax', 8192, 64) == full / 2
-    assert bench.ncu_traffic('error_correction+f_relax', 4096, 4) is None           # captured for another interval length
+    full = bench.ncu_traffic('f_relax', 16384, 64)
+    assert full is not None and abs(full / (64 * 16384 * 8184) - 1) < 0.01          # DRAM bytes = algorithmic bytes
+    assert bench.ncu_traffic('f_relax', 8192, 64) == full / 2
+    assert bench.ncu_traffic('f_relax', 4096, 4) is None                             # captured for another interval length
     assert bench.ncu_traffic('no such sweep', 1, 64) is None
     s = bench.ClockSampler(0)
     s.proc = type('P', (), {'terminate': lambda self: None})()
