@@ -63,7 +63,9 @@ SOLVER_KW = dict(cf_iter=1, cycle_type='V', nested_iteration=True, tol=1e-10)
 # 16385 and 1025 coarse points converges in 3 FCF V-cycles and is the fastest of the 24 hierarchies tried on 1 and on 8
 # GPUs (scripts/hierarchy_sweep.py, profiles/r01o_hierarchy_sweep.txt); cfg4 (advection, coarsening 2): 4 levels -- MGRIT
 # contracts slowly on this hyperbolic problem and deep hierarchies stall (10 levels: 129 V-cycles to 1e-10, 4 levels: 10;
-# scripts/cfg4_sweep.py, profiles/r02_cfg4_sweep.txt: 11 depth / cycle combinations, this one is the fastest).
+# scripts/cfg4_sweep.py, profiles/r02_cfg4_sweep.txt).  Since the coarsest level is solved time-parallel in Fourier space
+# (csrc/fourier.cu) a long coarsest level costs a few milliseconds instead of a chain of dependent solves, and the
+# two-level hierarchy -- 4 V-cycles -- is the fastest of the 11 depth / cycle combinations (profiles/r02r_cfg4_sweep.txt).
 _HEAT1D = {k: v for k, v in HEAT_KW.items() if k not in ('t_start', 't_stop')}
 WORKLOADS = {
     'cfg5': dict(app='heat1d', kw=_HEAT1D, t=(0, 2, 2 ** 20 + 1), coarsening=(64, 16), solver=SOLVER_KW, ndof=1023,
@@ -75,7 +77,7 @@ WORKLOADS = {
     'cfg3': dict(app='heat2d', kw=dict(x_start=0, x_end=1, y_start=0, y_end=1, nx=512, ny=512, a=1, rhs=rhs_2d),
                  t=(0, 5, 4097), coarsening=(8, 8, 8), solver=dict(cycle_type='F', tol=1e-10), ndof=512 * 512,
                  text='heat_2d backward Euler 512x512 nt=4097 on [0,5]'),
-    'cfg4': dict(app='advection1d', kw=dict(c=1, x_start=-1, x_end=1, nx=4096), t=(0, 2, 65537), coarsening=(2,) * 3,
+    'cfg4': dict(app='advection1d', kw=dict(c=1, x_start=-1, x_end=1, nx=4096), t=(0, 2, 65537), coarsening=(2,),
                  solver=dict(cf_iter=1, cycle_type='V', nested_iteration=True, tol=1e-10), ndof=4095,
                  text='advection 1D upwind nx=4096 nt=65537 on [0,2]'),
 }
@@ -85,7 +87,7 @@ CPU_SAMPLES = {
     'cfg5': ((2049, (64, 16)), (32769, (64, 16))),
     'cfg2': ((1025, (4, 4)), (4097, (4, 4))),
     'cfg1': ((101, (2,)), (101, (2,))),
-    'cfg4': ((129, (2,) * 3), (513, (2,) * 3)),
+    'cfg4': ((129, (2,)), (513, (2,))),
     'cfg3': None,                     # see cpu_sample(): a 512 x 512 SuperLU solve takes seconds, a spatially reduced grid is timed
 }
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 9
+#define MGB_ABI_VERSION 10
 
 /* application kinds (which Phi) */
 #define MGB_APP_HEAT1D 1      /* heat/heat_1d.py:198-217   backward Euler, Toeplitz tridiagonal solve      */
@@ -104,7 +104,8 @@ typedef struct mgb_level {
     const double *t_dev;    /* [npts] time values of the level's points (needed by the ODE apps)  */
     double p[8];            /* application scalars (dahlquist: p[0] = lambda)                     */
     int32_t ip[4];          /* application integers (dahlquist: ip[0] = method; heat2d: ip[0] =   */
-                            /* first tile of boundary nodes)                                      */
+                            /* first tile of boundary nodes, ip[1] = 1 for backward Euler: lets   */
+                            /* the one-thread-per-mode sweeps drop the explicit factor)           */
     const double *sig_dev;  /* HEAT2D: [pitch] fx*lambda_k + fy*mu_l per sine coefficient, the    */
                             /* Dirichlet value per boundary node, 0 in the padding; else NULL     */
     const double *diag_dev; /* HEAT1D_SINE: [2][chunk][team_threads] thread-transposed: the       */
@@ -253,6 +254,9 @@ int mgb_set_stop_flag(const int32_t *flag_dev);
 int mgb_write_flag(int32_t *flag_dev, int32_t value, void *stream);
 int mgb_convergence_flag(const double *norm_dev, int32_t t_norm, double tol, double *hist_dev, int32_t *flag_dev,
                          void *stream);
+/* One time rank: mgb_temporal_norm and mgb_convergence_flag in one launch (nothing to reduce in between). */
+int mgb_temporal_norm_flag(const double *sq_dev, int32_t count, int32_t t_norm, double *out_dev, double tol, double *hist_dev,
+                           int32_t *flag_dev, void *stream);
 
 /* Nested iteration, mgrit.py:559-563: fine.u[c_j] = coarse.u[j] for j >= 1. */
 int mgb_inject_up(const mgb_level *fine, const mgb_level *coarse, void *stream);
@@ -277,6 +281,26 @@ int mgb_heat2d_to_rows(int32_t nx, int32_t ny, const double *sx_dev, const doubl
 /* The inverse: nodes[b] from rows[b]. */
 int mgb_heat2d_from_rows(int32_t nx, int32_t ny, const double *sx_dev, const double *sy_dev, const double *rows_dev,
                          double *nodes_dev, int32_t count, double *work_dev, void *stream);
+
+/* ---- Advection1D: the coarsest-level solve in Fourier space (csrc/fourier.cu) ------------------------------------ */
+/* mgrit.py:459-486 on a level of Advection1D (advection_1d.py:129-143): Phi_i = (I + dt_i (c/dx)(I - S))^-1 is circulant,
+ * so u_i = g_i + Phi_i(u_{i-1}) decouples under the discrete Fourier transform into n/2 + 1 complex scalar recurrences
+ *     W[i][k] = W[i-1][k] / (1 + nu_i (1 - exp(-2 pi i k / n))) + W[i][k],   nu_i = c_over_dx (t[i] - t[i-1]),
+ * which run time-parallel in one launch.  Three calls replace the chain of npts - 1 dependent cyclic solves:
+ *     work  = rfft([u[0]; g[1..]])     mgb_rows_rfft    (Bluestein: any n <= 4096; row r -> [2 (n/2+1)] doubles re, im)
+ *     recurrences in place on work      mgb_advection1d_spectral_recur
+ *     u[i]  = irfft(work[i]), i >= 1    mgb_rows_irfft
+ * Tables (made once per n by mgb_circ_fft_tables; M = mgb_circ_fft_length(n) = 2^p >= 2n - 1): tw [M/2], chirp [n],
+ * bhat [M] complex doubles each; work_dev: M complex doubles of scratch.  ld* in doubles, ldc and ldw even, c_dev and
+ * work_dev 16-byte aligned. */
+int mgb_circ_fft_length(int32_t n);
+int mgb_circ_fft_tables(int32_t n, double *tw_dev, double *chirp_dev, double *bhat_dev, double *work_dev, void *stream);
+int mgb_rows_rfft(int32_t m, int32_t n, const double *a_dev, int64_t lda, const double *a_row0_dev, const double *tw_dev,
+                  const double *chirp_dev, const double *bhat_dev, double *c_dev, int64_t ldc, void *stream);
+int mgb_rows_irfft(int32_t m, int32_t first_row, int32_t n, const double *c_dev, int64_t ldc, const double *tw_dev,
+                   const double *chirp_dev, const double *bhat_dev, double *out_dev, int64_t ldo, void *stream);
+int mgb_advection1d_spectral_recur(int32_t n, int32_t npts, const double *t_dev, double c_over_dx, double *work_dev,
+                                   int64_t ldw, void *stream);
 
 /* ---- Heat1D: the coarsest-level solve in sine space (csrc/spectral.cu) ------------------------------------- */
 /* mgrit.py:459-486 runs npts-1 dependent Phi applications on one spatial system; every time rank waits for that chain

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libmgrit_b200.so')
 APP_BATCHED = 0            # no fused team kernels: the batched path (core/batched.py, csrc/generic.cu)
 APP_HEAT1D, APP_ADVECTION1D, APP_DAHLQUIST, APP_BRUSSELATOR, APP_HEAT2D, APP_HEAT1D_2PTS, APP_HEAT1D_SINE = 1, 2, 3, 4, 5, 6, 7
 TNORM_ONE, TNORM_TWO, TNORM_INF = 1, 2, 3
-ABI_VERSION = 9
+ABI_VERSION = 10
 F_RELAX_LAST_ONLY = 1
 CORRECT_F_RELAX, CORRECT_GHOST, CORRECT_LAST_ONLY = 1, 2, 4
 DAHLQUIST_METHODS = {'BE': 0, 'FE': 1, 'TR': 2, 'MR': 3}
@@ -67,6 +67,8 @@ SYMBOLS = {
     'mgb_temporal_norm': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'mgb_set_stop_flag': (C.c_int, [C.c_void_p]),
     'mgb_write_flag': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    'mgb_temporal_norm_flag': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     'mgb_convergence_flag': (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mgb_inject_up': (C.c_int, [_LP, _LP, C.c_void_p]),
     'mgb_step': (C.c_int, [_LP, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -84,6 +86,14 @@ SYMBOLS = {
     'mgb_heat1d_spectral_recur': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_sine_level_solve': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_heat1d_spectral_fixup': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    'mgb_circ_fft_length': (C.c_int, [C.c_int32]),
+    'mgb_circ_fft_tables': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mgb_rows_rfft': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int64, C.c_void_p]),
+    'mgb_rows_irfft': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int64, C.c_void_p]),
+    'mgb_advection1d_spectral_recur': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_int64,
+                                                 C.c_void_p]),
     'mgb_rows_lincomb': (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_int32,
                                    C.c_void_p, C.c_double, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_int32,
                                    C.c_void_p, C.c_void_p]),

@@ -39,3 +39,73 @@ class Advection1D(DeviceApplication):
                    sconst=dl.step_const_table(self.kind, dts * fac, self.nx, team_threads, chunk))
         tab['cw'] = tab['sconst'].shape[1]
         return tab
+
+    # ---- coarsest-level solve in Fourier space (csrc/fourier.cu) -------------------------------------------------
+    SPECTRAL_MIN_POINTS = 96     # below this the sequential Phi chain (mgb_forward_solve) is as fast
+    spectral_single_rank_only = True
+    SPECTRAL_MAX_N = 4096        # one row's convolution (2^p >= 2n - 1 complex doubles) must fit in shared memory
+
+    def spectral_solver(self, level):
+        """A FourierSolve for `level` (the coarsest DeviceLevel of a hierarchy), or None when the chain of Phi
+        applications is used: short levels, long rows, or MGB_ADVECTION_FOURIER=0."""
+        import os
+        if (os.environ.get('MGB_ADVECTION_FOURIER', '1') == '0' or level.npts < self.SPECTRAL_MIN_POINTS
+                or self.nx > self.SPECTRAL_MAX_N):
+            return None
+        return FourierSolve(self, level)
+
+    def spectral_min_points(self):
+        return self.SPECTRAL_MIN_POINTS
+
+
+_FFT_TABLES = {}         # (device, n) -> (tw, chirp, bhat)
+
+
+def circ_fft_tables(n, dev):
+    """Twiddles, chirp and the chirp's spectrum for rows of length n (include/mgrit_b200.h, mgb_circ_fft_tables)."""
+    torch = dl._torch()
+    key = (dev.index, int(n))
+    hit = _FFT_TABLES.get(key)
+    if hit is None:
+        m = _lib.lib().mgb_circ_fft_length(int(n))
+        mk = lambda cnt: torch.empty((cnt, 2), dtype=torch.float64, device=dev)
+        tw, chirp, bhat, work = mk(m // 2), mk(n), mk(m), mk(m)
+        _lib.check(_lib.lib().mgb_circ_fft_tables(int(n), tw.data_ptr(), chirp.data_ptr(), bhat.data_ptr(), work.data_ptr(),
+                                                  _lib.current_stream_ptr()), 'circ_fft_tables')
+        hit = (tw, chirp, bhat, work)            # `work` stays alive until the stream has used it
+        _FFT_TABLES[key] = hit
+    return hit[:3]
+
+
+class FourierSolve:
+    """u_i = g_i + Phi_i(u_{i-1}) over a whole level (mgrit.py:459-486) as a real Fourier transform of all rows, n/2 + 1
+    complex scalar recurrences that run time-parallel, and the inverse transform (include/mgrit_b200.h, "the
+    coarsest-level solve in Fourier space").  One time rank; with several ranks the solver keeps the chain."""
+    def __init__(self, app, level):
+        torch = dl._torch()
+        dev = level.u.device
+        self.level, self.n = level, int(app.nx)
+        self.fac = float(app.c) / float(app.dx)                      # advection_1d.py:108
+        self.h2d_bytes = 0
+        level.ensure_t_dev()                                         # the recurrences read dt_i = t[i] - t[i-1]
+        self.tw, self.chirp, self.bhat = circ_fft_tables(self.n, dev)
+        self.ldw = 2 * (self.n // 2 + 1)
+        self.work = torch.empty((level.npts, self.ldw), dtype=torch.float64, device=dev)
+
+    def solve(self, comm):
+        """The whole level; returns the number of kernel launches."""
+        lv, lib, st = self.level, _lib.lib(), _lib.current_stream_ptr()
+        if lv.npts < 2:
+            return 0
+        src = lv.g if lv.g is not None else lv.u                     # a one-level "hierarchy" has no g: rows 1.. are zero
+        if lv.g is None:
+            lv.u[1:].zero_()
+        _lib.check(lib.mgb_rows_rfft(lv.npts, self.n, src.data_ptr(), lv.pitch, lv.u.data_ptr(), self.tw.data_ptr(),
+                                     self.chirp.data_ptr(), self.bhat.data_ptr(), self.work.data_ptr(), self.ldw, st),
+                   'rows_rfft')
+        _lib.check(lib.mgb_advection1d_spectral_recur(self.n, lv.npts, lv.t_dev.data_ptr(), self.fac, self.work.data_ptr(),
+                                                      self.ldw, st), 'advection1d_spectral_recur')
+        _lib.check(lib.mgb_rows_irfft(lv.npts, 1, self.n, self.work.data_ptr(), self.ldw, self.tw.data_ptr(),
+                                      self.chirp.data_ptr(), self.bhat.data_ptr(), lv.u.data_ptr(), lv.pitch, st),
+                   'rows_irfft')
+        return 3

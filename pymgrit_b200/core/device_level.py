@@ -8,6 +8,13 @@ import numpy as np
 from pymgrit_b200 import _lib
 
 _SHARED_TABLES = {}        # (device, table key) -> weak reference to a device tensor several levels point to
+TRACE = None               # a list while scripts/e2e_breakdown.py measures: (label, perf_counter seconds) marks of the setup
+
+
+def mark(label):
+    if TRACE is not None:
+        import time
+        TRACE.append((label, time.perf_counter()))
 
 
 def _torch():
@@ -115,13 +122,16 @@ class DeviceLevel:
         self.team_threads, self.chunk = (0, 0) if self.batched else team_shape(app.kind, self.n)
         # the (asynchronous) zero fill of the level arrays runs on the device while the host builds the tables
         self.zero_filled = bool(zero_u) and u_init is None
+        mark('level: shape')
         if u_init is not None:
             self.u = u_init
         elif zero_u:
             self.u = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev)
         else:
             self.u = torch.empty((self.npts, self.pitch), dtype=torch.float64, device=dev)
+        mark('level: u allocated')
         self.g = torch.zeros((self.npts, self.pitch), dtype=torch.float64, device=dev) if with_g else None
+        mark('level: g allocated')
         self.cpts = None if cpts is None else np.asarray(cpts, dtype=np.int32)
         self._keep = []                                   # tensors referenced by the struct
         self.h2d_bytes = 0
@@ -136,7 +146,9 @@ class DeviceLevel:
         torch = _torch()
         app, dev = self.app, self.u.device
         tiny = app.kind in (_lib.APP_DAHLQUIST, _lib.APP_BRUSSELATOR)
+        mark('tables: begin')
         tab = app.level_tables(self.t, self.team_threads, self.chunk)
+        mark('tables: host tables made')
 
         def up(a, dtype):
             if a is None:
@@ -222,6 +234,7 @@ class DeviceLevel:
         for k, v in enumerate(tab.get('ip', [])):
             c.ip[k] = int(v)
         self.c = c
+        mark('tables: uploaded')
 
     @property
     def ref(self):

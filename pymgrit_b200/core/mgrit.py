@@ -250,6 +250,8 @@ class Mgrit:
         last = self._lv[-1]
         maker = getattr(problem[-1], 'spectral_solver', None)
         min_pts = problem[-1].spectral_min_points() if hasattr(problem[-1], 'spectral_min_points') else 1 << 30
+        if maker is not None and getattr(problem[-1], 'spectral_single_rank_only', False) and self.comm_time_size > 1:
+            maker = None                     # (Advection1D's Fourier solve: the rank-to-rank chain stays)
         flags.append(maker is not None and last.npts >= min_pts)
         flags = self.comm_time.all_true(flags)          # every rank must take the same path: one small all-reduce
         self._fused_down = flags[:-1] + [False]
@@ -750,6 +752,12 @@ class Mgrit:
         """Residual norms, temporal norm, reduction over the time ranks, and the device-side stopping test."""
         lv0 = self._lv[0]
         ncp = 0 if lv0.cpts is None else len(lv0.cpts)
+        if ncp > 0 and self.comm_time_size == 1:
+            sq = self.compute_residual()             # one rank: norm and stopping test in one launch
+            _lib.check(_lib.lib().mgb_temporal_norm_flag(sq.data_ptr(), ncp, self._t_norm_id, self._norm_out.data_ptr(),
+                                                         float(self.tol), self._hist_dev[slot:].data_ptr(),
+                                                         self._flag.data_ptr(), self._stream()), 'temporal_norm_flag')
+            return
         if ncp > 0:
             sq = self.compute_residual()
             _lib.check(_lib.lib().mgb_temporal_norm(sq.data_ptr(), ncp, self._t_norm_id, self._norm_out.data_ptr(),

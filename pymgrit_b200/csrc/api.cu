@@ -226,8 +226,10 @@ __global__ void k_copy_rows(const double *__restrict__ src, double *__restrict__
 __device__ __forceinline__ double tn_map(double v, int mode) { return mode == MGB_TNORM_TWO ? v : sqrt(v); }
 __device__ __forceinline__ double tn_comb(double a, double b, int mode) { return mode == MGB_TNORM_INF ? fmax(a, b) : a + b; }
 
+// hist != nullptr (one time rank: nothing to reduce between the norm and the stopping test): the norm also goes to hist[0]
+// and the flag goes up if the stopping test of mgrit.py:626 holds -- k_convergence_flag in the same launch
 __global__ void k_temporal_norm(const double *__restrict__ sq, int count, int mode, double *__restrict__ out,
-                                const int *__restrict__ stop) {
+                                const int *__restrict__ stop, double tol, double *__restrict__ hist, int *__restrict__ flag) {
     if (stop != nullptr && *stop != 0) return;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     const int T = blockDim.x;
@@ -248,7 +250,14 @@ __global__ void k_temporal_norm(const double *__restrict__ sq, int count, int mo
         if ((int)threadIdx.x < d) s[threadIdx.x] = tn_comb(s[threadIdx.x], s[threadIdx.x + d], mode);
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = s[0];
+    if (threadIdx.x == 0) {
+        out[0] = s[0];
+        if (hist != nullptr) {
+            hist[0] = s[0];
+            const double conv = (mode == MGB_TNORM_TWO) ? sqrt(s[0]) : s[0];
+            if (conv < tol) *flag = 1;
+        }
+    }
 }
 
 __global__ void k_axpby(int n, double a, const double *__restrict__ x, double b, const double *__restrict__ y,
@@ -518,8 +527,20 @@ int mgb_temporal_norm(const double *sq_dev, int32_t count, int32_t t_norm, doubl
     if (sq_dev == nullptr || out_dev == nullptr || count < 0 || t_norm < 1 || t_norm > 3)
         return fail(MGB_EINVAL, "bad argument%s");
     if (device_info() == nullptr) return MGB_ECUDA;
-    k_temporal_norm<<<1, 1024, 0, (cudaStream_t)stream>>>(sq_dev, count, t_norm, out_dev, g_stop);
+    k_temporal_norm<<<1, 1024, 0, (cudaStream_t)stream>>>(sq_dev, count, t_norm, out_dev, g_stop, 0.0, nullptr, nullptr);
     return cuda_fail(cudaGetLastError(), "temporal_norm");
+}
+
+int mgb_temporal_norm_flag(const double *sq_dev, int32_t count, int32_t t_norm, double *out_dev, double tol, double *hist_dev,
+                           int32_t *flag_dev, void *stream) {
+    if (sq_dev == nullptr || out_dev == nullptr || hist_dev == nullptr || flag_dev == nullptr || count < 0 || t_norm < 1 ||
+        t_norm > 3)
+        return fail(MGB_EINVAL, "bad argument%s");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    // the kernel's own stop test (flag_dev is the registered stop flag while a solve is queued ahead) keeps the history
+    // of an iteration that was queued after the criterion was met untouched, like k_convergence_flag
+    k_temporal_norm<<<1, 1024, 0, (cudaStream_t)stream>>>(sq_dev, count, t_norm, out_dev, flag_dev, tol, hist_dev, flag_dev);
+    return cuda_fail(cudaGetLastError(), "temporal_norm_flag");
 }
 
 int mgb_set_stop_flag(const int32_t *flag_dev) {

@@ -1,0 +1,465 @@
+// fourier.cu -- the sequential coarsest-level solve of Advection1D without its sequential Phi chain.
+//
+// mgrit.py:459-486 computes u_i = g_i + Phi_i(u_{i-1}), i = 1..N-1, one Phi after the other; Phi_i = (I + dt_i L)^-1 with
+// the CIRCULANT upwind matrix L = (c/dx)(I - S), (S u)_j = u_{j-1} periodic (advection_1d.py:100-118, 129-143).  A
+// circulant matrix is diagonalised by the discrete Fourier transform: with X_k = sum_j x_j exp(-2 pi i j k / n) the solve
+// becomes, per frequency k, the complex scalar recurrence
+//     U_i[k] = U_{i-1}[k] / (1 + nu_i (1 - exp(-i theta_k))) + G_i[k],     nu_i = (c/dx) dt_i,  theta_k = 2 pi k / n,
+// i.e. a composition of affine maps that runs TIME-PARALLEL (chunks of steps composed, combined, rerun -- the scheme of
+// spectral.cu's k_sine_solve with complex coefficients).  8192 dependent cyclic solves of cfg 4's coarsest level become
+// two transforms of all rows and ~2 N / chunks dependent complex FMAs.  The same linear systems are solved exactly (a
+// direct method like the reference's SuperLU call); only the order of the rounding errors differs (tests: <= 1e-12).
+//
+// n is arbitrary (nx = 4096 -> n = 4095 = 3^2 5 7 13), so the transform is Bluestein's: j k = (j^2 + k^2 - (k-j)^2) / 2,
+//     X_k = conj(w_k) sum_j (x_j conj(w_j)) w_{k-j},      w_m = exp(i pi m^2 / n)      (m^2 reduced mod 2n in integers)
+// a cyclic convolution of length M = 2^p >= 2n - 1 done with a radix-2 FFT in shared memory: one CTA per row, M complex
+// doubles (128 KB for n <= 4096), decimation in frequency forwards (natural in, bit-reversed out), the chirp's spectrum
+// stored in that same bit-reversed order, decimation in time backwards (bit-reversed in, natural out).  Rows are real, so
+// only k = 0 .. n/2 are kept: [npts][2 (n/2 + 1)] doubles (re, im).
+#include "../../include/mgrit_b200.h"
+#include "phi.cuh"
+#include "table.h"
+
+namespace mgb {
+
+int heat2d_fail(const char *msg);  // api.cu: records the message, returns MGB_EINVAL
+
+namespace fourier {
+
+constexpr int kThreads = 512;   // radix-8 passes hold 8 complex values per thread: 128 registers each
+
+__device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cmulc(const double2 a, const double2 b) {  // a * conj(b)
+    return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
+}
+
+// tw[t] = exp(-2 pi i t / M), t < M/2;  chirp[j] = exp(i pi j^2 / n), j < n;  b[m] = chirp[|m|] wrapped to length M
+__global__ void k_tables(int n, int M, double2 *__restrict__ tw, double2 *__restrict__ chirp, double2 *__restrict__ b) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < M / 2) {
+        double sn, cs;
+        sincospi(-2.0 * (double)q / (double)M, &sn, &cs);
+        tw[q] = make_double2(cs, sn);
+    }
+    if (q < M) {
+        int m = -1;
+        if (q < n) m = q;
+        else if (M - q < n) m = M - q;
+        double2 v = make_double2(0.0, 0.0);
+        if (m >= 0) {
+            const long r = ((long)m * m) % (2L * n);
+            double sn, cs;
+            sincospi((double)r / (double)n, &sn, &cs);
+            v = make_double2(cs, sn);
+            if (q < n) chirp[q] = v;
+        }
+        b[q] = v;
+    }
+}
+
+// Radix-2 decimation-in-frequency stages s_top, s_top-1, .., s_top-RL+1 of the in-place transform (natural order in,
+// bit-reversed order out) in ONE pass over shared memory: a thread takes the 2^RL elements hi 2^(s_top+1) + a 2^q + lo
+// (q = s_top-RL+1) into registers and runs the RL stages there.  Radix 8 moves the row through shared memory 5 times
+// instead of 13 (the passes are bound by shared-memory bandwidth, not by the FP64 pipe).  mul != nullptr: the results are
+// multiplied by mul[index] on the way out (the chirp's spectrum, stored in the same bit-reversed order).
+template <int RL>
+__device__ __forceinline__ void dif_pass(double2 *z, const int log2m, const int s_top, const double2 *__restrict__ tw,
+                                         const double2 *__restrict__ mul) {
+    constexpr int RN = 1 << RL;
+    const int q = s_top - RL + 1, H = 1 << (log2m - 1), groups = 1 << (log2m - RL);
+    for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+        const int lo = gi & ((1 << q) - 1), hi = gi >> q;
+        const int base = (hi << (s_top + 1)) + lo;
+        double2 v[RN];
+#pragma unroll
+        for (int a = 0; a < RN; ++a) v[a] = z[base + (a << q)];
+#pragma unroll
+        for (int j = 0; j < RL; ++j) {
+            const int s = s_top - j, ha = 1 << (RL - 1 - j);     // pairs (a, a + ha), a with that bit clear
+#pragma unroll
+            for (int a = 0; a < RN; ++a) {
+                if (a & ha) continue;
+                const int pos = ((a & (ha - 1)) << q) + lo;
+                const double2 w = __ldg(tw + pos * (H >> s));
+                const double2 x = v[a], y = v[a + ha];
+                v[a] = make_double2(x.x + y.x, x.y + y.y);
+                v[a + ha] = cmul(make_double2(x.x - y.x, x.y - y.y), w);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < RN; ++a) {
+            const int idx = base + (a << q);
+            z[idx] = mul ? cmul(v[a], __ldg(mul + idx)) : v[a];
+        }
+    }
+    __syncthreads();
+}
+// the inverse flow graph, stages q .. q+RL-1 ascending (bit-reversed order in, natural order out, not scaled)
+template <int RL>
+__device__ __forceinline__ void dit_pass(double2 *z, const int log2m, const int q, const double2 *__restrict__ tw) {
+    constexpr int RN = 1 << RL;
+    const int s_top = q + RL - 1, H = 1 << (log2m - 1), groups = 1 << (log2m - RL);
+    for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+        const int lo = gi & ((1 << q) - 1), hi = gi >> q;
+        const int base = (hi << (s_top + 1)) + lo;
+        double2 v[RN];
+#pragma unroll
+        for (int a = 0; a < RN; ++a) v[a] = z[base + (a << q)];
+#pragma unroll
+        for (int j = RL - 1; j >= 0; --j) {
+            const int s = s_top - j, ha = 1 << (RL - 1 - j);
+#pragma unroll
+            for (int a = 0; a < RN; ++a) {
+                if (a & ha) continue;
+                const int pos = ((a & (ha - 1)) << q) + lo;
+                const double2 x = v[a];
+                const double2 y = cmulc(v[a + ha], __ldg(tw + pos * (H >> s)));
+                v[a] = make_double2(x.x + y.x, x.y + y.y);
+                v[a + ha] = make_double2(x.x - y.x, x.y - y.y);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < RN; ++a) z[base + (a << q)] = v[a];
+    }
+    __syncthreads();
+}
+// in place, natural order in, bit-reversed order out (times mul on the way out of the last pass)
+__device__ __forceinline__ void fft_dif(double2 *z, const int log2m, const double2 *__restrict__ tw,
+                                        const double2 *__restrict__ mul) {
+    int s = log2m - 1;
+    for (; s >= 5; s -= 3) dif_pass<3>(z, log2m, s, tw, nullptr);   // at least 3 stages remain after each of these
+    // s + 1 in {3, 4, 5} stages left (or fewer for short rows)
+    if (s + 1 == 5) {
+        dif_pass<3>(z, log2m, s, tw, nullptr);
+        dif_pass<2>(z, log2m, s - 3, tw, mul);
+    } else if (s + 1 == 4) {
+        dif_pass<2>(z, log2m, s, tw, nullptr);
+        dif_pass<2>(z, log2m, s - 2, tw, mul);
+    } else if (s + 1 == 3) {
+        dif_pass<3>(z, log2m, s, tw, mul);
+    } else if (s + 1 == 2) {
+        dif_pass<2>(z, log2m, s, tw, mul);
+    } else {
+        dif_pass<1>(z, log2m, s, tw, mul);
+    }
+}
+// the inverse flow graph: bit-reversed order in, natural order out, not scaled (divide by M)
+__device__ __forceinline__ void ifft_dit(double2 *z, const int log2m, const double2 *__restrict__ tw) {
+    const int rem = log2m % 3 == 0 ? 3 : (log2m % 3 == 1 ? (log2m >= 4 ? 4 : 1) : (log2m >= 5 ? 5 : 2));
+    int q = 0;
+    if (rem == 5) {
+        dit_pass<2>(z, log2m, 0, tw);
+        dit_pass<3>(z, log2m, 2, tw);
+        q = 5;
+    } else if (rem == 4) {
+        dit_pass<2>(z, log2m, 0, tw);
+        dit_pass<2>(z, log2m, 2, tw);
+        q = 4;
+    } else if (rem == 3) {
+        dit_pass<3>(z, log2m, 0, tw);
+        q = 3;
+    } else if (rem == 2) {
+        dit_pass<2>(z, log2m, 0, tw);
+        q = 2;
+    } else {
+        dit_pass<1>(z, log2m, 0, tw);
+        q = 1;
+    }
+    for (; q < log2m; q += 3) dit_pass<3>(z, log2m, q, tw);
+}
+// z <- cyclic convolution of z with the chirp (times M)
+__device__ __forceinline__ void chirp_conv(double2 *z, const int log2m, const double2 *__restrict__ tw,
+                                           const double2 *__restrict__ bhat) {
+    fft_dif(z, log2m, tw, bhat);
+    ifft_dit(z, log2m, tw);
+}
+
+__global__ void __launch_bounds__(kThreads) k_bhat(const int log2m, const double2 *__restrict__ tw,
+                                                   const double2 *__restrict__ b, double2 *__restrict__ bhat) {
+    extern __shared__ double2 z[];
+    const int M = 1 << log2m;
+    for (int p = threadIdx.x; p < M; p += blockDim.x) z[p] = b[p];
+    __syncthreads();
+    fft_dif(z, log2m, tw, nullptr);
+    for (int p = threadIdx.x; p < M; p += blockDim.x) bhat[p] = z[p];
+}
+
+// Rows are real: two of them share one complex transform, Z = F(x_a + i x_b), X_a[k] = (Z_k + conj(Z_{n-k})) / 2,
+// X_b[k] = (Z_k - conj(Z_{n-k})) / (2i).
+// C[r][2k], C[r][2k+1] = re, im of sum_j A[r][j] exp(-2 pi i j k / n), k = 0 .. n/2.  Row 0 of A from a_row0 if not null.
+__global__ void __launch_bounds__(kThreads) k_rows_rfft(const int rows, const int n, const int log2m,
+                                                        const double *__restrict__ A, const long lda,
+                                                        const double *__restrict__ a_row0, const double2 *__restrict__ tw,
+                                                        const double2 *__restrict__ chirp, const double2 *__restrict__ bhat,
+                                                        double *__restrict__ Cm, const long ldc, const int *__restrict__ stop) {
+    if (stop != nullptr && *stop != 0) return;
+    extern __shared__ double2 z[];
+    const int M = 1 << log2m, K = n / 2 + 1;
+    const double scale = 0.5 / (double)M;
+    for (int pr = blockIdx.x; 2 * pr < rows; pr += gridDim.x) {
+        const int ra = 2 * pr, rb = ra + 1;
+        const double *xa = (ra == 0 && a_row0 != nullptr) ? a_row0 : A + (long)ra * lda;
+        const double *xb = rb < rows ? A + (long)rb * lda : nullptr;
+        for (int j = threadIdx.x; j < M; j += blockDim.x) {
+            double2 v = make_double2(0.0, 0.0);
+            if (j < n) v = cmulc(make_double2(xa[j], xb ? xb[j] : 0.0), __ldg(chirp + j));
+            z[j] = v;
+        }
+        __syncthreads();
+        chirp_conv(z, log2m, tw, bhat);
+        double2 *oa = reinterpret_cast<double2 *>(Cm + (long)ra * ldc);
+        double2 *ob = xb ? reinterpret_cast<double2 *>(Cm + (long)rb * ldc) : nullptr;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const int km = (k == 0) ? 0 : n - k;
+            const double2 zk = cmulc(z[k], __ldg(chirp + k)), zm = cmulc(z[km], __ldg(chirp + km));
+            // (Z_k + conj(Z_m)) / 2  and  (Z_k - conj(Z_m)) / (2i) = (Im(Z_k) + Im(Z_m), Re(Z_m) - Re(Z_k)) / 2
+            oa[k] = make_double2((zk.x + zm.x) * scale, (zk.y - zm.y) * scale);
+            if (ob) ob[k] = make_double2((zk.y + zm.y) * scale, (zm.x - zk.x) * scale);
+        }
+        __syncthreads();
+    }
+}
+
+// out[r][j] = (1/n) sum_{k<n} X[r][k] exp(+2 pi i j k / n) with X[r][n-k] = conj(X[r][k]), rows first_row .. rows-1, two
+// rows per transform: Y = X_a + i X_b (Hermitian extensions), x_a + i x_b = conj(F(conj(Y))) / n.
+__global__ void __launch_bounds__(kThreads) k_rows_irfft(const int rows, const int first_row, const int n, const int log2m,
+                                                         const double *__restrict__ Cm, const long ldc,
+                                                         const double2 *__restrict__ tw, const double2 *__restrict__ chirp,
+                                                         const double2 *__restrict__ bhat, double *__restrict__ out,
+                                                         const long ldo, const int *__restrict__ stop) {
+    if (stop != nullptr && *stop != 0) return;
+    extern __shared__ double2 z[];
+    const int M = 1 << log2m, K = n / 2 + 1;
+    const double scale = 1.0 / ((double)M * (double)n);
+    for (int pr = blockIdx.x; first_row + 2 * pr < rows; pr += gridDim.x) {
+        const int ra = first_row + 2 * pr, rb = ra + 1;
+        const double2 *Xa = reinterpret_cast<const double2 *>(Cm + (long)ra * ldc);
+        const double2 *Xb = rb < rows ? reinterpret_cast<const double2 *>(Cm + (long)rb * ldc) : nullptr;
+        for (int k = threadIdx.x; k < M; k += blockDim.x) {
+            double2 v = make_double2(0.0, 0.0);
+            if (k < n) {
+                // Hermitian extension: X[k] for k <= n/2, conj(X[n-k]) above
+                const bool up = k >= K;
+                const int kk = up ? n - k : k;
+                double2 a = Xa[kk], b = Xb ? Xb[kk] : make_double2(0.0, 0.0);
+                if (up) {
+                    a.y = -a.y;
+                    b.y = -b.y;
+                }
+                // conj(Y) = conj(a + i b) = (a.x - b.y) - i (a.y + b.x)
+                v = cmulc(make_double2(a.x - b.y, -(a.y + b.x)), __ldg(chirp + k));
+            }
+            z[k] = v;
+        }
+        __syncthreads();
+        chirp_conv(z, log2m, tw, bhat);
+        double *oa = out + (long)ra * ldo;
+        double *ob = Xb ? out + (long)rb * ldo : nullptr;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const double2 f = cmulc(z[j], __ldg(chirp + j));     // F(conj(Y))_j times M
+            oa[j] = f.x * scale;
+            if (ob) ob[j] = -f.y * scale;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- the complex recurrences, time-parallel (spectral.cu k_sine_solve with complex factors) ----------------------------
+constexpr int kFreqs = 16;      // frequencies per CTA: 16 consecutive double2 = 256 B per row access
+constexpr int kMaxChunks = 64;  // x chunks of consecutive steps = 1024 threads
+
+// factor of step i for frequency (cx, sx) = (1 - cos theta, sin theta): 1 / (1 + nu cx + i nu sx)
+__device__ __forceinline__ double2 step_factor(const double nu, const double cx, const double sx) {
+    const double dr = fma(nu, cx, 1.0), di = nu * sx;
+    const double inv = __drcp_rn(fma(dr, dr, di * di));
+    return make_double2(dr * inv, -di * inv);
+}
+
+template <bool STORE>
+__device__ __forceinline__ void cplx_chunk(double2 &u, double2 &prod, double2 *__restrict__ W, const long ldw2, const int k,
+                                           const bool act, const int i0, const int i1, const double *__restrict__ t,
+                                           const double fac, const double cx, const double sx) {
+    constexpr int B = 4;
+    int i = i0;
+    for (; i + B <= i1; i += B) {
+        double2 gv[B];
+        double tv[B + 1];
+#pragma unroll
+        for (int j = 0; j < B; ++j) gv[j] = W[(long)(i + j) * ldw2 + k];
+#pragma unroll
+        for (int j = 0; j <= B; ++j) tv[j] = __ldg(t + i - 1 + j);
+        double2 f[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) f[j] = step_factor(fac * __dsub_rn(tv[j + 1], tv[j]), cx, sx);
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const double2 m = cmul(u, f[j]);
+            u = make_double2(m.x + gv[j].x, m.y + gv[j].y);
+            if (STORE) {
+                if (act) W[(long)(i + j) * ldw2 + k] = u;
+            } else {
+                prod = cmul(prod, f[j]);
+            }
+        }
+    }
+    for (; i < i1; ++i) {
+        const double2 f = step_factor(fac * __dsub_rn(__ldg(t + i), __ldg(t + i - 1)), cx, sx);
+        const double2 g = W[(long)i * ldw2 + k];
+        const double2 m = cmul(u, f);
+        u = make_double2(m.x + g.x, m.y + g.y);
+        if (STORE) {
+            if (act) W[(long)i * ldw2 + k] = u;
+        } else {
+            prod = cmul(prod, f);
+        }
+    }
+}
+
+// W[i][k] <- W[i-1][k] f_i[k] + W[i][k], i = 1 .. npts-1, in place (W[0] = transformed start value, W[i] = transformed g_i)
+__global__ void __launch_bounds__(1024) k_cplx_solve(double2 *__restrict__ W, const long ldw2, const int n, const int K,
+                                                     const int npts, const double *__restrict__ t, const double fac,
+                                                     const int len, const int *__restrict__ stop) {
+    if (stop != nullptr && *stop != 0) return;
+    __shared__ double2 sA[kMaxChunks][kFreqs], sB[kMaxChunks][kFreqs];
+    const int tx = threadIdx.x, c = threadIdx.y, nch = blockDim.y;
+    const int kreal = blockIdx.x * kFreqs + tx;
+    const bool act = kreal < K;
+    const int k = act ? kreal : K - 1;  // idle lanes of the last CTA shadow the last frequency and store nothing
+    double sn, cs;
+    {   // theta = 2 pi k / n, reduced exactly: sincospi(2 k / n)
+        sincospi(2.0 * (double)k / (double)n, &sn, &cs);
+    }
+    const double cx = 1.0 - cs, sx = sn;
+    const int i0 = min(npts, 1 + c * len), i1 = min(npts, i0 + len);
+    double2 a = make_double2(1.0, 0.0), b = make_double2(0.0, 0.0);
+    if (nch > 1) {
+        cplx_chunk<false>(b, a, W, ldw2, k, act, i0, i1, t, fac, cx, sx);
+        sA[c][tx] = a;
+        sB[c][tx] = b;
+        __syncthreads();
+    }
+    double2 u = W[k];
+    for (int cc = 0; cc < c; ++cc) {
+        const double2 m = cmul(sA[cc][tx], u);
+        u = make_double2(m.x + sB[cc][tx].x, m.y + sB[cc][tx].y);
+    }
+    double2 unused = make_double2(1.0, 0.0);
+    cplx_chunk<true>(u, unused, W, ldw2, k, act, i0, i1, t, fac, cx, sx);
+}
+
+static int log2_conv_len(int n) {
+    int p = 0;
+    while ((1L << p) < 2L * n - 1) ++p;
+    return p < 1 ? 1 : p;
+}
+
+}  // namespace fourier
+}  // namespace mgb
+
+using namespace mgb;
+using namespace mgb::fourier;
+
+extern "C" {
+
+int mgb_circ_fft_length(int32_t n) {
+    if (n < 1) return 0;
+    return 1 << log2_conv_len(n);
+}
+
+int mgb_circ_fft_tables(int32_t n, double *tw_dev, double *chirp_dev, double *bhat_dev, double *work_dev, void *stream) {
+    if (n < 1 || tw_dev == nullptr || chirp_dev == nullptr || bhat_dev == nullptr || work_dev == nullptr)
+        return heat2d_fail("circ_fft_tables: bad argument");
+    const DeviceInfo *di = device_info();
+    if (di == nullptr) return MGB_ECUDA;
+    const int p = log2_conv_len(n), M = 1 << p;
+    const size_t smem = (size_t)M * sizeof(double2);
+    if ((int)smem > di->max_smem_optin) return heat2d_fail("circ_fft_tables: row too long for shared memory (n <= 4096)");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_tables<<<(M + 255) / 256, 256, 0, st>>>(n, M, (double2 *)tw_dev, (double2 *)chirp_dev, (double2 *)work_dev);
+    cudaError_t e = cudaFuncSetAttribute(k_bhat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    k_bhat<<<1, kThreads, smem, st>>>(p, (const double2 *)tw_dev, (const double2 *)work_dev, (double2 *)bhat_dev);
+    return cuda_fail(cudaGetLastError(), "circ_fft_tables");
+}
+
+static int fft_smem(int n, int *p_out, size_t *smem_out) {
+    const DeviceInfo *di = device_info();
+    if (di == nullptr) return MGB_ECUDA;
+    const int p = log2_conv_len(n);
+    const size_t smem = ((size_t)1 << p) * sizeof(double2);
+    if ((int)smem > di->max_smem_optin) return heat2d_fail("rows_rfft: row too long for shared memory (n <= 4096)");
+    *p_out = p;
+    *smem_out = smem;
+    return MGB_OK;
+}
+
+int mgb_rows_rfft(int32_t m, int32_t n, const double *a_dev, int64_t lda, const double *a_row0_dev, const double *tw_dev,
+                  const double *chirp_dev, const double *bhat_dev, double *c_dev, int64_t ldc, void *stream) {
+    if (m < 0 || n < 1 || a_dev == nullptr || tw_dev == nullptr || chirp_dev == nullptr || bhat_dev == nullptr ||
+        c_dev == nullptr || lda < n || ldc < 2 * (n / 2 + 1) || (ldc & 1) || ((uintptr_t)c_dev & 15))
+        return heat2d_fail("rows_rfft: bad argument");
+    int p;
+    size_t smem;
+    if (int rc = fft_smem(n, &p, &smem)) return rc;
+    if (m == 0) return MGB_OK;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_rows_rfft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        configured = smem;
+    }
+    const DeviceInfo *di = device_info();
+    const int per_sm = (int)(di->max_smem_optin / smem) > 0 ? (int)(di->max_smem_optin / smem) : 1;
+    const int cap = di->sms * (per_sm > 2 ? 2 : per_sm);
+    k_rows_rfft<<<(m + 1) / 2 < cap ? (m + 1) / 2 : cap, kThreads, smem, (cudaStream_t)stream>>>(
+        m, n, p, a_dev, lda, a_row0_dev, (const double2 *)tw_dev, (const double2 *)chirp_dev, (const double2 *)bhat_dev, c_dev,
+        ldc, stop_flag());
+    return cuda_fail(cudaGetLastError(), "rows_rfft");
+}
+
+int mgb_rows_irfft(int32_t m, int32_t first_row, int32_t n, const double *c_dev, int64_t ldc, const double *tw_dev,
+                   const double *chirp_dev, const double *bhat_dev, double *out_dev, int64_t ldo, void *stream) {
+    if (m < 0 || first_row < 0 || n < 1 || c_dev == nullptr || tw_dev == nullptr || chirp_dev == nullptr ||
+        bhat_dev == nullptr || out_dev == nullptr || ldo < n || ldc < 2 * (n / 2 + 1) || (ldc & 1) || ((uintptr_t)c_dev & 15))
+        return heat2d_fail("rows_irfft: bad argument");
+    int p;
+    size_t smem;
+    if (int rc = fft_smem(n, &p, &smem)) return rc;
+    if (m <= first_row) return MGB_OK;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_rows_irfft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        configured = smem;
+    }
+    const DeviceInfo *di = device_info();
+    const int per_sm = (int)(di->max_smem_optin / smem) > 0 ? (int)(di->max_smem_optin / smem) : 1;
+    const int cap = di->sms * (per_sm > 2 ? 2 : per_sm);
+    const int work = (m - first_row + 1) / 2;
+    k_rows_irfft<<<work < cap ? work : cap, kThreads, smem, (cudaStream_t)stream>>>(
+        m, first_row, n, p, c_dev, ldc, (const double2 *)tw_dev, (const double2 *)chirp_dev, (const double2 *)bhat_dev, out_dev,
+        ldo, stop_flag());
+    return cuda_fail(cudaGetLastError(), "rows_irfft");
+}
+
+int mgb_advection1d_spectral_recur(int32_t n, int32_t npts, const double *t_dev, double c_over_dx, double *work_dev,
+                                   int64_t ldw, void *stream) {
+    if (n < 1 || npts < 1 || t_dev == nullptr || work_dev == nullptr || ldw < 2 * (n / 2 + 1) || (ldw & 1) ||
+        ((uintptr_t)work_dev & 15))
+        return heat2d_fail("advection1d_spectral_recur: bad argument");
+    if (device_info() == nullptr) return MGB_ECUDA;
+    if (npts < 2) return MGB_OK;
+    const int K = n / 2 + 1, steps = npts - 1;
+    int nch = steps / 8;  // at least 8 steps per chunk
+    if (nch > kMaxChunks) nch = kMaxChunks;
+    if (nch < 1) nch = 1;
+    const int len = (steps + nch - 1) / nch;
+    const dim3 grid((K + kFreqs - 1) / kFreqs), block(kFreqs, nch);
+    k_cplx_solve<<<grid, block, 0, (cudaStream_t)stream>>>((double2 *)work_dev, ldw / 2, n, K, npts, t_dev, c_over_dx, len,
+                                                           stop_flag());
+    return cuda_fail(cudaGetLastError(), "advection1d_spectral_recur");
+}
+
+}  // extern "C"

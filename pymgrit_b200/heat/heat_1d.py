@@ -248,7 +248,9 @@ class Heat1D(DeviceApplication):
     def _level_tables_sine(self, t, team_threads, chunk):
         torch = dl._torch()
         tab, dt_full = self.sine_host_tables(t, team_threads, chunk)
+        dl.mark('heat1d: dt classes, diag')
         shared = self._sine_device_tables(team_threads, chunk)
+        dl.mark('heat1d: shared device tables')
         split = self._rhs_split
         # the same tables in natural mode order for the one-thread-per-mode sweeps (csrc/sine_modes.cu)
         nat_host = tab.pop('nat')
@@ -262,7 +264,9 @@ class Heat1D(DeviceApplication):
             tab['nrhs'] = shared['nrhs']
             tab['rhs_x_dev'] = shared['rhs_x']
             out = dl.pinned_array((len(t), tab['nrhs'])) if len(t) >= (1 << 15) else None
+            dl.mark('heat1d: nat upload, pinned buffer')
             tab['rhs_t'] = split.coefficients(t, scale=dt_full, out=out)
+            dl.mark('heat1d: rhs time factors')
         return tab
 
     # ---- coarsest-level solve in sine space (csrc/spectral.cu) ---------------------------------------------------

@@ -242,7 +242,7 @@ class Heat2D(DeviceApplication):
         dt_full = np.zeros(len(t))
         dt_full[1:] = np.diff(t)
         tab = dict(ndt=len(dts), dtidx=dtidx, sconst=sconst, cw=8, nsys=fam.nsys, sig_dev=st['sig'],
-                   ip=[fam.first_boundary, 0, 0, 0])
+                   ip=[fam.first_boundary, 1 if th == 1 else 0, 0, 0])
 
         def in_time(vals):
             """dt_i (theta b(t_i) + (1 - theta) b(t_{i-1})) from b at every point of t (heat_2d.py:302, 309-313, 356)."""

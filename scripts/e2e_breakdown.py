@@ -48,8 +48,21 @@ for k in range(8):
     print('hierarchy %.1f ms | Mgrit() %.1f ms | solve() %.1f ms | readback %.1f ms | total %.1f ms' % (*ms, sum(ms)))
     print('    ' + ' | '.join('%s %.2f' % ph for ph in s.setup_phases))
     del s
+# finer marks of one more run (core/device_level.py mark())
+from pymgrit_b200.core import device_level as dl
+dl.TRACE = []
+t_begin = time.perf_counter()
+ms, s = run()
+marks, dl.TRACE = dl.TRACE, None
+prev = t_begin
+print('marks of one run (ms since the previous mark):')
+for label, tm in marks:
+    print('    %-36s %7.3f   (at %7.3f)' % (label, 1e3 * (tm - prev), 1e3 * (tm - t_begin)))
+    prev = tm
+del s
 pr = cProfile.Profile()
 pr.enable()
 run()
 pr.disable()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(60)
+pstats.Stats(pr).sort_stats('tottime').print_stats(40)

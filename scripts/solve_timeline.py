@@ -1,6 +1,6 @@
 """Device-time breakdown of one solve of the headline workload: CUDA events around every sweep, summed per (sweep, level).
 
-    python scripts/solve_timeline.py [cfg5|cfg2] [coarsening, e.g. 16,16,8]
+    python scripts/solve_timeline.py [cfg1..cfg5] [coarsening, e.g. 16,16,8]
 
 Also prints host-side wall time of restart()+solve() so the gap between the device busy time and the wall time
 (launch overhead, synchronisations in the convergence test) is visible.
@@ -31,7 +31,9 @@ nt, co = bench.workload_grid(wl)
 if len(sys.argv) > 2:
     co = tuple(int(x) for x in sys.argv[2].split(','))
 
-solver = P.Mgrit(problem=bench.hierarchy(P.Heat1D, nt, co), logging_lvl=logging.WARNING, **bench.SOLVER_KW)
+w = bench.WORKLOADS[wl]
+solver = P.Mgrit(problem=bench.build_levels(bench.app_class(P, w['app']), w['kw'], w['t'], co), logging_lvl=logging.WARNING,
+                 **w['solver'])
 for _ in range(2):
     solver.restart()
     solver.solve()

@@ -25,7 +25,7 @@ def test_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.mgb_abi_version() == _lib.ABI_VERSION == 9
+    assert lib.mgb_abi_version() == _lib.ABI_VERSION == 10
 
 
 def test_struct_layout_matches_header(lib):

@@ -1,0 +1,64 @@
+"""CPU: the algorithm of csrc/fourier.cu restated in numpy -- Bluestein's transform for rows of arbitrary length and the
+complex scalar recurrences per frequency -- against the oracle's chain of Advection1D steps (mgrit.py:459-486 with
+advection_1d.py:129-143).  Pins the sign conventions and the step factor 1 / (1 + nu (1 - exp(-i theta)))."""
+import numpy as np
+import pytest
+
+from oracle import mgrit_oracle as O
+
+
+def bluestein_tables(n):
+    m = 1
+    while m < 2 * n - 1:
+        m *= 2
+    j = np.arange(n)
+    chirp = np.exp(1j * np.pi * ((j * j) % (2 * n)) / n)          # m^2 reduced mod 2n in integers (k_tables)
+    b = np.zeros(m, complex)
+    b[:n] = chirp
+    b[m - np.arange(1, n)] = chirp[1:]
+    return m, chirp, np.fft.fft(b)
+
+
+def rfft_rows(x, n, m, chirp, bhat):
+    z = np.zeros((x.shape[0], m), complex)
+    z[:, :n] = x * np.conj(chirp)
+    conv = np.fft.ifft(np.fft.fft(z, axis=1) * bhat, axis=1)
+    k = n // 2 + 1
+    return np.conj(chirp[:k]) * conv[:, :k]
+
+
+def irfft_rows(xh, n, m, chirp, bhat):
+    k = n // 2 + 1
+    full = np.zeros((xh.shape[0], n), complex)
+    full[:, :k] = np.conj(xh)
+    hi = np.arange(k, n)
+    full[:, k:] = xh[:, n - hi]
+    z = np.zeros((xh.shape[0], m), complex)
+    z[:, :n] = full * np.conj(chirp)
+    conv = np.fft.ifft(np.fft.fft(z, axis=1) * bhat, axis=1)
+    return (np.conj(chirp) * conv[:, :n]).real / n
+
+
+@pytest.mark.parametrize('nx,uniform', [(16, True), (17, False), (130, True), (258, False)])
+def test_fourier_recurrences_reproduce_the_chain_of_advection_steps(nx, uniform):
+    npts = 40
+    t = np.linspace(0, 2, npts) if uniform else 2 * np.linspace(0, 1, npts) ** 1.4
+    app = O.Advection1DOracle(c=1, x_start=-1, x_end=1, nx=nx, t_interval=t)
+    n = app.n
+    rng = np.random.default_rng(nx)
+    g = rng.standard_normal((npts, n)) * 1e-2
+    u = np.zeros((npts, n))
+    u[0] = np.asarray(app.u0).reshape(-1)
+    for i in range(1, npts):
+        u[i] = g[i] + app.phi(u[i - 1], t[i - 1], t[i])
+    m, chirp, bhat = bluestein_tables(n)
+    w = rfft_rows(np.vstack([u[:1], g[1:]]), n, m, chirp, bhat)
+    assert np.allclose(w, np.fft.rfft(np.vstack([u[:1], g[1:]]), axis=1), rtol=0, atol=1e-12)
+    theta = 2 * np.pi * np.arange(n // 2 + 1) / n
+    cx, sx = 1 - np.cos(theta), np.sin(theta)
+    fac = app.c / app.dx
+    for i in range(1, npts):
+        nu = fac * (t[i] - t[i - 1])
+        w[i] = w[i] + w[i - 1] / ((1 + nu * cx) + 1j * nu * sx)
+    back = irfft_rows(w, n, m, chirp, bhat)
+    assert np.max(np.abs(back[1:] - u[1:])) <= 1e-12 * np.max(np.abs(u))

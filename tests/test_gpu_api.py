@@ -283,6 +283,83 @@ def test_spectral_coarse_solve_matches_phi_chain(P, variant):
     assert float(spectral[:, lv.n:].abs().max()) == 0.0           # the row padding stays zero
 
 
+@pytest.mark.parametrize('n', [1, 2, 3, 5, 16, 20, 33, 100, 300, 1000, 1500, 4095, 4096])
+def test_rows_rfft_matches_numpy(P, n):
+    """csrc/fourier.cu: the real Fourier transform of rows of any length n <= 4096 (Bluestein's algorithm on a radix-2 FFT
+    in shared memory) and its inverse, against numpy.fft: 1e-13 of the largest coefficient."""
+    import torch
+    from pymgrit_b200.advection.advection_1d import circ_fft_tables
+    lib = P._lib.lib()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    tw, chirp, bhat = circ_fft_tables(n, dev)
+    rows, k = 7 + (n & 1), n // 2 + 1                   # rows are transformed in pairs: an odd and an even count
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((rows, n + 3))
+    row0 = rng.standard_normal(n)
+    a_dev, row0_dev = torch.as_tensor(a).to(dev), torch.as_tensor(row0).to(dev)
+    c = torch.zeros((rows, 2 * k + 2), dtype=torch.float64, device=dev)
+    st = P._lib.current_stream_ptr()
+    P._lib.check(lib.mgb_rows_rfft(rows, n, a_dev.data_ptr(), n + 3, row0_dev.data_ptr(), tw.data_ptr(), chirp.data_ptr(),
+                                   bhat.data_ptr(), c.data_ptr(), 2 * k + 2, st), 'rows_rfft')
+    want = np.fft.rfft(np.vstack([row0[None], a[1:, :n]]), axis=1)
+    got = c.cpu().numpy()[:, :2 * k].reshape(rows, k, 2)
+    got = got[..., 0] + 1j * got[..., 1]
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want)) * max(1.0, np.log2(n + 1))
+    assert float(c[:, 2 * k:].abs().max()) == 0.0
+    out = torch.full((rows, n + 1), 7.0, dtype=torch.float64, device=dev)
+    P._lib.check(lib.mgb_rows_irfft(rows, 1, n, c.data_ptr(), 2 * k + 2, tw.data_ptr(), chirp.data_ptr(), bhat.data_ptr(),
+                                    out.data_ptr(), n + 1, st), 'rows_irfft')
+    back = out.cpu().numpy()
+    assert np.all(back[0] == 7.0) and np.all(back[:, n] == 7.0)          # row 0 and the padding are not touched
+    assert np.max(np.abs(back[1:, :n] - a[1:, :n])) <= 1e-13 * np.max(np.abs(a)) * max(1.0, np.log2(n + 1))
+
+
+@pytest.mark.parametrize('variant', ['uniform', 'nonuniform_t', 'nx4096', 'nx100_even'])
+def test_fourier_coarse_solve_matches_phi_chain(P, variant, monkeypatch):
+    """The coarsest-level solve of Advection1D in Fourier space (csrc/fourier.cu: real FFT of all rows, time-parallel
+    complex recurrences, inverse FFT) against the chain of cyclic bidiagonal Phi applications it replaces
+    (mgrit.py:459-486, advection_1d.py:129-143), on the same u[0] and FAS right-hand side g: 1e-12 relative."""
+    import logging
+    import torch
+    nx = {'nx4096': 4096, 'nx100_even': 101}.get(variant, 258)
+    nt = 1025 if variant != 'nx4096' else 385
+    t = np.linspace(0, 2, nt)
+    if variant == 'nonuniform_t':
+        t = 2 * np.linspace(0, 1, nt) ** 1.3
+    kw = dict(c=1, x_start=-1, x_end=1, nx=nx)
+    fine = P.Advection1D(t_interval=t, **kw)
+    coarse = P.Advection1D(t_interval=t[::2], **kw)
+    solver = P.Mgrit(problem=[fine, coarse], nested_iteration=False, logging_lvl=logging.WARNING)
+    assert type(solver._spectral.get(1)).__name__ == 'FourierSolve'
+    lv = solver._lv[1]
+    gen = torch.Generator(device='cuda').manual_seed(11)
+    lv.g[:, :lv.n] = torch.randn((lv.npts, lv.n), generator=gen, device='cuda', dtype=torch.float64) * 1e-2
+    solver.forward_solve(1)
+    spectral = lv.u.clone()
+    sp = solver._spectral.pop(1)
+    lv.u[1:].zero_()
+    solver.forward_solve(1)
+    chain = lv.u.clone()
+    solver._spectral[1] = sp
+    assert float(chain[1:].abs().max()) > 1e-3
+    assert torch.equal(spectral[0], chain[0])                            # the start value is not rewritten
+    assert float((spectral - chain)[:, :lv.n].abs().max()) <= 1e-12 * float(chain[:, :lv.n].abs().max())
+    if lv.pitch > lv.n:
+        assert float(spectral[:, lv.n:].abs().max()) == 0.0              # the row padding stays zero
+    # and the whole solve: same iteration count and history with and without it
+    info_f = solver.solve()
+    monkeypatch.setenv('MGB_ADVECTION_FOURIER', '0')
+    plain = P.Mgrit(problem=[P.Advection1D(t_interval=t, **kw), P.Advection1D(t_interval=t[::2], **kw)],
+                    nested_iteration=False, logging_lvl=logging.WARNING)
+    assert not plain._spectral
+    info_c = plain.solve()
+    assert len(info_f['conv']) == len(info_c['conv'])
+    assert np.allclose(info_f['conv'], info_c['conv'], rtol=1e-6, atol=1e-13)
+    n0 = solver._lv[0].n
+    uf, uc = solver._lv[0].u[:, :n0], plain._lv[0].u[:, :n0]
+    assert float((uf - uc).abs().max()) <= 1e-11 * float(uc.abs().max())
+
+
 @pytest.mark.parametrize('variant', ['uniform', 'nonuniform_t', 'zero_rhs', 'rank2_rhs', 'nx1001_product', 'short'])
 def test_sine_level_solve_matches_phi_chain(P, variant):
     """A level kept in sine space: the time-parallel scalar recurrences of mgb_sine_level_solve against (a) the chain of
@@ -506,4 +583,22 @@ def test_one_thread_per_mode_sweeps_are_bit_identical_to_the_team_kernels(P, nam
     team, info_t = run_b200(name)
     assert len(info_m['conv']) == len(info_t['conv'])
     assert np.allclose(info_m['conv'], info_t['conv'], rtol=1e-12, atol=0)
+    assert np.array_equal(solution_rows(modes)[0], solution_rows(team)[0])
+
+
+@pytest.mark.parametrize('name', ['heat2d_example', 'heat2d_cfg3_small', 'heat2d_bc', 'heat2d_cn', 'heat2d_cn_3lvl',
+                                  'heat2d_fe'])
+def test_heat2d_one_thread_per_mode_sweeps_are_bit_identical_to_the_team_kernels(P, name, monkeypatch):
+    """Heat2D rows always hold sine coefficients, so the hot sweeps run as one thread per coefficient too
+    (csrc/sine_modes.cu TilePhi: backward Euler on uniform levels, and the general theta / several-step-size variant);
+    same operations per element as the tile teams of csrc/sweeps.cuh, Dirichlet tiles included."""
+    from b200_util import run_b200, solution_rows
+    if name not in C.CASES:
+        pytest.skip('case not defined')
+    monkeypatch.setenv('MGB_SINE_MODES', '1')
+    modes, info_m = run_b200(name)
+    monkeypatch.setenv('MGB_SINE_MODES', '0')
+    team, info_t = run_b200(name)
+    assert len(info_m['conv']) == len(info_t['conv'])
+    assert np.allclose(info_m['conv'], info_t['conv'], rtol=1e-10, atol=1e-300)
     assert np.array_equal(solution_rows(modes)[0], solution_rows(team)[0])

@@ -126,6 +126,46 @@ def test_cfg4_advection_full_size(P):
         assert abs(np.sqrt(sq[k]) - np.linalg.norm(r)) <= 1e-10 * np.linalg.norm(pair[1])
 
 
+def test_cfg4_advection_two_level_to_tolerance(P):
+    """configs[3] as bench.py runs it: two levels, coarsening 2, the coarsest level (32769 points) solved time-parallel in
+    Fourier space (csrc/fourier.cu).  To the tolerance 1e-10 (4 V-cycles), then: every F-point is Phi of its predecessor,
+    the C-point defects are what the solver reports, the first k*m points are the time-stepping solution, and the same
+    run with the chain of dependent solves on the coarsest level (MGB_ADVECTION_FOURIER=0) gives the same history."""
+    import os
+    from oracle import mgrit_oracle as O
+    kw = dict(c=1, x_start=-1, x_end=1, nx=4096)
+    t0 = np.linspace(0, 2, 65537)
+    out = {}
+    for mode in ('1', '0'):
+        os.environ['MGB_ADVECTION_FOURIER'] = mode
+        try:
+            solver = P.Mgrit(problem=_hierarchy(lambda t: P.Advection1D(t_interval=t, **kw), t0, [2]),
+                             logging_lvl=logging.WARNING, tol=1e-10, cf_iter=1, nested_iteration=True, max_iter=20)
+            assert bool(solver._spectral) == (mode == '1')
+            out[mode] = (solver, solver.solve())
+        finally:
+            os.environ.pop('MGB_ADVECTION_FOURIER', None)
+    solver, info = out['1']
+    conv = info['conv']
+    assert len(conv) == 4 and conv[-1] < 1e-10 and np.all(conv[1:] < conv[:-1]), conv
+    conv_chain = out['0'][1]['conv']
+    assert len(conv_chain) == len(conv)
+    assert np.max(np.abs(conv_chain - conv)) <= 1e-10 * max(conv[0], 1.0), (conv, conv_chain)
+    orc = O.Advection1DOracle(solver='c', t_interval=t0, **kw)
+    rng = np.random.default_rng(5)
+    sample = sorted(set(int(i) for i in rng.integers(1, len(t0), 24)) | {1, 2, len(t0) - 1})
+    _check_fixed_point(solver, orc, info, sample)
+    npre = len(conv) * 2 + 1
+    got = _rows(solver, np.arange(npre))
+    u = orc.u0.copy()
+    for i in range(1, npre):
+        u = orc.phi(u, t0[i - 1], t0[i])
+        assert np.max(np.abs(got[i] - u)) <= 1e-10 * np.max(np.abs(u)), i
+    # both runs agree at sampled points to the accuracy of the iteration
+    a, b = _rows(solver, sample), _rows(out['0'][0], sample)
+    assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))
+
+
 def test_cfg3_heat2d_full_size(P):
     """configs[2]: heat_2d backward Euler 512 x 512, nt=4097 on [0, 5], 4-level F-cycle, coarsening 8."""
     from oracle import mgrit_oracle as O
