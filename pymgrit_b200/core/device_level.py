@@ -32,6 +32,8 @@ class _PinnedArray(np.ndarray):
 
 
 _PINNED_POOL = {}         # bytes -> list of [page-locked tensor, CUDA event of the last upload from it or None]
+import threading
+_POOL_LOCK = threading.Lock()   # level 0's host tables are made on a helper thread (DeviceLevel.start_host_tables)
 
 
 def pinned_array(shape):
@@ -44,18 +46,19 @@ def pinned_array(shape):
     shape = tuple(int(v) for v in shape)
     nbytes = 8 * int(np.prod(shape)) if shape else 8
     ten = None
-    for ent in _PINNED_POOL.setdefault(nbytes, []):
-        if sys.getrefcount(ent[0]) <= 2:                # only the pool (and this call) hold it: its array was dropped
-            if ent[1] is not None:
-                ent[1].synchronize()
-                ent[1] = None
-            ten, slot = ent[0], ent
-            break
-    if ten is None:
-        ten = torch.empty((nbytes // 8,), dtype=torch.float64, pin_memory=True)
-        slot = [ten, None]
-        if len(_PINNED_POOL[nbytes]) < 4:
-            _PINNED_POOL[nbytes].append(slot)
+    with _POOL_LOCK:
+        for ent in _PINNED_POOL.setdefault(nbytes, []):
+            if sys.getrefcount(ent[0]) <= 2:            # only the pool (and this call) hold it: its array was dropped
+                if ent[1] is not None:
+                    ent[1].synchronize()
+                    ent[1] = None
+                ten, slot = ent[0], ent
+                break
+        if ten is None:
+            ten = torch.empty((nbytes // 8,), dtype=torch.float64, pin_memory=True)
+            slot = [ten, None]
+            if len(_PINNED_POOL[nbytes]) < 4:
+                _PINNED_POOL[nbytes].append(slot)
     view = ten.view(shape) if shape else ten
     arr = view.numpy().view(_PinnedArray)
     arr._owner = view
@@ -137,8 +140,32 @@ class DeviceLevel:
         self.h2d_bytes = 0
         self.nsys = 1
         self.c = None
+        self._host_job = None
         if not defer_tables:
             self.finish_tables()
+
+    def start_host_tables(self):
+        """Deferred tables of a long level whose application splits them into a host part (NumPy on the table threads,
+        into page-locked memory) and a device part: the host part starts now on a helper thread, so that it runs while
+        the constructor of the solver allocates the other levels, builds their tables and queues nested iteration;
+        finish_tables() waits for it.  Nothing changes in what is computed."""
+        import os
+        fn = getattr(self.app, 'level_tables_host', None)
+        if (fn is None or self.c is not None or self.batched or self._host_job is not None or self.npts < _PAR_MIN
+                or os.environ.get('MGB_TABLES_AHEAD', '1') == '0'):
+            return
+        torch = _torch()
+        dev, box = self.u.device, {}
+
+        def work():
+            try:
+                with torch.cuda.device(dev):            # page-locked buffers belong to this rank's device context
+                    box['host'] = fn(self.t, self.team_threads, self.chunk)
+            except BaseException as exc:                # re-raised by finish_tables() on the constructor's thread
+                box['error'] = exc
+        th = threading.Thread(target=work, name='mgb-level-tables', daemon=True)
+        th.start()
+        self._host_job = (th, box)
 
     def finish_tables(self):
         if self.c is not None or self.batched:
@@ -147,7 +174,16 @@ class DeviceLevel:
         app, dev = self.app, self.u.device
         tiny = app.kind in (_lib.APP_DAHLQUIST, _lib.APP_BRUSSELATOR)
         mark('tables: begin')
-        tab = app.level_tables(self.t, self.team_threads, self.chunk)
+        if self._host_job is not None:
+            th, box = self._host_job
+            self._host_job = None
+            th.join()
+            mark('tables: waited for the helper thread')
+            if 'error' in box:
+                raise box['error']
+            tab = app.level_tables_finish(box['host'], self.team_threads, self.chunk)
+        else:
+            tab = app.level_tables(self.t, self.team_threads, self.chunk)
         mark('tables: host tables made')
 
         def up(a, dtype):

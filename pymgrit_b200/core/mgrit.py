@@ -230,6 +230,8 @@ class Mgrit:
             self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0, defer_tables=defer,
                                         zero_u=not (defer and max_iter > 0 and not (callable(output_fcn) and
                                                                                     output_lvl == 2))))
+            if defer:
+                self._lv[0].start_host_tables()      # the long host tables of level 0 are made while the rest is set up
         self._f_uninit = self.lvl_max > 1 and not self._lv[0].zero_filled
         phase('level arrays + coarse-level tables')
         # levels whose down-sweep runs as one fused launch (mgb_down_sweep): unweighted C-relaxation, at least one

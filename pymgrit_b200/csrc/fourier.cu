@@ -12,10 +12,11 @@
 //
 // n is arbitrary (nx = 4096 -> n = 4095 = 3^2 5 7 13), so the transform is Bluestein's: j k = (j^2 + k^2 - (k-j)^2) / 2,
 //     X_k = conj(w_k) sum_j (x_j conj(w_j)) w_{k-j},      w_m = exp(i pi m^2 / n)      (m^2 reduced mod 2n in integers)
-// a cyclic convolution of length M = 2^p >= 2n - 1 done with a radix-2 FFT in shared memory: one CTA per row, M complex
-// doubles (128 KB for n <= 4096), decimation in frequency forwards (natural in, bit-reversed out), the chirp's spectrum
-// stored in that same bit-reversed order, decimation in time backwards (bit-reversed in, natural out).  Rows are real, so
-// only k = 0 .. n/2 are kept: [npts][2 (n/2 + 1)] doubles (re, im).
+// a cyclic convolution of length M = 2^p >= 2n - 1 done with a fast Fourier transform in shared memory: one CTA per PAIR of
+// rows (two real rows are the real and imaginary part of one complex transform), M complex doubles (136 KB with padding
+// for n <= 4096), decimation in frequency forwards (natural in, bit-reversed out), the chirp's spectrum stored in that
+// same bit-reversed order, decimation in time backwards (bit-reversed in, natural out), radix-8 / radix-16 passes in
+// registers.  Rows are real, so only k = 0 .. n/2 are kept: [npts][2 (n/2 + 1)] doubles (re, im).
 #include "../../include/mgrit_b200.h"
 #include "phi.cuh"
 #include "table.h"
@@ -59,14 +60,40 @@ __global__ void k_tables(int n, int M, double2 *__restrict__ tw, double2 *__rest
     }
 }
 
-// Radix-2 decimation-in-frequency stages s_top, s_top-1, .., s_top-RL+1 of the in-place transform (natural order in,
-// bit-reversed order out) in ONE pass over shared memory: a thread takes the 2^RL elements hi 2^(s_top+1) + a 2^q + lo
-// (q = s_top-RL+1) into registers and runs the RL stages there.  Radix 8 moves the row through shared memory 5 times
-// instead of 13 (the passes are bound by shared-memory bandwidth, not by the FP64 pipe).  mul != nullptr: the results are
-// multiplied by mul[index] on the way out (the chirp's spectrum, stored in the same bit-reversed order).
-template <int RL>
+// ---- the transform of one row in shared memory ------------------------------------------------------------------------
+// The radix-2 flow graph (decimation in frequency forwards: natural order in, bit-reversed out; its mirror image
+// backwards) is walked in PASSES of RL = 3 or 4 consecutive stages: a thread takes the 2^RL elements
+// hi 2^(s_top+1) + a 2^q + lo (q = s_top-RL+1) into registers and runs the RL stages there, so a row of 8192 points
+// crosses shared memory 4 times per direction instead of 13.  The passes are bound by the shared-memory pipe (ncu:
+// l1tex 85 %, FP64 pipe 15 %, profiles/r02s_fourier_ncu.txt), hence:
+//   * one twiddle load per stage and group, W^(lo); the other twiddles of the stage differ from it by a fixed 16th root
+//     of unity (W^(a' 2^q + lo) = W^lo exp(-i pi a' / ha)), applied in registers;
+//   * element i lives at z[i + i/16]: the 16 elements a thread owns in the last pass (stride 1) and the rows of 16 that a
+//     quarter warp touches fall into different banks;
+//   * the first forward pass reads its input straight from global memory (the caller's functor), the last forward pass
+//     multiplies by the chirp's spectrum on the way out.
+__device__ __forceinline__ int pad(const int i) { return i + (i >> 4); }
+
+// w * exp(-i pi k / 8), k = 0 .. 7 (k is a compile-time constant after unrolling)
+__device__ __forceinline__ double2 rot16(const double2 w, const int k) {
+    constexpr double c1 = 0.92387953251128673848, s1 = 0.38268343236508978178, h = 0.70710678118654752440;
+    switch (k) {
+        case 0: return w;
+        case 1: return cmul(w, make_double2(c1, -s1));
+        case 2: return cmul(w, make_double2(h, -h));
+        case 3: return cmul(w, make_double2(s1, -c1));
+        case 4: return make_double2(w.y, -w.x);
+        case 5: return cmul(w, make_double2(-s1, -c1));
+        case 6: return cmul(w, make_double2(-h, -h));
+        default: return cmul(w, make_double2(-c1, -s1));
+    }
+}
+
+// stages s_top .. s_top-RL+1 forwards.  src(i): element i of the input (shared memory, or the caller's global data for the
+// first pass); mul != nullptr: the results are multiplied by mul[i] on the way out (last pass).
+template <int RL, class Src>
 __device__ __forceinline__ void dif_pass(double2 *z, const int log2m, const int s_top, const double2 *__restrict__ tw,
-                                         const double2 *__restrict__ mul) {
+                                         const double2 *__restrict__ mul, Src src) {
     constexpr int RN = 1 << RL;
     const int q = s_top - RL + 1, H = 1 << (log2m - 1), groups = 1 << (log2m - RL);
     for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
@@ -74,15 +101,17 @@ __device__ __forceinline__ void dif_pass(double2 *z, const int log2m, const int 
         const int base = (hi << (s_top + 1)) + lo;
         double2 v[RN];
 #pragma unroll
-        for (int a = 0; a < RN; ++a) v[a] = z[base + (a << q)];
+        for (int a = 0; a < RN; ++a) v[a] = src(base + (a << q));
 #pragma unroll
         for (int j = 0; j < RL; ++j) {
-            const int s = s_top - j, ha = 1 << (RL - 1 - j);     // pairs (a, a + ha), a with that bit clear
+            const int s = s_top - j;
+            constexpr int kOne = 1;
+            const int ha = kOne << (RL - 1 - j);                 // pairs (a, a + ha), a with that bit clear
+            const double2 ws = __ldg(tw + lo * (H >> s));        // W_(2^(s+1))^lo
 #pragma unroll
             for (int a = 0; a < RN; ++a) {
                 if (a & ha) continue;
-                const int pos = ((a & (ha - 1)) << q) + lo;
-                const double2 w = __ldg(tw + pos * (H >> s));
+                const double2 w = rot16(ws, (a & (ha - 1)) * (8 / ha));
                 const double2 x = v[a], y = v[a + ha];
                 v[a] = make_double2(x.x + y.x, x.y + y.y);
                 v[a + ha] = cmul(make_double2(x.x - y.x, x.y - y.y), w);
@@ -91,12 +120,12 @@ __device__ __forceinline__ void dif_pass(double2 *z, const int log2m, const int 
 #pragma unroll
         for (int a = 0; a < RN; ++a) {
             const int idx = base + (a << q);
-            z[idx] = mul ? cmul(v[a], __ldg(mul + idx)) : v[a];
+            z[pad(idx)] = mul ? cmul(v[a], __ldg(mul + idx)) : v[a];
         }
     }
     __syncthreads();
 }
-// the inverse flow graph, stages q .. q+RL-1 ascending (bit-reversed order in, natural order out, not scaled)
+// the mirror image: stages q .. q+RL-1 ascending, conjugate twiddles, not scaled
 template <int RL>
 __device__ __forceinline__ void dit_pass(double2 *z, const int log2m, const int q, const double2 *__restrict__ tw) {
     constexpr int RN = 1 << RL;
@@ -106,73 +135,96 @@ __device__ __forceinline__ void dit_pass(double2 *z, const int log2m, const int 
         const int base = (hi << (s_top + 1)) + lo;
         double2 v[RN];
 #pragma unroll
-        for (int a = 0; a < RN; ++a) v[a] = z[base + (a << q)];
+        for (int a = 0; a < RN; ++a) v[a] = z[pad(base + (a << q))];
 #pragma unroll
         for (int j = RL - 1; j >= 0; --j) {
-            const int s = s_top - j, ha = 1 << (RL - 1 - j);
+            const int s = s_top - j;
+            constexpr int kOne = 1;
+            const int ha = kOne << (RL - 1 - j);
+            const double2 ws = __ldg(tw + lo * (H >> s));
 #pragma unroll
             for (int a = 0; a < RN; ++a) {
                 if (a & ha) continue;
-                const int pos = ((a & (ha - 1)) << q) + lo;
+                const double2 w = rot16(ws, (a & (ha - 1)) * (8 / ha));
                 const double2 x = v[a];
-                const double2 y = cmulc(v[a + ha], __ldg(tw + pos * (H >> s)));
+                const double2 y = cmulc(v[a + ha], w);
                 v[a] = make_double2(x.x + y.x, x.y + y.y);
                 v[a + ha] = make_double2(x.x - y.x, x.y - y.y);
             }
         }
 #pragma unroll
-        for (int a = 0; a < RN; ++a) z[base + (a << q)] = v[a];
+        for (int a = 0; a < RN; ++a) z[pad(base + (a << q))] = v[a];
     }
     __syncthreads();
 }
-// in place, natural order in, bit-reversed order out (times mul on the way out of the last pass)
-__device__ __forceinline__ void fft_dif(double2 *z, const int log2m, const double2 *__restrict__ tw,
-                                        const double2 *__restrict__ mul) {
+
+// passes of the forward transform from the top stage down: sizes rl[], top stages top[]
+struct Plan {
+    int count;
+    int rl[6], top[6];
+};
+__device__ __forceinline__ Plan make_plan(const int log2m) {
+    Plan p;
+    p.count = 0;
     int s = log2m - 1;
-    for (; s >= 5; s -= 3) dif_pass<3>(z, log2m, s, tw, nullptr);   // at least 3 stages remain after each of these
-    // s + 1 in {3, 4, 5} stages left (or fewer for short rows)
+    while (s + 1 > 5) {
+        p.rl[p.count] = 3;
+        p.top[p.count++] = s;
+        s -= 3;
+    }
     if (s + 1 == 5) {
-        dif_pass<3>(z, log2m, s, tw, nullptr);
-        dif_pass<2>(z, log2m, s - 3, tw, mul);
-    } else if (s + 1 == 4) {
-        dif_pass<2>(z, log2m, s, tw, nullptr);
-        dif_pass<2>(z, log2m, s - 2, tw, mul);
-    } else if (s + 1 == 3) {
-        dif_pass<3>(z, log2m, s, tw, mul);
-    } else if (s + 1 == 2) {
-        dif_pass<2>(z, log2m, s, tw, mul);
-    } else {
-        dif_pass<1>(z, log2m, s, tw, mul);
+        p.rl[p.count] = 3;
+        p.top[p.count++] = s;
+        s -= 3;
+    }
+    p.rl[p.count] = s + 1;   // 1 .. 4 stages left
+    p.top[p.count++] = s;
+    return p;
+}
+
+template <class Src>
+__device__ __forceinline__ void run_dif(double2 *z, const int log2m, const int rl, const int s_top,
+                                        const double2 *__restrict__ tw, const double2 *__restrict__ mul, Src src) {
+    switch (rl) {
+        case 1: dif_pass<1>(z, log2m, s_top, tw, mul, src); break;
+        case 2: dif_pass<2>(z, log2m, s_top, tw, mul, src); break;
+        case 3: dif_pass<3>(z, log2m, s_top, tw, mul, src); break;
+        default: dif_pass<4>(z, log2m, s_top, tw, mul, src); break;
+    }
+}
+__device__ __forceinline__ void run_dit(double2 *z, const int log2m, const int rl, const int q, const double2 *__restrict__ tw) {
+    switch (rl) {
+        case 1: dit_pass<1>(z, log2m, q, tw); break;
+        case 2: dit_pass<2>(z, log2m, q, tw); break;
+        case 3: dit_pass<3>(z, log2m, q, tw); break;
+        default: dit_pass<4>(z, log2m, q, tw); break;
+    }
+}
+
+// z <- transform of the input `first(i)` (natural order in, bit-reversed out), times mul on the way out if not null
+template <class Src>
+__device__ __forceinline__ void fft_dif(double2 *z, const int log2m, const double2 *__restrict__ tw,
+                                        const double2 *__restrict__ mul, Src first) {
+    const Plan p = make_plan(log2m);
+    auto smem = [z](const int i) { return z[pad(i)]; };
+    for (int k = 0; k < p.count; ++k) {
+        const double2 *m = (k == p.count - 1) ? mul : nullptr;
+        if (k == 0)
+            run_dif(z, log2m, p.rl[0], p.top[0], tw, m, first);
+        else
+            run_dif(z, log2m, p.rl[k], p.top[k], tw, m, smem);
     }
 }
 // the inverse flow graph: bit-reversed order in, natural order out, not scaled (divide by M)
 __device__ __forceinline__ void ifft_dit(double2 *z, const int log2m, const double2 *__restrict__ tw) {
-    const int rem = log2m % 3 == 0 ? 3 : (log2m % 3 == 1 ? (log2m >= 4 ? 4 : 1) : (log2m >= 5 ? 5 : 2));
-    int q = 0;
-    if (rem == 5) {
-        dit_pass<2>(z, log2m, 0, tw);
-        dit_pass<3>(z, log2m, 2, tw);
-        q = 5;
-    } else if (rem == 4) {
-        dit_pass<2>(z, log2m, 0, tw);
-        dit_pass<2>(z, log2m, 2, tw);
-        q = 4;
-    } else if (rem == 3) {
-        dit_pass<3>(z, log2m, 0, tw);
-        q = 3;
-    } else if (rem == 2) {
-        dit_pass<2>(z, log2m, 0, tw);
-        q = 2;
-    } else {
-        dit_pass<1>(z, log2m, 0, tw);
-        q = 1;
-    }
-    for (; q < log2m; q += 3) dit_pass<3>(z, log2m, q, tw);
+    const Plan p = make_plan(log2m);
+    for (int k = p.count - 1; k >= 0; --k) run_dit(z, log2m, p.rl[k], p.top[k] - p.rl[k] + 1, tw);
 }
-// z <- cyclic convolution of z with the chirp (times M)
+// z <- cyclic convolution of the input with the chirp (times M)
+template <class Src>
 __device__ __forceinline__ void chirp_conv(double2 *z, const int log2m, const double2 *__restrict__ tw,
-                                           const double2 *__restrict__ bhat) {
-    fft_dif(z, log2m, tw, bhat);
+                                           const double2 *__restrict__ bhat, Src first) {
+    fft_dif(z, log2m, tw, bhat, first);
     ifft_dit(z, log2m, tw);
 }
 
@@ -180,10 +232,8 @@ __global__ void __launch_bounds__(kThreads) k_bhat(const int log2m, const double
                                                    const double2 *__restrict__ b, double2 *__restrict__ bhat) {
     extern __shared__ double2 z[];
     const int M = 1 << log2m;
-    for (int p = threadIdx.x; p < M; p += blockDim.x) z[p] = b[p];
-    __syncthreads();
-    fft_dif(z, log2m, tw, nullptr);
-    for (int p = threadIdx.x; p < M; p += blockDim.x) bhat[p] = z[p];
+    fft_dif(z, log2m, tw, nullptr, [b](const int i) { return b[i]; });
+    for (int p = threadIdx.x; p < M; p += blockDim.x) bhat[p] = z[pad(p)];
 }
 
 // Rows are real: two of them share one complex transform, Z = F(x_a + i x_b), X_a[k] = (Z_k + conj(Z_{n-k})) / 2,
@@ -202,18 +252,15 @@ __global__ void __launch_bounds__(kThreads) k_rows_rfft(const int rows, const in
         const int ra = 2 * pr, rb = ra + 1;
         const double *xa = (ra == 0 && a_row0 != nullptr) ? a_row0 : A + (long)ra * lda;
         const double *xb = rb < rows ? A + (long)rb * lda : nullptr;
-        for (int j = threadIdx.x; j < M; j += blockDim.x) {
-            double2 v = make_double2(0.0, 0.0);
-            if (j < n) v = cmulc(make_double2(xa[j], xb ? xb[j] : 0.0), __ldg(chirp + j));
-            z[j] = v;
-        }
-        __syncthreads();
-        chirp_conv(z, log2m, tw, bhat);
+        chirp_conv(z, log2m, tw, bhat, [=](const int j) {
+            if (j >= n) return make_double2(0.0, 0.0);
+            return cmulc(make_double2(xa[j], xb ? xb[j] : 0.0), __ldg(chirp + j));
+        });
         double2 *oa = reinterpret_cast<double2 *>(Cm + (long)ra * ldc);
         double2 *ob = xb ? reinterpret_cast<double2 *>(Cm + (long)rb * ldc) : nullptr;
         for (int k = threadIdx.x; k < K; k += blockDim.x) {
             const int km = (k == 0) ? 0 : n - k;
-            const double2 zk = cmulc(z[k], __ldg(chirp + k)), zm = cmulc(z[km], __ldg(chirp + km));
+            const double2 zk = cmulc(z[pad(k)], __ldg(chirp + k)), zm = cmulc(z[pad(km)], __ldg(chirp + km));
             // (Z_k + conj(Z_m)) / 2  and  (Z_k - conj(Z_m)) / (2i) = (Im(Z_k) + Im(Z_m), Re(Z_m) - Re(Z_k)) / 2
             oa[k] = make_double2((zk.x + zm.x) * scale, (zk.y - zm.y) * scale);
             if (ob) ob[k] = make_double2((zk.y + zm.y) * scale, (zm.x - zk.x) * scale);
@@ -237,28 +284,23 @@ __global__ void __launch_bounds__(kThreads) k_rows_irfft(const int rows, const i
         const int ra = first_row + 2 * pr, rb = ra + 1;
         const double2 *Xa = reinterpret_cast<const double2 *>(Cm + (long)ra * ldc);
         const double2 *Xb = rb < rows ? reinterpret_cast<const double2 *>(Cm + (long)rb * ldc) : nullptr;
-        for (int k = threadIdx.x; k < M; k += blockDim.x) {
-            double2 v = make_double2(0.0, 0.0);
-            if (k < n) {
-                // Hermitian extension: X[k] for k <= n/2, conj(X[n-k]) above
-                const bool up = k >= K;
-                const int kk = up ? n - k : k;
-                double2 a = Xa[kk], b = Xb ? Xb[kk] : make_double2(0.0, 0.0);
-                if (up) {
-                    a.y = -a.y;
-                    b.y = -b.y;
-                }
-                // conj(Y) = conj(a + i b) = (a.x - b.y) - i (a.y + b.x)
-                v = cmulc(make_double2(a.x - b.y, -(a.y + b.x)), __ldg(chirp + k));
+        chirp_conv(z, log2m, tw, bhat, [=](const int k) {
+            if (k >= n) return make_double2(0.0, 0.0);
+            // Hermitian extension: X[k] for k <= n/2, conj(X[n-k]) above
+            const bool up = k >= K;
+            const int kk = up ? n - k : k;
+            double2 a = Xa[kk], b = Xb ? Xb[kk] : make_double2(0.0, 0.0);
+            if (up) {
+                a.y = -a.y;
+                b.y = -b.y;
             }
-            z[k] = v;
-        }
-        __syncthreads();
-        chirp_conv(z, log2m, tw, bhat);
+            // conj(Y) = conj(a + i b) = (a.x - b.y) - i (a.y + b.x)
+            return cmulc(make_double2(a.x - b.y, -(a.y + b.x)), __ldg(chirp + k));
+        });
         double *oa = out + (long)ra * ldo;
         double *ob = Xb ? out + (long)rb * ldo : nullptr;
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            const double2 f = cmulc(z[j], __ldg(chirp + j));     // F(conj(Y))_j times M
+            const double2 f = cmulc(z[pad(j)], __ldg(chirp + j));     // F(conj(Y))_j times M
             oa[j] = f.x * scale;
             if (ob) ob[j] = -f.y * scale;
         }
@@ -374,7 +416,7 @@ int mgb_circ_fft_tables(int32_t n, double *tw_dev, double *chirp_dev, double *bh
     const DeviceInfo *di = device_info();
     if (di == nullptr) return MGB_ECUDA;
     const int p = log2_conv_len(n), M = 1 << p;
-    const size_t smem = (size_t)M * sizeof(double2);
+    const size_t smem = (size_t)(M + M / 16 + 1) * sizeof(double2);
     if ((int)smem > di->max_smem_optin) return heat2d_fail("circ_fft_tables: row too long for shared memory (n <= 4096)");
     cudaStream_t st = (cudaStream_t)stream;
     k_tables<<<(M + 255) / 256, 256, 0, st>>>(n, M, (double2 *)tw_dev, (double2 *)chirp_dev, (double2 *)work_dev);
@@ -388,7 +430,7 @@ static int fft_smem(int n, int *p_out, size_t *smem_out) {
     const DeviceInfo *di = device_info();
     if (di == nullptr) return MGB_ECUDA;
     const int p = log2_conv_len(n);
-    const size_t smem = ((size_t)1 << p) * sizeof(double2);
+    const size_t smem = (((size_t)1 << p) + ((size_t)1 << p) / 16 + 1) * sizeof(double2);   // element i at z[i + i/16]
     if ((int)smem > di->max_smem_optin) return heat2d_fail("rows_rfft: row too long for shared memory (n <= 4096)");
     *p_out = p;
     *smem_out = smem;

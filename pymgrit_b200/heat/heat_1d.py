@@ -226,6 +226,9 @@ class Heat1D(DeviceApplication):
     def level_tables(self, t, team_threads, chunk):
         if self._in_sine:
             return self._level_tables_sine(t, team_threads, chunk)
+        return self._level_tables_node(t, team_threads, chunk)
+
+    def _level_tables_node(self, t, team_threads, chunk):
         fac = self.a / self.dx ** 2                                   # heat_1d.py:185
         t = np.asarray(t, dtype=float)
         dt_full, dt_lo, dt_hi = dl.time_steps(t)
@@ -245,13 +248,28 @@ class Heat1D(DeviceApplication):
             tab['rhs_dense'] = split.dense(t) * dt_full[:, None]
         return tab
 
-    def _level_tables_sine(self, t, team_threads, chunk):
-        torch = dl._torch()
+    def level_tables_host(self, t, team_threads, chunk):
+        """The part of level_tables() that needs no device: step classes, eigenvalue tables, the time factors of the
+        right-hand side (into page-locked memory on long grids).  DeviceLevel.start_host_tables runs it on a helper
+        thread for level 0; level_tables_finish() adds the device tables."""
+        if not self._in_sine:
+            return dict(node=self._level_tables_node(t, team_threads, chunk))
         tab, dt_full = self.sine_host_tables(t, team_threads, chunk)
         dl.mark('heat1d: dt classes, diag')
+        split = self._rhs_split
+        if split.kind == 'separable':
+            out = dl.pinned_array((len(t), split.basis.shape[0])) if len(t) >= (1 << 15) else None
+            tab['rhs_t'] = split.coefficients(t, scale=dt_full, out=out)
+            dl.mark('heat1d: rhs time factors')
+        return dict(sine=tab)
+
+    def level_tables_finish(self, host, team_threads, chunk):
+        if 'node' in host:
+            return host['node']
+        torch = dl._torch()
+        tab = host['sine']
         shared = self._sine_device_tables(team_threads, chunk)
         dl.mark('heat1d: shared device tables')
-        split = self._rhs_split
         # the same tables in natural mode order for the one-thread-per-mode sweeps (csrc/sine_modes.cu)
         nat_host = tab.pop('nat')
         q = shared['nrhs']
@@ -260,14 +278,14 @@ class Heat1D(DeviceApplication):
         if q:
             nat[2:].copy_(shared['rxh'])
         tab['nat_dev'] = nat
-        if split.kind == 'separable':
+        if self._rhs_split.kind == 'separable':
             tab['nrhs'] = shared['nrhs']
             tab['rhs_x_dev'] = shared['rhs_x']
-            out = dl.pinned_array((len(t), tab['nrhs'])) if len(t) >= (1 << 15) else None
-            dl.mark('heat1d: nat upload, pinned buffer')
-            tab['rhs_t'] = split.coefficients(t, scale=dt_full, out=out)
-            dl.mark('heat1d: rhs time factors')
+        dl.mark('heat1d: nat upload')
         return tab
+
+    def _level_tables_sine(self, t, team_threads, chunk):
+        return self.level_tables_finish(self.level_tables_host(t, team_threads, chunk), team_threads, chunk)
 
     # ---- coarsest-level solve in sine space (csrc/spectral.cu) ---------------------------------------------------
     SPECTRAL_MIN_POINTS = 24     # below this the sequential Phi chain (mgb_forward_solve) is as fast
