@@ -282,6 +282,13 @@ int mgb_heat2d_to_rows(int32_t nx, int32_t ny, const double *sx_dev, const doubl
 int mgb_heat2d_from_rows(int32_t nx, int32_t ny, const double *sx_dev, const double *sy_dev, const double *rows_dev,
                          double *nodes_dev, int32_t count, double *work_dev, void *stream);
 
+/* ---- host-side passes of the setup (csrc/host_tables.cu; no device, multi-threaded, bit-identical to NumPy) --------- */
+/* dt[0] = 0, dt[i] = t[i] - t[i-1]; lo / hi = the smallest / largest step. */
+int mgb_host_time_steps(const double *t, int64_t n, double *dt, double *lo, double *hi, int32_t threads);
+/* out[i][k] = src[k][i] * scale[i] (scale may be NULL): [q][n] rows with stride ld_src -> [n][q]. */
+int mgb_host_scale_rows(const double *src, int64_t ld_src, int32_t q, int64_t n, const double *scale, double *out,
+                        int32_t threads);
+
 /* ---- Advection1D: the coarsest-level solve in Fourier space (csrc/fourier.cu) ------------------------------------ */
 /* mgrit.py:459-486 on a level of Advection1D (advection_1d.py:129-143): Phi_i = (I + dt_i (c/dx)(I - S))^-1 is circulant,
  * so u_i = g_i + Phi_i(u_{i-1}) decouples under the discrete Fourier transform into n/2 + 1 complex scalar recurrences

@@ -310,6 +310,12 @@ class DeviceLevel:
 _PAR_MIN = 1 << 17          # arrays at least this long are worked on in pieces by the table threads
 
 
+def host_threads():
+    """Threads for the native host passes (csrc/host_tables.cu): memory-bound, 8 are enough."""
+    import os
+    return max(1, min(8, os.cpu_count() or 1))
+
+
 def parallel_pieces(n, fn):
     """fn(a, b) over pieces [a, b) of range(n) on the table threads (core/rhs_tables.py; NumPy releases the GIL), in
     this thread for short ranges.  Returns the list of results in order."""
@@ -331,6 +337,13 @@ def time_steps(t):
     dt[0] = 0.0
     if len(t) == 1:
         return dt, 0.0, 0.0
+
+    if len(t) >= _PAR_MIN and t.flags.c_contiguous:
+        # long grids: native threads (csrc/host_tables.cu) -- no interpreter lock held while the other levels are built
+        lo, hi = C.c_double(0.0), C.c_double(0.0)
+        _lib.check(_lib.lib().mgb_host_time_steps(t.ctypes.data, len(t), dt.ctypes.data, C.byref(lo), C.byref(hi),
+                                                  host_threads()), 'host_time_steps')
+        return dt, lo.value, hi.value
 
     def piece(a, b):                       # steps into points a+1 .. b
         np.subtract(t[a + 1:b + 1], t[a:b], out=dt[a + 1:b + 1])

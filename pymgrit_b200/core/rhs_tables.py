@@ -288,7 +288,14 @@ class RhsSplit:
             if hit is not None:
                 cached = self._valid[hit[0]][:, hit[1]:hit[1] + len(t)]
         if cached is not None and cached.shape == (q, len(t)):   # found while validating this grid
-            from pymgrit_b200.core.device_level import parallel_pieces
+            from pymgrit_b200.core.device_level import parallel_pieces, host_threads, _PAR_MIN
+            if (len(t) >= _PAR_MIN and cached.dtype == np.float64 and cached.strides[1] == 8 and cached.strides[0] % 8 == 0
+                    and out.flags.c_contiguous and (scale is None or scale.flags.c_contiguous)):
+                from pymgrit_b200 import _lib            # native threads, no interpreter lock (csrc/host_tables.cu)
+                _lib.check(_lib.lib().mgb_host_scale_rows(cached.ctypes.data, cached.strides[0] // 8, q, len(t),
+                                                          None if scale is None else scale.ctypes.data, out.ctypes.data,
+                                                          host_threads()), 'host_scale_rows')
+                return out
 
             def piece(a, b):
                 for k in range(q):

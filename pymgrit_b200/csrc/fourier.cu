@@ -66,8 +66,10 @@ __global__ void k_tables(int n, int M, double2 *__restrict__ tw, double2 *__rest
 // hi 2^(s_top+1) + a 2^q + lo (q = s_top-RL+1) into registers and runs the RL stages there, so a row of 8192 points
 // crosses shared memory 4 times per direction instead of 13.  The passes are bound by the shared-memory pipe (ncu:
 // l1tex 85 %, FP64 pipe 15 %, profiles/r02s_fourier_ncu.txt), hence:
-//   * one twiddle load per stage and group, W^(lo); the other twiddles of the stage differ from it by a fixed 16th root
-//     of unity (W^(a' 2^q + lo) = W^lo exp(-i pi a' / ha)), applied in registers;
+//   * one twiddle load per pass and group, W^(lo) of the top stage: the next stage's W^(lo) is its square, and the other
+//     twiddles of a stage differ from W^(lo) by a fixed 16th root of unity (W^(a' 2^q + lo) = W^lo exp(-i pi a' / ha));
+//     after that the passes wait for L1 misses of the table loads no longer (ncu long scoreboard 5.2 -> ...);
+//   * the chirp's spectrum is stored in the order the last forward pass reads it (coalesced over the threads);
 //   * element i lives at z[i + i/16]: the 16 elements a thread owns in the last pass (stride 1) and the rows of 16 that a
 //     quarter warp touches fall into different banks;
 //   * the first forward pass reads its input straight from global memory (the caller's functor), the last forward pass
@@ -102,12 +104,11 @@ __device__ __forceinline__ void dif_pass(double2 *z, const int log2m, const int 
         double2 v[RN];
 #pragma unroll
         for (int a = 0; a < RN; ++a) v[a] = src(base + (a << q));
+        double2 ws = __ldg(tw + lo * (H >> s_top));              // W_(2^(s_top+1))^lo; the next stage's is its square
 #pragma unroll
         for (int j = 0; j < RL; ++j) {
-            const int s = s_top - j;
             constexpr int kOne = 1;
             const int ha = kOne << (RL - 1 - j);                 // pairs (a, a + ha), a with that bit clear
-            const double2 ws = __ldg(tw + lo * (H >> s));        // W_(2^(s+1))^lo
 #pragma unroll
             for (int a = 0; a < RN; ++a) {
                 if (a & ha) continue;
@@ -116,11 +117,13 @@ __device__ __forceinline__ void dif_pass(double2 *z, const int log2m, const int 
                 v[a] = make_double2(x.x + y.x, x.y + y.y);
                 v[a + ha] = cmul(make_double2(x.x - y.x, x.y - y.y), w);
             }
+            ws = cmul(ws, ws);
         }
 #pragma unroll
         for (int a = 0; a < RN; ++a) {
             const int idx = base + (a << q);
-            z[pad(idx)] = mul ? cmul(v[a], __ldg(mul + idx)) : v[a];
+            // mul is stored in the order this (last, q = 0) pass reads it: [a][group], coalesced over the threads
+            z[pad(idx)] = mul ? cmul(v[a], __ldg(mul + a * groups + gi)) : v[a];
         }
     }
     __syncthreads();
@@ -136,12 +139,15 @@ __device__ __forceinline__ void dit_pass(double2 *z, const int log2m, const int 
         double2 v[RN];
 #pragma unroll
         for (int a = 0; a < RN; ++a) v[a] = z[pad(base + (a << q))];
+        double2 wj[RL];                                          // W^lo of stages s_top, s_top-1, ..: successive squares
+        wj[0] = __ldg(tw + lo * (H >> s_top));
+#pragma unroll
+        for (int j = 1; j < RL; ++j) wj[j] = cmul(wj[j - 1], wj[j - 1]);
 #pragma unroll
         for (int j = RL - 1; j >= 0; --j) {
-            const int s = s_top - j;
             constexpr int kOne = 1;
             const int ha = kOne << (RL - 1 - j);
-            const double2 ws = __ldg(tw + lo * (H >> s));
+            const double2 ws = wj[j];
 #pragma unroll
             for (int a = 0; a < RN; ++a) {
                 if (a & ha) continue;
@@ -233,7 +239,10 @@ __global__ void __launch_bounds__(kThreads) k_bhat(const int log2m, const double
     extern __shared__ double2 z[];
     const int M = 1 << log2m;
     fft_dif(z, log2m, tw, nullptr, [b](const int i) { return b[i]; });
-    for (int p = threadIdx.x; p < M; p += blockDim.x) bhat[p] = z[pad(p)];
+    // stored as the last forward pass reads it: element (group gi, a) = index gi 2^RL + a at [a][gi]
+    const Plan pl = make_plan(log2m);
+    const int rl = pl.rl[pl.count - 1], groups = M >> rl;
+    for (int p = threadIdx.x; p < M; p += blockDim.x) bhat[(p & ((1 << rl) - 1)) * groups + (p >> rl)] = z[pad(p)];
 }
 
 // Rows are real: two of them share one complex transform, Z = F(x_a + i x_b), X_a[k] = (Z_k + conj(Z_{n-k})) / 2,

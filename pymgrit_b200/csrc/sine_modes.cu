@@ -45,6 +45,8 @@ struct DiagPhi {
                                     // chains of dependent row loads per CTA, so the SM needs many CTAs in flight
     static constexpr int MINB_DOWN = 3;
     static constexpr bool kSplitNorm = false;  // a CTA of the residual kernel walks all chunks of a row
+    static constexpr bool kHoist = false;  // the tables are read per item, where they are used (L1 / L2 hits): held across
+                                           // the items of a CTA they cost registers (down-sweep of cfg5 0.258 -> 0.284 ms)
     double d[R];
     double rx[Q > 0 ? Q : 1][R];
     bool recip;
@@ -95,6 +97,7 @@ struct TilePhi {
     static constexpr int MINB = (TB_ * 3 <= 1536 && !GEN && Q_ <= 1) ? 3 : 2;
     static constexpr int MINB_DOWN = 2;
     static constexpr bool kSplitNorm = true;  // one partial sum of squares per (C-point, chunk)
+    static constexpr bool kHoist = true;  // the reciprocals are divisions and the tables long: made once per CTA
     double inv[R];  // 1 / (1 + theta dt sig) for the step size dtc; Dirichlet chunk: the boundary values
     double rx[Q > 0 ? Q : 1][R];
     double sg[GEN ? R : 1];
@@ -271,11 +274,12 @@ __global__ void __launch_bounds__(P::TB, P::MINB) k_chain(const LevelDev L, cons
     MGB_RETURN_IF_STOPPED(L)
     MGB_MODES_CTA(P, L, nch)
     P phi;
-    phi.load(L, m0);
+    if (P::kHoist) phi.load(L, m0);
     for (int k = kg; k < L.ncpts; k += ng) {
         int s, e;
         interval(L, k, s, e);
         if (e - s <= 1) continue;
+        if (!P::kHoist) phi.load(L, m0);
         double x[P::R];
         ldrow<P>(x, L.u, s, L.pitch, m0, n);
         if (last_only) {
@@ -297,10 +301,13 @@ __global__ void __launch_bounds__(P::TB, P::MINB_DOWN) k_down(const LevelDev L, 
     MGB_MODES_CTA(P, L, nch)
     constexpr int Q = P::Q, R = P::R;
     P phi, cphi;
-    phi.load(L, m0);
-    cphi.load_coarse(G, m0, phi);
+    if (P::kHoist) {
+        phi.load(L, m0);
+        cphi.load_coarse(G, m0, phi);
+    }
     for (int j = 1 + kg; j < L.ncpts; j += ng) {
         const int a = __ldg(L.cpts + j - 1), c = __ldg(L.cpts + j);
+        if (!P::kHoist) phi.load(L, m0);
         double x[R], yc[R], w[R];
         // time factors of the item's single steps, all in flight before the first row is waited for
         double ct_c[Q > 0 ? Q : 1], ct_a[Q > 0 ? Q : 1], ct_j[Q > 0 ? Q : 1];
@@ -333,7 +340,13 @@ __global__ void __launch_bounds__(P::TB, P::MINB_DOWN) k_down(const LevelDev L, 
         // w = Phi_c(x) with the coarse level's factors
 #pragma unroll
         for (int r = 0; r < R; ++r) w[r] = x[r];
-        cphi.step(w, G, j, ct_j);
+        if (P::kHoist) {
+            cphi.step(w, G, j, ct_j);
+        } else {
+            P cl;
+            cl.load_coarse(G, m0, phi);
+            cl.step(w, G, j, ct_j);
+        }
         // F-relaxation chain and the fine step into c
         run_steps<P, false>(x, phi, L, a + 1, c, m0, n);
         phi.step(x, L, c, ct_c);
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(P::TB, P::MINB) k_correct(const LevelDev L, co
     MGB_MODES_CTA(P, L, nch)
     constexpr int R = P::R;
     P phi;
-    if (frelax) phi.load(L, m0);
+    if (frelax && P::kHoist) phi.load(L, m0);
     for (int k = kg; k < L.ncpts; k += ng) {
         int s, e;
         interval(L, k, s, e);
@@ -375,6 +388,7 @@ __global__ void __launch_bounds__(P::TB, P::MINB) k_correct(const LevelDev L, co
             strow<P>(x, L.u, s, L.pitch, m0, n);
         }
         if (!relax) continue;
+        if (!P::kHoist) phi.load(L, m0);
         if (frelax == 2) {
             run_steps<P, false>(x, phi, L, s + 1, e, m0, n);
             strow<P>(x, L.u, e - 1, L.pitch, m0, n);
