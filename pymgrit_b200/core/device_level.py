@@ -82,6 +82,21 @@ def _stage_small(host):
     return arr
 
 
+def upload_small(dst, host):
+    """dst (device tensor) <- host array through pooled page-locked memory, asynchronously.  The pool entry is marked
+    with an event recorded after the copy: the pool hands the buffer out again only once the copy has run.  (A staging
+    array that is merely dropped after queueing its copy can be overwritten by the next table before the device has read
+    it -- seen as an intermittent wrong reciprocal table on two time ranks, where the device lags the host during the
+    setup.)"""
+    torch = _torch()
+    a = _stage_small(np.ascontiguousarray(host))
+    dst.copy_(a._owner, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    a._slot[1] = ev
+    return dst
+
+
 def team_shape(kind, n):
     import os
     forced = os.environ.get('MGB_SHAPE_%d' % kind)            # experiments: "threads,chunk" for application kind `kind`
@@ -258,6 +273,7 @@ class DeviceLevel:
         c.sig_dev = ptr(sig)
         diag = up(tab.get('diag'), np.float64)
         nat = tab.get('nat_dev')
+        self.nat_dev = nat
         if nat is not None:
             self._keep.append(nat)
         c.nat_dev = ptr(nat)

@@ -229,7 +229,8 @@ class Mgrit:
             # constructor and the first iteration would see the difference, so a per-iteration output_fcn keeps the fill.
             self._lv.append(DeviceLevel(problem[lvl], part.t_local[lvl], cpts=cp, with_g=lvl > 0, defer_tables=defer,
                                         zero_u=not (defer and max_iter > 0 and not (callable(output_fcn) and
-                                                                                    output_lvl == 2))))
+                                                                                    output_lvl == 2))
+                                        or _os.environ.get('MGB_ZERO_U') == '1'))
             if defer:
                 self._lv[0].start_host_tables()      # the long host tables of level 0 are made while the rest is set up
         self._f_uninit = self.lvl_max > 1 and not self._lv[0].zero_filled
@@ -732,7 +733,7 @@ class Mgrit:
                 return self.conv[k] < self.tol
 
             done = False
-            queued = 0
+            queued = last_read = 0
             for iteration in range(self.iter_max):
                 self.iteration(lvl=0, cycle_type=self.cycle_type, iteration=iteration, first_f=True)
                 self._queue_convergence(iteration + 1)
@@ -741,11 +742,26 @@ class Mgrit:
                 ev.record()
                 events[iteration + 1] = ev
                 queued = iteration + 1
-                if iteration >= 1 and read(iteration):
-                    done = True                      # iteration `iteration + 1` is queued but will not run
-                    break
-            if not done:
-                read(queued)
+                if iteration >= 1 and last_read < iteration:
+                    last_read = iteration
+                    if read(iteration):
+                        done = True                  # iteration `iteration + 1` is queued but will not run
+                        break
+                # If the two residuals known so far say that the iteration just queued will meet the tolerance (linear
+                # convergence), wait for its residual instead of queueing one more cycle of sweeps that would return at
+                # once: same result, a cycle's worth of launches less.  A wrong guess costs one host round trip.
+                if last_read >= 2 and self.conv[last_read - 1] > 0:
+                    rate = self.conv[last_read] / self.conv[last_read - 1]
+                    steps = queued - last_read
+                    if 0 < rate < 1 and self.conv[last_read] * rate ** steps < self.tol:
+                        while last_read < queued and not done:
+                            last_read += 1
+                            done = read(last_read)
+                        if done:
+                            break
+            while not done and last_read < queued:
+                last_read += 1
+                done = read(last_read)
         finally:
             _lib.check(lib.mgb_write_flag(flag_ptr, 0, self._stream()), 'write_flag')
             _lib.check(lib.mgb_set_stop_flag(None), 'set_stop_flag')

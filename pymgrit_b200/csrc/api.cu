@@ -427,7 +427,7 @@ int mgb_f_relax(const mgb_level *lvl, int32_t flags, void *stream) {
     if (L.cpts == nullptr) return fail(MGB_EINVAL, "f_relax needs the C-point table%s");
     // one thread per mode for the chains that store one point; with every F-point stored the sweep is a stream of rows and
     // the team kernel's bulk stores are the better writer (88 % against 85 % of the HBM peak, profiles/r02p_*)
-    if (sine_modes_ok(L) && ((flags & MGB_F_RELAX_LAST_ONLY) || L.npts < kStreamPoints)) return sine_modes_f_relax(L, flags, st);
+    if (sine_modes_entry(0) && sine_modes_ok(L) && ((flags & MGB_F_RELAX_LAST_ONLY) || L.npts < kStreamPoints)) return sine_modes_f_relax(L, flags, st);
     return tab->f_relax(L, flags, st);
 }
 
@@ -459,7 +459,7 @@ int mgb_down_sweep(const mgb_level *fine, const mgb_level *coarse, void *stream)
     if (int rc = check_level(coarse, &tab2, &G)) return rc;
     if (int rc = check_pair(fine, coarse)) return rc;
     if (tab->down == nullptr) return fail(MGB_ENOSHAPE, "no fused down-sweep for this application%s");
-    if (sine_modes_ok(L) && sine_modes_coarse_ok(G, L)) return sine_modes_down(L, G, st);
+    if (sine_modes_entry(1) && sine_modes_ok(L) && sine_modes_coarse_ok(G, L)) return sine_modes_down(L, G, st);
     return tab->down(L, G, st);
 }
 
@@ -470,7 +470,7 @@ int mgb_error_correction(const mgb_level *fine, const mgb_level *coarse, int32_t
     if (int rc = check_level(coarse, &tab2, &G)) return rc;
     if (int rc = check_pair(fine, coarse)) return rc;
     const int frelax = (flags & MGB_CORRECT_F_RELAX) ? ((flags & MGB_CORRECT_LAST_ONLY) ? 2 : 1) : 0;
-    if (sine_modes_ok(L) && (frelax != 1 || L.npts < kStreamPoints)) return sine_modes_correct(L, G, frelax, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
+    if (sine_modes_entry(2) && sine_modes_ok(L) && (frelax != 1 || L.npts < kStreamPoints)) return sine_modes_correct(L, G, frelax, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
     return tab->correct(L, G, frelax, (flags & MGB_CORRECT_GHOST) ? 0 : 1, st);
 }
 
@@ -489,7 +489,7 @@ int mgb_local_coarse_solve(const mgb_level *lvl, const double *old_dev, int32_t 
 int mgb_residual_norms(const mgb_level *lvl, double *out_sq_dev, void *stream) {
     MGB_PROLOGUE(lvl)
     if (L.cpts == nullptr || out_sq_dev == nullptr) return fail(MGB_EINVAL, "residual_norms needs C-points and an output%s");
-    if (sine_modes_ok(L)) return sine_modes_residual(L, out_sq_dev, st);
+    if (sine_modes_entry(3) && sine_modes_ok(L)) return sine_modes_residual(L, out_sq_dev, st);
     return tab->residual(L, out_sq_dev, st);
 }
 

@@ -502,6 +502,14 @@ static bool tile_simple(const LevelDev &L) { return L.ip[1] == 1 && L.ndt == 1; 
 }  // namespace modes
 
 // ---- entry points used by api.cu ---------------------------------------------------------------------------------
+// MGB_SINE_MODES_MASK (experiments): bit 0 f_relax, 1 down_sweep, 2 error_correction, 3 residual_norms; default all
+static bool mode_entry_on(int bit) {
+    const char *e = getenv("MGB_SINE_MODES_MASK");
+    return !(e && e[0]) || ((atoi(e) >> bit) & 1);
+}
+
+bool sine_modes_entry(int bit) { return mode_entry_on(bit); }
+
 bool sine_modes_ok(const LevelDev &L) {
     const char *e = getenv("MGB_SINE_MODES");  // "0": the team kernels of sweeps.cuh instead (tests compare the two)
     const bool on = !(e && e[0] == '0');

@@ -16,6 +16,7 @@ const int *stop_flag();                          // api.cu: the device flag of m
 
 // sine_modes.cu: the hot sweeps of a HEAT1D_SINE level with one thread per mode
 bool sine_modes_ok(const LevelDev &L);
+bool sine_modes_entry(int bit);   // experiments: MGB_SINE_MODES_MASK
 bool sine_modes_coarse_ok(const LevelDev &G, const LevelDev &L);
 int sine_modes_f_relax(const LevelDev &L, int flags, cudaStream_t st);
 int sine_modes_down(const LevelDev &L, const LevelDev &G, cudaStream_t st);

@@ -274,7 +274,7 @@ class Heat1D(DeviceApplication):
         nat_host = tab.pop('nat')
         q = shared['nrhs']
         nat = torch.empty((2 + q, nat_host.shape[1]), dtype=torch.float64, device=shared['lam'].device)
-        nat[:2].copy_(dl._stage_small(nat_host)._owner, non_blocking=True)
+        dl.upload_small(nat[:2], nat_host)
         if q:
             nat[2:].copy_(shared['rxh'])
         tab['nat_dev'] = nat

@@ -283,6 +283,32 @@ def test_spectral_coarse_solve_matches_phi_chain(P, variant):
     assert float(spectral[:, lv.n:].abs().max()) == 0.0           # the row padding stays zero
 
 
+def test_small_table_uploads_survive_a_busy_device(P):
+    """The small Phi tables go to the device through pooled page-locked buffers with asynchronous copies.  While the device
+    is busy (here: a queue of matrix products; on several time ranks: the setup of the communicator) the host runs ahead
+    of those copies, so a buffer must not be handed out again before its copy has run: every level's natural-order
+    table must hold that level's own reciprocals.  (Regression: heat1d_small_f_cf2 stalled at 4.9e-10 in one of eight
+    runs on two ranks because a level read another level's 1 / (1 + dt lam).)"""
+    import logging
+    import torch
+    x = torch.randn(6144, 6144, device='cuda', dtype=torch.float64)
+    for _ in range(6):                                   # tens of milliseconds of queued device work
+        x = (x @ x) * 1e-4
+    t = np.linspace(0, 2, 129)
+    kw = dict(x_start=0, x_end=1, nx=17, a=1, init_cond=C.heat_init, rhs=C.heat_rhs)
+    levels = [P.Heat1D(t_interval=t[::2 ** k], **kw) for k in range(4)]
+    solver = P.Mgrit(problem=levels, nested_iteration=False, logging_lvl=logging.WARNING)
+    assert solver.problem[0].kind == P._lib.APP_HEAT1D_SINE
+    torch.cuda.synchronize()
+    for lv in solver._lv:
+        host, _ = lv.app.sine_host_tables(lv.t, lv.team_threads, lv.chunk)
+        assert np.array_equal(lv.nat_dev[:2].cpu().numpy(), host['nat'])
+        for name, ten in (('sconst', lv.c.sconst_dev), ):
+            assert ten
+    info = solver.solve()
+    assert info['conv'][-1] < 1e-7
+
+
 @pytest.mark.parametrize('n', [1, 2, 3, 5, 16, 20, 33, 100, 300, 1000, 1500, 4095, 4096])
 def test_rows_rfft_matches_numpy(P, n):
     """csrc/fourier.cu: the real Fourier transform of rows of any length n <= 4096 (Bluestein's algorithm on a radix-2 FFT
