@@ -252,24 +252,33 @@ __global__ void __launch_bounds__(kThreads) k_rows_rfft(const int rows, const in
                                                         const double *__restrict__ A, const long lda,
                                                         const double *__restrict__ a_row0, const double2 *__restrict__ tw,
                                                         const double2 *__restrict__ chirp, const double2 *__restrict__ bhat,
-                                                        double *__restrict__ Cm, const long ldc, const int *__restrict__ stop) {
+                                                        double *__restrict__ Cm, const long ldc, const int *__restrict__ stop,
+                                                        const int chirp_smem) {
     if (stop != nullptr && *stop != 0) return;
     extern __shared__ double2 z[];
     const int M = 1 << log2m, K = n / 2 + 1;
     const double scale = 0.5 / (double)M;
+    // the chirp is read three times per transform: once per CTA into shared memory when it fits behind the row
+    const double2 *ch = chirp;
+    if (chirp_smem) {
+        double2 *cs = z + (M + M / 16 + 1);
+        for (int j = threadIdx.x; j < n; j += blockDim.x) cs[j] = chirp[j];
+        ch = cs;
+        __syncthreads();
+    }
     for (int pr = blockIdx.x; 2 * pr < rows; pr += gridDim.x) {
         const int ra = 2 * pr, rb = ra + 1;
         const double *xa = (ra == 0 && a_row0 != nullptr) ? a_row0 : A + (long)ra * lda;
         const double *xb = rb < rows ? A + (long)rb * lda : nullptr;
         chirp_conv(z, log2m, tw, bhat, [=](const int j) {
             if (j >= n) return make_double2(0.0, 0.0);
-            return cmulc(make_double2(xa[j], xb ? xb[j] : 0.0), __ldg(chirp + j));
+            return cmulc(make_double2(xa[j], xb ? xb[j] : 0.0), ch[j]);
         });
         double2 *oa = reinterpret_cast<double2 *>(Cm + (long)ra * ldc);
         double2 *ob = xb ? reinterpret_cast<double2 *>(Cm + (long)rb * ldc) : nullptr;
         for (int k = threadIdx.x; k < K; k += blockDim.x) {
             const int km = (k == 0) ? 0 : n - k;
-            const double2 zk = cmulc(z[pad(k)], __ldg(chirp + k)), zm = cmulc(z[pad(km)], __ldg(chirp + km));
+            const double2 zk = cmulc(z[pad(k)], ch[k]), zm = cmulc(z[pad(km)], ch[km]);
             // (Z_k + conj(Z_m)) / 2  and  (Z_k - conj(Z_m)) / (2i) = (Im(Z_k) + Im(Z_m), Re(Z_m) - Re(Z_k)) / 2
             oa[k] = make_double2((zk.x + zm.x) * scale, (zk.y - zm.y) * scale);
             if (ob) ob[k] = make_double2((zk.y + zm.y) * scale, (zm.x - zk.x) * scale);
@@ -284,11 +293,18 @@ __global__ void __launch_bounds__(kThreads) k_rows_irfft(const int rows, const i
                                                          const double *__restrict__ Cm, const long ldc,
                                                          const double2 *__restrict__ tw, const double2 *__restrict__ chirp,
                                                          const double2 *__restrict__ bhat, double *__restrict__ out,
-                                                         const long ldo, const int *__restrict__ stop) {
+                                                         const long ldo, const int *__restrict__ stop, const int chirp_smem) {
     if (stop != nullptr && *stop != 0) return;
     extern __shared__ double2 z[];
     const int M = 1 << log2m, K = n / 2 + 1;
     const double scale = 1.0 / ((double)M * (double)n);
+    const double2 *ch = chirp;
+    if (chirp_smem) {
+        double2 *cs = z + (M + M / 16 + 1);
+        for (int j = threadIdx.x; j < n; j += blockDim.x) cs[j] = chirp[j];
+        ch = cs;
+        __syncthreads();
+    }
     for (int pr = blockIdx.x; first_row + 2 * pr < rows; pr += gridDim.x) {
         const int ra = first_row + 2 * pr, rb = ra + 1;
         const double2 *Xa = reinterpret_cast<const double2 *>(Cm + (long)ra * ldc);
@@ -304,12 +320,12 @@ __global__ void __launch_bounds__(kThreads) k_rows_irfft(const int rows, const i
                 b.y = -b.y;
             }
             // conj(Y) = conj(a + i b) = (a.x - b.y) - i (a.y + b.x)
-            return cmulc(make_double2(a.x - b.y, -(a.y + b.x)), __ldg(chirp + k));
+            return cmulc(make_double2(a.x - b.y, -(a.y + b.x)), ch[k]);
         });
         double *oa = out + (long)ra * ldo;
         double *ob = Xb ? out + (long)rb * ldo : nullptr;
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            const double2 f = cmulc(z[pad(j)], __ldg(chirp + j));     // F(conj(Y))_j times M
+            const double2 f = cmulc(z[pad(j)], ch[j]);     // F(conj(Y))_j times M
             oa[j] = f.x * scale;
             if (ob) ob[j] = -f.y * scale;
         }
@@ -435,12 +451,17 @@ int mgb_circ_fft_tables(int32_t n, double *tw_dev, double *chirp_dev, double *bh
     return cuda_fail(cudaGetLastError(), "circ_fft_tables");
 }
 
-static int fft_smem(int n, int *p_out, size_t *smem_out) {
+static int fft_smem(int n, int *p_out, size_t *smem_out, int *chirp_smem) {
     const DeviceInfo *di = device_info();
     if (di == nullptr) return MGB_ECUDA;
     const int p = log2_conv_len(n);
-    const size_t smem = (((size_t)1 << p) + ((size_t)1 << p) / 16 + 1) * sizeof(double2);   // element i at z[i + i/16]
+    size_t smem = (((size_t)1 << p) + ((size_t)1 << p) / 16 + 1) * sizeof(double2);   // element i at z[i + i/16]
     if ((int)smem > di->max_smem_optin) return heat2d_fail("rows_rfft: row too long for shared memory (n <= 4096)");
+    *chirp_smem = 0;
+    if ((long)(smem + (size_t)n * sizeof(double2)) <= (long)di->max_smem_optin) {   // the chirp behind the row
+        smem += (size_t)n * sizeof(double2);
+        *chirp_smem = 1;
+    }
     *p_out = p;
     *smem_out = smem;
     return MGB_OK;
@@ -451,9 +472,9 @@ int mgb_rows_rfft(int32_t m, int32_t n, const double *a_dev, int64_t lda, const 
     if (m < 0 || n < 1 || a_dev == nullptr || tw_dev == nullptr || chirp_dev == nullptr || bhat_dev == nullptr ||
         c_dev == nullptr || lda < n || ldc < 2 * (n / 2 + 1) || (ldc & 1) || ((uintptr_t)c_dev & 15))
         return heat2d_fail("rows_rfft: bad argument");
-    int p;
+    int p, chirp_smem;
     size_t smem;
-    if (int rc = fft_smem(n, &p, &smem)) return rc;
+    if (int rc = fft_smem(n, &p, &smem, &chirp_smem)) return rc;
     if (m == 0) return MGB_OK;
     static size_t configured = 0;
     if (smem > configured) {
@@ -466,7 +487,7 @@ int mgb_rows_rfft(int32_t m, int32_t n, const double *a_dev, int64_t lda, const 
     const int cap = di->sms * (per_sm > 2 ? 2 : per_sm);
     k_rows_rfft<<<(m + 1) / 2 < cap ? (m + 1) / 2 : cap, kThreads, smem, (cudaStream_t)stream>>>(
         m, n, p, a_dev, lda, a_row0_dev, (const double2 *)tw_dev, (const double2 *)chirp_dev, (const double2 *)bhat_dev, c_dev,
-        ldc, stop_flag());
+        ldc, stop_flag(), chirp_smem);
     return cuda_fail(cudaGetLastError(), "rows_rfft");
 }
 
@@ -475,9 +496,9 @@ int mgb_rows_irfft(int32_t m, int32_t first_row, int32_t n, const double *c_dev,
     if (m < 0 || first_row < 0 || n < 1 || c_dev == nullptr || tw_dev == nullptr || chirp_dev == nullptr ||
         bhat_dev == nullptr || out_dev == nullptr || ldo < n || ldc < 2 * (n / 2 + 1) || (ldc & 1) || ((uintptr_t)c_dev & 15))
         return heat2d_fail("rows_irfft: bad argument");
-    int p;
+    int p, chirp_smem;
     size_t smem;
-    if (int rc = fft_smem(n, &p, &smem)) return rc;
+    if (int rc = fft_smem(n, &p, &smem, &chirp_smem)) return rc;
     if (m <= first_row) return MGB_OK;
     static size_t configured = 0;
     if (smem > configured) {
@@ -491,7 +512,7 @@ int mgb_rows_irfft(int32_t m, int32_t first_row, int32_t n, const double *c_dev,
     const int work = (m - first_row + 1) / 2;
     k_rows_irfft<<<work < cap ? work : cap, kThreads, smem, (cudaStream_t)stream>>>(
         m, first_row, n, p, c_dev, ldc, (const double2 *)tw_dev, (const double2 *)chirp_dev, (const double2 *)bhat_dev, out_dev,
-        ldo, stop_flag());
+        ldo, stop_flag(), chirp_smem);
     return cuda_fail(cudaGetLastError(), "rows_irfft");
 }
 

@@ -47,11 +47,22 @@ _PI = np.longdouble('3.14159265358979323846264338327950288')
 SINE_GEMM_MAX = 2048        # largest n transformed with the dense sine matrix when n + 1 is not a power of two
 
 
+_EIG = {}
+
+
 def heat1d_eigenvalues(n, fac):
     """lam_k = fac * 4 sin^2(pi k / (2 (n+1))), k = 1..n, of fac * tridiag(-1, 2, -1) (heat_1d.py:177-196), in extended
-    precision."""
-    k = np.arange(1, n + 1).astype(np.longdouble)
-    return np.longdouble(fac) * 4 * np.sin(k * _PI / (2 * (n + 1))) ** 2
+    precision (read-only: every level of a hierarchy asks for the same array)."""
+    key = (int(n), np.longdouble(fac).tobytes())
+    lam = _EIG.get(key)
+    if lam is None:
+        if len(_EIG) > 16:
+            _EIG.clear()
+        k = np.arange(1, n + 1).astype(np.longdouble)
+        lam = np.longdouble(fac) * 4 * np.sin(k * _PI / (2 * (n + 1))) ** 2
+        lam.setflags(write=False)
+        _EIG[key] = lam
+    return lam
 
 
 class SineTransform:

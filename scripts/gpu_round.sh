@@ -33,4 +33,9 @@ echo "ncu full rc=$?"
 python scripts/solve_timeline.py cfg5 > gpurun_out/${tag}_timeline_cfg5_n1.txt 2>&1; head -18 gpurun_out/${tag}_timeline_cfg5_n1.txt
 MGB_HEAT1D_SINE=0 python scripts/solve_timeline.py cfg5 > gpurun_out/${tag}_timeline_cfg5_n1_node_space.txt 2>&1; head -3 gpurun_out/${tag}_timeline_cfg5_n1_node_space.txt
 timeout 300 python scripts/e2e_breakdown.py cfg5 > gpurun_out/${tag}_e2e_breakdown_n1.txt 2>&1; head -8 gpurun_out/${tag}_e2e_breakdown_n1.txt
+for wl in cfg2 cfg3 cfg4; do python scripts/solve_timeline.py $wl > gpurun_out/${tag}_timeline_${wl}_n1.txt 2>&1; head -3 gpurun_out/${tag}_timeline_${wl}_n1.txt; done
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_rows_rfft|k_rows_irfft|k_cplx_solve" -s 3 -c 3 \
+   -o gpurun_out/${tag}_fourier -f python scripts/profile_fourier.py > gpurun_out/${tag}_ncu_fourier.log 2>&1; echo "ncu fourier rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_chain|k_down|k_correct|k_residual" -s 5 -c 5 \
+   -o gpurun_out/${tag}_cfg3_modes -f python scripts/profile_cfg3.py > gpurun_out/${tag}_ncu_cfg3.log 2>&1; echo "ncu cfg3 rc=$?"
 ls gpurun_out | grep ${tag}
