@@ -3,8 +3,11 @@ import glob
 import json
 import os
 
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, 'profiles')
+TAG = sys.argv[1] if len(sys.argv) > 1 else 'r03'
 
 
 def load(name):
@@ -16,7 +19,7 @@ print('| config (BASELINE.json) | hierarchy | iterations to 1e-10 | device, ms |
       'CPU: reference algorithm on the box (cores) | ratio e2e / CPU |')
 print('|---|---|---|---|---|---|---|---|---|')
 for wl in ('cfg1', 'cfg2', 'cfg3', 'cfg4', 'cfg5'):
-    d = load(f'r02_bench_{wl}_n1.json')
+    d = load(f'{TAG}_bench_{wl}_n1.json')
     if d is None:
         continue
     w = d['config']['workload']
@@ -31,7 +34,7 @@ for wl in ('cfg1', 'cfg2', 'cfg3', 'cfg4', 'cfg5'):
 print()
 print('| cfg 5 on N GPUs | 1 | 2 | 4 | 8 |')
 print('|---|---|---|---|---|')
-rows = {n: load(f'r02_bench_cfg5_n{n}.json') for n in (1, 2, 4, 8)}
+rows = {n: load(f'{TAG}_bench_cfg5_n{n}.json') for n in (1, 2, 4, 8)}
 def cell(fn):
     return ' | '.join(fn(rows[n]) if rows[n] else '-' for n in (1, 2, 4, 8))
 print('| device time to 1e-10, ms | ' + cell(lambda d: f"{d['ms_per_step']:.2f}") + ' |')
@@ -47,3 +50,15 @@ print('|---|---|---|---|---|---|')
 for k in d['kernels']:
     print(f"| {k['name']} | {k['ms']:.3f} | {k['gbs']:.0f} | {k.get('hbm_frac', 0):.2f} | {k.get('fp64_frac', 0):.2f} | "
           f"{k['launches_per_iteration']} / {k['launches_per_solve']} |")
+
+for wl, title in (('cfg3', 'level-0 sweep of cfg 3 (512 intervals of 8, rows of 2 MiB)'),
+                  ('cfg4', 'level-0 sweep of cfg 4 (32 768 intervals of 2, rows of 32 KiB)')):
+    d = load(f'{TAG}_bench_{wl}_n1.json')
+    if d is None:
+        continue
+    print()
+    print(f'| {title} | ms | GB/s | of measured HBM peak | per iteration / per solve |')
+    print('|---|---|---|---|---|')
+    for k in d['kernels']:
+        print(f"| {k['name']} | {k['ms']:.3f} | {k['gbs']:.0f} | {k.get('hbm_frac', 0):.2f} | "
+              f"{k['launches_per_iteration']} / {k['launches_per_solve']} |")

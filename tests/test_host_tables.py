@@ -226,3 +226,40 @@ def test_sine_space_tables_restate_the_heat1d_step(nx):
             ref = orc.phi(u, grid[i - 1], grid[i])
             assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))
             u = ref
+
+
+def test_native_host_passes_are_bit_identical_to_numpy():
+    """csrc/host_tables.cu (no device): the step sizes of a time grid with their extrema, and the scaled transpose of the
+    time factors of a right-hand side, against the NumPy expressions they replace -- every element the same IEEE
+    operation, for uniform and non-uniform grids, one and several threads, strided input rows."""
+    import ctypes as C
+    from pymgrit_b200 import _lib
+    lib = _lib.lib()
+    rng = np.random.default_rng(3)
+    for n, threads in ((1, 4), (2, 4), (1000, 1), (70001, 3), (300007, 8)):
+        t = np.cumsum(rng.random(n) + 1e-3) if n % 2 else np.linspace(0.0, 2.0, n)
+        dt = np.full(n, np.nan)
+        lo, hi = C.c_double(-1.0), C.c_double(-1.0)
+        assert lib.mgb_host_time_steps(t.ctypes.data, n, dt.ctypes.data, C.byref(lo), C.byref(hi), threads) == 0
+        ref = np.zeros(n)
+        ref[1:] = t[1:] - t[:-1]
+        assert np.array_equal(dt, ref)
+        if n > 1:
+            assert lo.value == ref[1:].min() and hi.value == ref[1:].max()
+        else:
+            assert lo.value == 0.0 and hi.value == 0.0
+        for q in (1, 2, 3):
+            wide = rng.standard_normal((q, n + 5))
+            src = wide[:, 2:2 + n]                                   # rows with a stride
+            scale = rng.standard_normal(n)
+            out = np.full((n, q), np.nan)
+            assert lib.mgb_host_scale_rows(src.ctypes.data, src.strides[0] // 8, q, n, scale.ctypes.data, out.ctypes.data,
+                                           threads) == 0
+            assert np.array_equal(out, (src * scale).T)
+            assert lib.mgb_host_scale_rows(src.ctypes.data, src.strides[0] // 8, q, n, None, out.ctypes.data, threads) == 0
+            assert np.array_equal(out, src.T)
+    # and through the host helpers that call them on long grids
+    from pymgrit_b200.core import device_level as dl
+    t = np.linspace(0, 2, dl._PAR_MIN + 77) ** 1.1
+    dt, lo, hi = dl.time_steps(t)
+    assert np.array_equal(dt[1:], t[1:] - t[:-1]) and dt[0] == 0.0 and lo == dt[1:].min() and hi == dt[1:].max()
