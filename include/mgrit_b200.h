@@ -285,6 +285,8 @@ int mgb_heat2d_from_rows(int32_t nx, int32_t ny, const double *sx_dev, const dou
 /* ---- host-side passes of the setup (csrc/host_tables.cu; no device, multi-threaded, bit-identical to NumPy) --------- */
 /* dt[0] = 0, dt[i] = t[i] - t[i-1]; lo / hi = the smallest / largest step. */
 int mgb_host_time_steps(const double *t, int64_t n, double *dt, double *lo, double *hi, int32_t threads);
+/* out[i] = i * step + start (product and sum rounded separately, like numpy.linspace's arange(n) * step + start). */
+int mgb_host_affine_ramp(double start, double step, int64_t n, double *out, int32_t threads);
 /* out[i][k] = src[k][i] * scale[i] (scale may be NULL): [q][n] rows with stride ld_src -> [n][q]. */
 int mgb_host_scale_rows(const double *src, int64_t ld_src, int32_t q, int64_t n, const double *scale, double *out,
                         int32_t threads);

@@ -87,6 +87,7 @@ SYMBOLS = {
     'mgb_sine_level_solve': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_heat1d_spectral_fixup': (C.c_int, [_LP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'mgb_host_time_steps': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, c_double_p, c_double_p, C.c_int32]),
+    'mgb_host_affine_ramp': (C.c_int, [C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_int32]),
     'mgb_host_scale_rows': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     'mgb_circ_fft_length': (C.c_int, [C.c_int32]),
     'mgb_circ_fft_tables': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -75,11 +75,18 @@ def linspace(t_start, t_stop, nt):
             t = np.linspace(t_start, t_stop, nt)
         else:
             t = np.empty(nt)
+            try:
+                from pymgrit_b200 import _lib
+                from pymgrit_b200.core.device_level import host_threads
+                native = _lib.lib().mgb_host_affine_ramp(start, step, nt, t.ctypes.data, host_threads()) == 0
+            except Exception:
+                native = False
 
             def piece(a, b):
                 np.multiply(np.arange(a, b, dtype=float), step, out=t[a:b])
                 t[a:b] += start
-            parallel_pieces(nt, piece)
+            if not native:
+                parallel_pieces(nt, piece)
             t[-1] = stop
     if nt > 1 and t[-1] > t[0]:
         if len(_INCREASING) > 64:

@@ -85,6 +85,23 @@ int mgb_host_time_steps(const double *t, int64_t n, double *dt, double *lo, doub
     return MGB_OK;
 }
 
+// out[i] = i * step + start, i < n (two roundings per element, as NumPy's linspace computes arange(n) * step + start:
+// a multiplication pass and an addition pass per block, so that no compiler contracts them into one fused operation)
+int mgb_host_affine_ramp(double start, double step, int64_t n, double *out, int32_t threads) {
+    if (out == nullptr || n < 0) return MGB_EINVAL;
+    split_range(n, threads, [&](int, int64_t a, int64_t b) {
+        double *__restrict__ o = out;
+        for (int64_t i0 = a; i0 < b; i0 += 2048) {
+            const int64_t i1 = std::min<int64_t>(b, i0 + 2048);
+            for (int64_t i = i0; i < i1; ++i) o[i] = (double)i * step;
+            volatile double s = start;            // the addition is a separate, visible operation
+            const double sv = s;
+            for (int64_t i = i0; i < i1; ++i) o[i] = o[i] + sv;
+        }
+    });
+    return MGB_OK;
+}
+
 // out[i][k] = src[k][i] (* scale[i]), i < n, k < q: the time factors of a separable right-hand side, [q][n] as they were
 // evaluated -> [n][q] as the kernels read them (core/rhs_tables.py RhsSplit.coefficients)
 int mgb_host_scale_rows(const double *src, int64_t ld_src, int32_t q, int64_t n, const double *scale, double *out,

@@ -188,12 +188,17 @@ class Heat2D(DeviceApplication):
         init = np.array(np.broadcast_to(self.init_cond(self.x_2d, self.y_2d), (nx, ny)), dtype=float)   # heat_2d.py:243
         self._apply_bc(init)
         self.vector_t_start.set_values(init)
-        if self.theta == 0 and np.any(self.boundary_values()):
+        # the Dirichlet data as the four boundary lines (what _apply_bc writes): a key of 4 (nx + ny) doubles instead of the
+        # nx x ny array, whose bytes took a millisecond per level to copy and to hash
+        edges = tuple(np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=float), shape))
+                      for v, shape in ((self.bc_left(self.x), (nx,)), (self.bc_right(self.x), (nx,)),
+                                       (self.bc_bottom(self.y), (ny,)), (self.bc_top(self.y), (ny,))))
+        if self.theta == 0 and any(np.any(e) for e in edges):
             # the reference's forward-Euler branch ADDS the Dirichlet values to the boundary nodes in every step
             # (heat_2d.py:346-353), so they grow with the step count: not reproduced on the device
             raise Exception("pymgrit_b200.Heat2D: method 'FE' is available for homogeneous Dirichlet data only")
         self._family_key = (nx, ny, float(x_start), float(x_end), float(y_start), float(y_end), float(a), id(rhs),
-                            self.boundary_values().tobytes())
+                            b''.join(e.tobytes() for e in edges))
         self.ndof = self.family().pitch
 
     def _apply_bc(self, b):                                  # heat_2d.py:244-247, 315-319: same order of writes

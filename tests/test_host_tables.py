@@ -263,3 +263,13 @@ def test_native_host_passes_are_bit_identical_to_numpy():
     t = np.linspace(0, 2, dl._PAR_MIN + 77) ** 1.1
     dt, lo, hi = dl.time_steps(t)
     assert np.array_equal(dt[1:], t[1:] - t[:-1]) and dt[0] == 0.0 and lo == dt[1:].min() and hi == dt[1:].max()
+
+
+@pytest.mark.parametrize('a,b,n', [(0, 2, 2 ** 20 + 1), (0, 5, 2 ** 17 + 3), (-1.3, 7.77, 300001), (0.1, 0.1000001, 2 ** 18),
+                                   (3, 1, 2 ** 17 + 1), (0, 2, 1000), (0.0, 0.0, 2 ** 17)])
+def test_long_time_grids_are_numpy_linspace_bit_for_bit(a, b, n):
+    """core/application.py linspace(): long grids are filled by native threads (mgb_host_affine_ramp: i * step + start with
+    the product and the sum rounded separately); the reference's grids are np.linspace (core/application.py:60), and every
+    dt-dependent constant of the engine is keyed on the exact differences of the grid."""
+    from pymgrit_b200.core.application import linspace
+    assert np.array_equal(linspace(a, b, n), np.linspace(a, b, n))
