@@ -23,5 +23,6 @@ from pymgrit_b200.dahlquist.dahlquist import Dahlquist, VectorDahlquist
 from pymgrit_b200.brusselator.brusselator import Brusselator, VectorBrusselator
 from pymgrit_b200.allen_cahn.allen_cahn import AllenCahn, VectorAllenCahn2D
 from pymgrit_b200.core.batched import BatchedApplication
+from pymgrit_b200.core.split import split_communicator
 
 __version__ = '0.1.0'

@@ -62,6 +62,15 @@ def worker(rank, size, port, out_dir):
     # no CUDA tensors over gloo: the peer-memory mailbox is not set up, NCCL/gloo send-recv stays (checked above)
     comm.setup_peer_exchange(solver)
     assert comm.mailbox is None
+    # split_communicator (reference core/split.py): space groups of consecutive ranks, time groups across them
+    from pymgrit_b200.core.split import split_communicator
+    cx, ct = split_communicator(None, 1)
+    assert dist.get_world_size(cx) == 1 and dist.get_world_size(ct) == size and dist.get_rank(ct) == rank
+    assert as_time_comm(ct).Get_size() == size
+    if size % 2 == 0:
+        cx, ct = split_communicator(None, 2)
+        assert dist.get_world_size(cx) == 2 and dist.get_rank(cx) == rank % 2
+        assert dist.get_world_size(ct) == size // 2 and dist.get_rank(ct) == rank // 2
     gathered = comm.allgather(part.window)
     np.save(os.path.join(out_dir, f'windows_{rank}.npy'), np.array(gathered))
     comm.barrier()
