@@ -26,7 +26,11 @@ void split_range(int64_t n, int threads, F fn) {
     const int64_t per = (n + nt - 1) / nt;
     for (int k = 1; k < nt; ++k) {
         const int64_t a = std::min(n, k * per), b = std::min(n, a + per);
-        pool.emplace_back([=] { fn(k, a, b); });
+        try {
+            pool.emplace_back([=] { fn(k, a, b); });
+        } catch (...) {   // no thread to be had (resource limits): the piece runs here -- nothing may cross the C ABI
+            fn(k, a, b);
+        }
     }
     fn(0, (int64_t)0, std::min(n, per));
     for (auto &th : pool) th.join();
