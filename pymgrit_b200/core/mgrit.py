@@ -518,10 +518,15 @@ class Mgrit:
         # correction + the F-relaxation of mgrit.py:287, one launch; on level 0 only the last F-point of every interval
         # is stored while the solver iterates (_materialise_f_points)
         lazy = lvl == 0 and self._lazy_f and self.lvl_max > 1 and self._batched is None
-        self.error_correction(lvl=lvl, f_relax=True, last_only=lazy)
+        # F-cycle: a V-cycle from this level follows at once.  Its down-sweep reads only the last F-point of every interval
+        # and its own correction + F-relaxation rewrites all of them, so the F-points stored here would be dead: same values
+        # with last_only (on cfg 3 that is 6 of the 17 rows a level-1 interval moves).
+        again = lvl != 0 and cycle_type == 'F'
+        dead_f = again and self._lazy_f and self._batched is None and self._xfer[lvl] is None
+        self.error_correction(lvl=lvl, f_relax=True, last_only=lazy or dead_f)
         if lazy:
             self._f_stale = True
-        if lvl != 0 and cycle_type == 'F':
+        if again:
             self.iteration(lvl=lvl, cycle_type='V', iteration=iteration, first_f=False)
 
     def f_relax(self, lvl: int, last_only: bool = False) -> None:
@@ -750,15 +755,12 @@ class Mgrit:
                 # If the two residuals known so far say that the iteration just queued will meet the tolerance (linear
                 # convergence), wait for its residual instead of queueing one more cycle of sweeps that would return at
                 # once: same result, a cycle's worth of launches less.  A wrong guess costs one host round trip.
-                if last_read >= 2 and self.conv[last_read - 1] > 0:
-                    rate = self.conv[last_read] / self.conv[last_read - 1]
-                    steps = queued - last_read
-                    if 0 < rate < 1 and self.conv[last_read] * rate ** steps < self.tol:
-                        while last_read < queued and not done:
-                            last_read += 1
-                            done = read(last_read)
-                        if done:
-                            break
+                if predicts_convergence(self.conv, last_read, queued, self.tol):
+                    while last_read < queued and not done:
+                        last_read += 1
+                        done = read(last_read)
+                    if done:
+                        break
             while not done and last_read < queued:
                 last_read += 1
                 done = read(last_read)
@@ -848,6 +850,15 @@ class Mgrit:
 
     def split_points(self, length: int, size: int, rank: int):
         return partition.split_points(length, size, rank)
+
+
+def predicts_convergence(conv, last_read: int, queued: int, tol: float) -> bool:
+    """True if the residuals read so far (conv[1 .. last_read]) say that the cycle queued last (number `queued`) will meet
+    the tolerance, assuming linear convergence at the rate of the last two of them."""
+    if last_read < 2 or queued <= last_read or not conv[last_read - 1] > 0:
+        return False
+    rate = conv[last_read] / conv[last_read - 1]
+    return bool(0 < rate < 1 and conv[last_read] * rate ** (queued - last_read) < tol)
 
 
 def _lib_torch():

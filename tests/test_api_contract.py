@@ -200,3 +200,17 @@ def test_examples_reach_the_device_boundary(name):
         assert 'CUDA' in str(err.value), str(err.value)
     finally:
         sys.path.remove(here)
+
+
+def test_predicted_stop_of_the_queued_ahead_loop():
+    """core/mgrit.py predicts_convergence: with two residuals known, the host waits for the residual of the cycle it has
+    just queued instead of queueing another one, if linear convergence at the observed rate meets the tolerance."""
+    from pymgrit_b200.core.mgrit import predicts_convergence
+    conv = np.array([0.0, 3.9e-7, 3.5e-9, 0.0, 0.0])            # cfg 5: the third cycle is queued, two residuals are read
+    assert predicts_convergence(conv, 2, 3, 1e-10)               # 3.5e-9 * 0.009 = 3.1e-11 < 1e-10
+    assert not predicts_convergence(conv, 2, 3, 1e-12)
+    assert not predicts_convergence(conv, 1, 2, 1e-10)           # one residual: no rate yet
+    assert not predicts_convergence(conv, 2, 2, 1e-10)           # nothing queued beyond what was read
+    assert not predicts_convergence(np.array([0.0, 1e-3, 2e-3, 0.0]), 2, 3, 1.0e-2)   # diverging: no prediction
+    assert not predicts_convergence(np.array([0.0, 0.0, 1e-3, 0.0]), 2, 3, 1.0)       # no previous residual
+    assert predicts_convergence(np.array([0.0, 1e-2, 1e-3, 0.0, 0.0]), 2, 4, 2e-5)    # two cycles queued ahead
