@@ -162,6 +162,12 @@ CASES = {
     # BASELINE.json configs[3] at reduced size
     'advection_cfg4_small': dict(app='advection1d', app_kw=dict(c=1, x_start=-1, x_end=1, nx=257), t=(0, 2, 1025),
                                  grids=_simple(5, 2), solver=dict(tol=1e-10, cf_iter=1, nested_iteration=True)),
+    # two levels with a long coarsest level (513 points): the coarsest solve runs in Fourier space (csrc/fourier.cu); nx - 1
+    # = 256 unknowns, and 301 - 1 = 300 = 2^2 3 5^2 (a length that is not a power of two: Bluestein's transform)
+    'advection_two_level_fourier': dict(app='advection1d', app_kw=dict(c=1, x_start=-1, x_end=1, nx=257), t=(0, 2, 1025),
+                                        grids=_simple(2, 2), solver=dict(tol=1e-10, cf_iter=1, nested_iteration=True)),
+    'advection_nx301_fourier': dict(app='advection1d', app_kw=dict(c=1, x_start=-1, x_end=1, nx=301), t=(0, 1, 513),
+                                    grids=_simple(3, 2), solver=dict(tol=1e-9, cf_iter=1, cycle_type='F')),
     'advection_nx4096_short': dict(app='advection1d', app_kw=dict(c=1, x_start=-1, x_end=1, nx=4096), t=(0, 2 / 256, 257),
                                    grids=_simple(3, 4), solver=dict(tol=1e-10)),
     # examples/example_heat_2d.py -> tests/mpi/results/heat_2d
