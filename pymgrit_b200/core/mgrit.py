@@ -176,6 +176,8 @@ class Mgrit:
 
         self.launches = 0
         self._f_stale = False
+        self._sweep_counts = {}                # level-0 sweeps launched by the last solve(), by name (time_level0_sweeps)
+        self._l0_store_hook = None             # set by _solve_queued_ahead: is the cycle being queued expected to be the last?
         self._f_uninit = False
         import os as _os
         self._lazy_f = _os.environ.get('MGB_LAZY_F', '1') != '0'
@@ -386,6 +388,10 @@ class Mgrit:
         self.launches += 1                      # every C-ABI sweep below is one kernel launch of this library
         return _lib.current_stream_ptr()
 
+    def _count(self, lvl, name):
+        if lvl == 0:
+            self._sweep_counts[name] = self._sweep_counts.get(name, 0) + 1
+
     def restart(self) -> None:
         """Forget the current iterate and redo the setup sweeps (initial guess, nested iteration) with the level tables
         that are already in HBM.  Not in the reference (which rebuilds everything); used by bench.py."""
@@ -422,6 +428,7 @@ class Mgrit:
         lv = self._lv[0]
         if self.lvl_max < 2 or lv.cpts is None:
             return []
+        counts = dict(self._sweep_counts)      # what the last solve() launched on level 0 (the calls below count too)
         k0 = len(lv.cpts) - 1
         m = self.m[0]
         row = 8.0 * lv.n
@@ -477,6 +484,11 @@ class Mgrit:
                    'algorithmic_bytes': nbytes, 'ms': ms, 'gbs': nbytes / (ms * 1e-3) / 1e9,
                    'launches_per_iteration': per_iter, 'launches_per_solve': per_solve,
                    'share_ms': ms * (per_iter * its + per_solve)}
+            if counts:
+                # counted during the last solve: the cycle predicted to be the last stores every F-point in its correction
+                # and the final F-relaxation does not run (_solve_queued_ahead), which the static columns do not know
+                ent['launches_last_solve'] = counts.get(name, 0)
+                ent['share_ms'] = ms * counts.get(name, 0)
             t_hbm = nbytes / (hbm_gbs * 1e9) * 1e3 if hbm_gbs else None
             t_fp = None
             if per_elem is not None:
@@ -523,9 +535,13 @@ class Mgrit:
         # with last_only (on cfg 3 that is 6 of the 17 rows a level-1 interval moves).
         again = lvl != 0 and cycle_type == 'F'
         dead_f = again and self._lazy_f and self._batched is None and self._xfer[lvl] is None
+        stale = lazy
+        if lazy and self._l0_store_hook is not None and self._l0_store_hook():
+            lazy = False                 # expected to be the last cycle: its correction stores every F-point (1.55 instead of
+                                         # 0.22 ms on cfg 5) and the final F-relaxation (1.47 ms + a host round trip) is not needed
         self.error_correction(lvl=lvl, f_relax=True, last_only=lazy or dead_f)
-        if lazy:
-            self._f_stale = True
+        if stale:
+            self._f_stale = lazy
         if again:
             self.iteration(lvl=lvl, cycle_type='V', iteration=iteration, first_f=False)
 
@@ -535,12 +551,14 @@ class Mgrit:
         if self._batched is not None:
             return self._batched.f_relax(lvl, last_only)
         flags = _lib.F_RELAX_LAST_ONLY if last_only else 0
+        self._count(lvl, 'f_relax(last point only)' if last_only else 'f_relax')
         _lib.check(_lib.lib().mgb_f_relax(self._lv[lvl].ref, flags, self._stream()), 'f_relax')
 
     def c_relax(self, lvl: int) -> None:
         """C-relaxation (mgrit.py:335-370)."""
         if self._batched is not None:
             return self._batched.c_relax(lvl)
+        self._count(lvl, 'c_relax')
         _lib.check(_lib.lib().mgb_c_relax(self._lv[lvl].ref, float(self.weight_c), self._stream()), 'c_relax')
         self._exchange_ghost(lvl)
 
@@ -564,6 +582,7 @@ class Mgrit:
             return
         if coarse.npts > 0 and fine.npts > 0 and len(fine.cpts) < 2:
             coarse.u[0].copy_(fine.u[0])             # no interval: the kernel (which injects point 0 too) has no work
+        self._count(lvl, 'fas_residual')
         _lib.check(_lib.lib().mgb_fas_residual(fine.ref, coarse.ref, self._stream()), 'fas_residual')
 
     def down_sweep(self, lvl: int) -> None:
@@ -577,6 +596,7 @@ class Mgrit:
             self._exchange_ghost(lvl)
         if coarse.npts > 0 and fine.npts > 0 and len(fine.cpts) < 2:
             coarse.u[0].copy_(fine.u[0])             # no interval: the kernel (which injects point 0 too) has no work
+        self._count(lvl, 'down_sweep(c_relax+f_relax+fas_residual)')
         _lib.check(_lib.lib().mgb_down_sweep(fine.ref, coarse.ref, self._stream()), 'down_sweep')
 
     def error_correction(self, lvl: int, f_relax: bool = False, last_only: bool = False) -> None:
@@ -595,6 +615,8 @@ class Mgrit:
             return
         flags = ((_lib.CORRECT_F_RELAX if f_relax else 0) | (_lib.CORRECT_GHOST if self.comm_time_rank > 0 else 0) |
                  (_lib.CORRECT_LAST_ONLY if f_relax and last_only else 0))
+        if f_relax:
+            self._count(lvl, 'error_correction+f_relax' + ('(last point only)' if last_only else ''))
         _lib.check(_lib.lib().mgb_error_correction(self._lv[lvl].ref, self._lv[lvl + 1].ref, flags, self._stream()),
                    'error_correction')
         # no exchange: every rank corrects its ghost copy itself (MGB_CORRECT_GHOST)
@@ -645,6 +667,7 @@ class Mgrit:
         if self._batched is not None:
             self._batched.residual_norms(self._sq)
             return self._sq
+        self._count(0, 'residual_norms')
         _lib.check(_lib.lib().mgb_residual_norms(self._lv[0].ref, self._sq.data_ptr(), self._stream()), 'residual_norms')
         return self._sq
 
@@ -737,34 +760,55 @@ class Mgrit:
                 self.solve_iter = k
                 return self.conv[k] < self.tol
 
-            done = False
-            queued = last_read = 0
+            st = {'done': False, 'last_read': 0, 'iteration': 0}
+
+            def read_up_to(k):
+                while st['last_read'] < k and not st['done']:
+                    st['last_read'] += 1
+                    st['done'] = read(st['last_read'])
+
+            def expect_last_cycle():
+                """Called by iteration() before the level-0 correction of the cycle being queued (number k, 0-based).  The
+                residual of cycle k - 1 arrives while the device works on what is already queued of cycle k (down-sweep and
+                coarse levels): wait for it, and say whether linear convergence at the rate of the last two residuals
+                makes cycle k the last one."""
+                k = st['iteration']
+                if k < 2 or st['done']:
+                    return False
+                read_up_to(k)
+                return (not st['done']) and predicts_convergence(self.conv, k, k + 1, self.tol)
+
+            lv0 = self._lv[0]
+            big = lv0.npts * lv0.pitch * 8 >= (1 << 30)      # short cycles: the wait would leave the device without work
+            import os
+            self._l0_store_hook = expect_last_cycle if (big and os.environ.get('MGB_PREDICT_LAST', '1') != '0') else None
+            queued = 0
             for iteration in range(self.iter_max):
+                st['iteration'] = iteration
                 self.iteration(lvl=0, cycle_type=self.cycle_type, iteration=iteration, first_f=True)
+                if st['done']:
+                    break                            # the hook saw that the previous cycle met the tolerance: this one is void
                 self._queue_convergence(iteration + 1)
                 ev = torch.cuda.Event()
                 self._hist_host[iteration + 1:iteration + 2].copy_(self._hist_dev[iteration + 1:iteration + 2], non_blocking=True)
                 ev.record()
                 events[iteration + 1] = ev
                 queued = iteration + 1
-                if iteration >= 1 and last_read < iteration:
-                    last_read = iteration
-                    if read(iteration):
-                        done = True                  # iteration `iteration + 1` is queued but will not run
-                        break
+                if iteration >= 1:
+                    read_up_to(iteration)
+                    if st['done']:
+                        break                        # iteration `iteration + 1` is queued but will not run
                 # If the two residuals known so far say that the iteration just queued will meet the tolerance (linear
                 # convergence), wait for its residual instead of queueing one more cycle of sweeps that would return at
                 # once: same result, a cycle's worth of launches less.  A wrong guess costs one host round trip.
-                if predicts_convergence(self.conv, last_read, queued, self.tol):
-                    while last_read < queued and not done:
-                        last_read += 1
-                        done = read(last_read)
-                    if done:
+                if predicts_convergence(self.conv, st['last_read'], queued, self.tol):
+                    read_up_to(queued)
+                    if st['done']:
                         break
-            while not done and last_read < queued:
-                last_read += 1
-                done = read(last_read)
+            if not st['done']:
+                read_up_to(queued)
         finally:
+            self._l0_store_hook = None
             _lib.check(lib.mgb_write_flag(flag_ptr, 0, self._stream()), 'write_flag')
             _lib.check(lib.mgb_set_stop_flag(None), 'set_stop_flag')
 
@@ -793,6 +837,7 @@ class Mgrit:
         """Iterate until the stopping criterion is met (mgrit.py:590-646)."""
         torch = _lib_torch()
         self.log_info("Start solve")
+        self._sweep_counts = {}
         runtime_solve_start = time.time()
         if self._can_queue_ahead():
             self._solve_queued_ahead()
