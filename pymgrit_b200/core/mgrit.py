@@ -779,7 +779,9 @@ class Mgrit:
                 return (not st['done']) and predicts_convergence(self.conv, k, k + 1, self.tol)
 
             lv0 = self._lv[0]
-            big = lv0.npts * lv0.pitch * 8 >= (1 << 30)      # short cycles: the wait would leave the device without work
+            # short cycles: the wait would leave the device without work.  Decided from the GLOBAL size of level 0, so that
+            # every time rank takes the same path (a rank that leaves the loop inside a cycle queues one reduction less)
+            big = len(self.global_t[0]) * lv0.pitch * 8 >= (1 << 30) * self.comm_time_size
             import os
             self._l0_store_hook = expect_last_cycle if (big and os.environ.get('MGB_PREDICT_LAST', '1') != '0') else None
             queued = 0
